@@ -1,0 +1,416 @@
+// TF32 tensor-core GEMM for sm_100a: TMA -> 128B-swizzled shared-memory ring ->
+// tcgen05.mma (accumulators in TMEM) -> tcgen05.ld epilogue.
+//
+//   D[m,n] = epilogue( sum_k A[m,k] * B[n,k] )          A: M x K, B: N x K (logical)
+//
+// Each operand is an fp32 row-major matrix in HBM and is either
+//   K-major  : stored [MN rows][K cols]   (reduction index contiguous), or
+//   MN-major : stored [K rows][MN cols]   (M / N index contiguous).
+// All four combinations occur on the GANMF path:
+// forward GEMMs read weights MN-major, the backward ones read the same weights
+// K-major, weight-gradient GEMMs read both activations MN-major.
+//
+// One CTA computes one 128 x BN output tile (optionally one K-split of it).
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2..5  : epilogue, one TMEM lane quarter each (warp_id % 4)
+// Stage = 32 fp32 of K (one 128-byte swizzle row), i.e. 4 UMMA (K=8) per stage.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "ptx.cuh"
+
+namespace ganmf {
+
+constexpr int TC_BM = 128;         // output tile rows (UMMA M)
+constexpr int TC_BK = 32;          // fp32 elements of K per stage (128 bytes)
+constexpr int TC_UMMA_K = 8;       // tf32: 32 bytes of K per instruction
+constexpr int TC_THREADS = 192;
+
+// Fused epilogue applied to every accumulator element (m, n):
+//   v = alpha * rs(m) * acc + bias[n] + beta1 * C1[m,n] + beta2 * C2[m,n]
+//   rs(m) = row_scale2 ? row_scale2[m >= row_split] : 1      (device-side scalars:
+//           the hinge-gate coefficients are only known on the device)
+//   out[m,n] = round_out ? rna_tf32(v) : v
+//   sumsq2[m >= row_split] += v*v                            (energy loss, fp64)
+struct Epilogue {
+  float* out = nullptr;
+  int ldo = 0;
+  float alpha = 1.f;
+  const float* row_scale2 = nullptr;
+  int row_split = 0x7fffffff;
+  const float* bias = nullptr;
+  const float* c1 = nullptr;
+  int ldc1 = 0;
+  float beta1 = 0.f;
+  const float* c2 = nullptr;
+  int ldc2 = 0;
+  float beta2 = 0.f;
+  int round_out = 0;
+  double* sumsq2 = nullptr;
+};
+
+struct TcGemmArgs {
+  int M, N, K;
+  int a_mn, b_mn;          // 1 = MN-major operand
+  int kb_per_split;        // k-blocks (of TC_BK) per blockIdx.z
+  float* ws;               // split-K partials [splits][M][ws_ld] (splits > 1)
+  int ws_ld;
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo;   // smem descriptor strides, bytes >> 4
+  uint32_t a_kstep, b_kstep;             // start-address advance per UMMA_K, bytes >> 4
+  uint32_t idesc;
+  Epilogue ep;
+};
+
+__device__ __forceinline__ float apply_epilogue(const Epilogue& ep, float acc, int m, int n,
+                                                float rs) {
+  float v = ep.alpha * rs * acc;
+  if (ep.bias) v += __ldg(ep.bias + n);
+  if (ep.c1) v += ep.beta1 * __ldg(ep.c1 + (size_t)m * ep.ldc1 + n);
+  if (ep.c2) v += ep.beta2 * __ldg(ep.c2 + (size_t)m * ep.ldc2 + n);
+  if (ep.round_out) v = ptx::round_tf32(v);
+  return v;
+}
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  // cute::UMMA::SmemDescriptor layout (sm_100): start[0,14) lbo[16,30) sbo[32,46)
+  // version=1 [46,48) layout_type[61,64) with SWIZZLE_128B = 2.
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(lbo & 0x3FFF) << 16;
+  d |= (uint64_t)(sbo & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;
+  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + align slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcGemmArgs args) {
+  using S = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM;
+  const int n0 = blockIdx.x * BN;
+  const int split = blockIdx.z;
+  const int total_kb = (args.K + TC_BK - 1) / TC_BK;
+  const int kb_begin = split * args.kb_per_split;
+  int kb_end = kb_begin + args.kb_per_split;
+  if (kb_end > total_kb) kb_end = total_kb;
+  const int nkb = kb_end - kb_begin;   // host guarantees >= 1 for every launched split
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::STAGE_BYTES;
+        uint8_t* sb = sa + S::A_BYTES;
+        const int k0 = (kb_begin + i) * TC_BK;
+        ptx::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        if (!args.a_mn) {
+          ptx::tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);          // box {32 k, 128 m}
+        } else {
+#pragma unroll
+          for (int j = 0; j < TC_BM / 32; ++j)                         // box {32 m, 32 k}
+            ptx::tma_load_2d(sa + j * (TC_BK * 128), &map_a, &full_bar[s], m0 + 32 * j, k0);
+        }
+        if (!args.b_mn) {
+          ptx::tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);          // box {32 k, BN n}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            ptx::tma_load_2d(sb + j * (TC_BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t sb = sa + S::A_BYTES;
+        const uint64_t da = make_smem_desc(sa, args.a_lbo, args.a_sbo);
+        const uint64_t db = make_smem_desc(sb, args.b_lbo, args.b_sbo);
+#pragma unroll
+        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+          ptx::mma_tf32_ss(tmem_base, da + (uint64_t)(k * args.a_kstep),
+                           db + (uint64_t)(k * args.b_kstep), args.idesc, (i | k) ? 1u : 0u);
+        }
+        ptx::mma_commit(&empty_bar[s]);      // frees the smem stage when those MMAs retire
+      }
+      ptx::mma_commit(tmem_full_bar);        // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < args.M;
+    const Epilogue& ep = args.ep;
+    const bool partial = gridDim.z > 1;
+    float rs = 1.f;
+    if (!partial && ep.row_scale2 && row_ok) rs = __ldg(ep.row_scale2 + (m >= ep.row_split ? 1 : 0));
+    float sq = 0.f;
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      ptx::tmem_ld_wait();
+      const int nb = n0 + c;
+      if (!row_ok || nb >= args.N) continue;
+      if (partial) {
+        float* dst = args.ws + ((size_t)split * args.M + m) * args.ws_ld + nb;
+        if (nb + 32 <= args.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) =
+                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        } else {
+          for (int j = 0; j < 32 && nb + j < args.N; ++j) dst[j] = __uint_as_float(r[j]);
+        }
+      } else {
+        float* dst = ep.out + (size_t)m * ep.ldo + nb;
+        if (nb + 32 <= args.N && (ep.ldo & 3) == 0 &&
+            (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v;
+            v.x = apply_epilogue(ep, __uint_as_float(r[j]), m, nb + j, rs);
+            v.y = apply_epilogue(ep, __uint_as_float(r[j + 1]), m, nb + j + 1, rs);
+            v.z = apply_epilogue(ep, __uint_as_float(r[j + 2]), m, nb + j + 2, rs);
+            v.w = apply_epilogue(ep, __uint_as_float(r[j + 3]), m, nb + j + 3, rs);
+            sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            *reinterpret_cast<float4*>(dst + j) = v;
+          }
+        } else {
+          for (int j = 0; j < 32 && nb + j < args.N; ++j) {
+            float v = apply_epilogue(ep, __uint_as_float(r[j]), m, nb + j, rs);
+            sq += v * v;
+            dst[j] = v;
+          }
+        }
+      }
+    }
+    if (!partial && ep.sumsq2) {
+      // rows of one warp may straddle row_split: reduce the two slots separately
+      float s0 = (row_ok && m < ep.row_split) ? sq : 0.f;
+      float s1 = (row_ok && m >= ep.row_split) ? sq : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      }
+      if (lane == 0) {
+        if (s0 != 0.f) atomicAdd(ep.sumsq2, (double)s0);
+        if (s1 != 0.f) atomicAdd(ep.sumsq2 + 1, (double)s1);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// Sum split-K partials in a fixed order (deterministic) and apply the epilogue.
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N,
+                                     int ws_ld, Epilogue ep) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  float v = 0.f;
+  const bool ok = n < N;
+  if (ok) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[((size_t)s * M + m) * ws_ld + n];
+    float rs = ep.row_scale2 ? __ldg(ep.row_scale2 + (m >= ep.row_split ? 1 : 0)) : 1.f;
+    v = apply_epilogue(ep, acc, m, n, rs);
+    ep.out[(size_t)m * ep.ldo + n] = v;
+  }
+  if (ep.sumsq2) {
+    float sq = ok ? v * v : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0 && sq != 0.f)
+      atomicAdd(ep.sumsq2 + (m >= ep.row_split ? 1 : 0), (double)sq);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// fp32 row-major matrix [rows][cols] with leading dimension ld (elements);
+// box = {box_cols (contiguous), box_rows}; 128B swizzle; OOB reads give zeros.
+inline int make_tmap_2d(CUtensorMap* map, const float* ptr, int rows, int cols, int ld,
+                        int box_cols, int box_rows, int tmap_dtype) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return 1;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, (CUtensorMapDataType)tmap_dtype, 2, const_cast<float*>(ptr), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+struct TcGemmCall {
+  const float* A; int lda; int a_mn;
+  const float* B; int ldb; int b_mn;
+  int M, N, K;
+  Epilogue ep;
+  int splits = 1;          // > 1 needs ws
+  float* ws = nullptr;     // >= splits * M * roundup(N,4) floats
+  int bn = 128;            // 128 or 256
+  int tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+};
+
+inline uint32_t make_idesc_tf32(int bn, int a_mn, int b_mn) {
+  // cute::UMMA::InstrDescriptor: c_format[4,6)=1 (F32) a_format[7,10)=2 (TF32)
+  // b_format[10,13)=2 a_major bit15 b_major bit16 n_dim[17,23)=N>>3 m_dim[24,29)=M>>4
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= 2u << 7;
+  d |= 2u << 10;
+  d |= (uint32_t)(a_mn ? 1 : 0) << 15;
+  d |= (uint32_t)(b_mn ? 1 : 0) << 16;
+  d |= (uint32_t)(bn >> 3) << 17;
+  d |= (uint32_t)(TC_BM >> 4) << 24;
+  return d;
+}
+
+template <int BN, int STAGES>
+inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const CUtensorMap& ma,
+                                    const CUtensorMap& mb, int splits, cudaStream_t stream) {
+  using S = TcSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((c.N + BN - 1) / BN, (c.M + TC_BM - 1) / TC_BM, splits);
+  tc_gemm_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, args);
+  return cudaGetLastError();
+}
+
+// Returns cudaSuccess or an error; never falls back to another implementation.
+inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
+  if (c.M <= 0 || c.N <= 0 || c.K <= 0) return cudaErrorInvalidValue;
+  if ((c.lda & 3) || (c.ldb & 3)) return cudaErrorInvalidValue;   // TMA: 16-byte row pitch
+  if ((reinterpret_cast<uintptr_t>(c.A) & 15) || (reinterpret_cast<uintptr_t>(c.B) & 15))
+    return cudaErrorInvalidValue;
+  const int bn = c.bn == 256 ? 256 : 128;
+  CUtensorMap ma, mb;
+  int rc;
+  if (!c.a_mn) rc = make_tmap_2d(&ma, c.A, c.M, c.K, c.lda, TC_BK, TC_BM, c.tmap_dtype);
+  else         rc = make_tmap_2d(&ma, c.A, c.K, c.M, c.lda, 32, TC_BK, c.tmap_dtype);
+  if (rc) return cudaErrorUnknown;
+  if (!c.b_mn) rc = make_tmap_2d(&mb, c.B, c.N, c.K, c.ldb, TC_BK, bn, c.tmap_dtype);
+  else         rc = make_tmap_2d(&mb, c.B, c.K, c.N, c.ldb, 32, TC_BK, c.tmap_dtype);
+  if (rc) return cudaErrorUnknown;
+
+  TcGemmArgs args;
+  args.M = c.M; args.N = c.N; args.K = c.K;
+  args.a_mn = c.a_mn; args.b_mn = c.b_mn;
+  const int total_kb = (c.K + TC_BK - 1) / TC_BK;
+  int splits = c.splits < 1 ? 1 : c.splits;
+  if (splits > total_kb) splits = total_kb;
+  int kbps = (total_kb + splits - 1) / splits;
+  splits = (total_kb + kbps - 1) / kbps;          // no empty split is ever launched
+  if (splits > 1 && !c.ws) return cudaErrorInvalidValue;
+  args.kb_per_split = kbps;
+  args.ws = c.ws;
+  args.ws_ld = (c.N + 3) & ~3;
+  // shared-memory matrix descriptors (bytes >> 4), 128B swizzle:
+  //  K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (=1).
+  //  MN-major: 32-element (128 B) chunks of MN, chunk stride LBO = TC_BK*128 B,
+  //            8-k groups 1024 B apart (SBO).
+  args.a_lbo = c.a_mn ? (TC_BK * 128) >> 4 : 1;
+  args.a_sbo = 1024 >> 4;
+  args.b_lbo = c.b_mn ? (TC_BK * 128) >> 4 : 1;
+  args.b_sbo = 1024 >> 4;
+  args.a_kstep = c.a_mn ? (1024 >> 4) : (TC_UMMA_K * 4) >> 4;
+  args.b_kstep = c.b_mn ? (1024 >> 4) : (TC_UMMA_K * 4) >> 4;
+  args.idesc = make_idesc_tf32(bn, c.a_mn, c.b_mn);
+  args.ep = c.ep;
+
+  cudaError_t e;
+  if (bn == 256) e = tc_gemm_launch_t<256, 4>(c, args, ma, mb, splits, stream);
+  else           e = tc_gemm_launch_t<128, 6>(c, args, ma, mb, splits, stream);
+  if (e != cudaSuccess) return e;
+  if (splits > 1) {
+    dim3 rb(256), rg((c.N + 255) / 256, c.M);
+    splitk_reduce_kernel<<<rg, rb, 0, stream>>>(c.ws, splits, c.M, c.N, args.ws_ld, c.ep);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace ganmf

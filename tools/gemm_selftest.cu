@@ -1,0 +1,161 @@
+// Standalone bring-up test for the tcgen05 TF32 GEMM (ganmf_b200/csrc/tc_gemm.cuh).
+// One configuration per process so that a trapped kernel cannot poison later cases:
+//   gemm_selftest M N K a_mn b_mn bn splits epi [probe] [tmap_dtype]
+// Inputs are multiples of 1/4 in [-1,1] (exact in tf32, sums exact in fp32), so the
+// plain GEMM must match the fp64 CPU result bit for bit.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include "../ganmf_b200/csrc/tc_gemm.cuh"
+
+#define CK(x)                                                                       \
+  do {                                                                              \
+    cudaError_t e_ = (x);                                                           \
+    if (e_ != cudaSuccess) {                                                        \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return 2;                                                                     \
+    }                                                                               \
+  } while (0)
+
+static uint32_t rng_state = 12345u;
+static inline uint32_t rnd() {
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return rng_state >> 8;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 9) {
+    printf("usage: %s M N K a_mn b_mn bn splits epi [probe] [tmap_dtype]\n", argv[0]);
+    return 1;
+  }
+  const int M = atoi(argv[1]), N = atoi(argv[2]), K = atoi(argv[3]);
+  const int a_mn = atoi(argv[4]), b_mn = atoi(argv[5]), bn = atoi(argv[6]);
+  const int splits = atoi(argv[7]), epi = atoi(argv[8]);
+  const int probe = argc > 9 ? atoi(argv[9]) : 0;
+  const int tmap_dtype = argc > 10 ? atoi(argv[10]) : (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  auto rup = [](int x, int a) { return (x + a - 1) / a * a; };
+
+  // storage: K-major [MN][K], MN-major [K][MN]
+  const int a_rows = a_mn ? K : M, a_cols = a_mn ? M : K, lda = rup(a_cols, 32);
+  const int b_rows = b_mn ? K : N, b_cols = b_mn ? N : K, ldb = rup(b_cols, 32);
+  const int ldo = rup(N, 32);
+  std::vector<float> hA((size_t)a_rows * lda, 0.f), hB((size_t)b_rows * ldb, 0.f);
+  std::vector<float> hC1((size_t)M * ldo, 0.f), hC2((size_t)M * ldo, 0.f), hBias(ldo, 0.f);
+  auto val = [&]() {
+    if (probe) return 1.0f + ldexpf(1.f, -11) + ldexpf(1.f, -12);
+    return (float)((int)(rnd() % 9) - 4) * 0.25f;
+  };
+  for (int r = 0; r < a_rows; ++r)
+    for (int c = 0; c < a_cols; ++c) hA[(size_t)r * lda + c] = val();
+  for (int r = 0; r < b_rows; ++r)
+    for (int c = 0; c < b_cols; ++c) hB[(size_t)r * ldb + c] = probe ? 1.0f : val();
+  // poison the padding columns: TMA bounds (true extents) must keep them out
+  for (int r = 0; r < a_rows; ++r)
+    for (int c = a_cols; c < lda; ++c) hA[(size_t)r * lda + c] = 1000.f;
+  for (int r = 0; r < b_rows; ++r)
+    for (int c = b_cols; c < ldb; ++c) hB[(size_t)r * ldb + c] = 1000.f;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      hC1[(size_t)m * ldo + n] = (float)((int)(rnd() % 17) - 8) * 0.125f;
+      hC2[(size_t)m * ldo + n] = (float)((int)(rnd() % 17) - 8) * 0.125f;
+    }
+  for (int n = 0; n < N; ++n) hBias[n] = (float)((int)(rnd() % 9) - 4) * 0.5f;
+
+  float *dA, *dB, *dO, *dC1, *dC2, *dBias, *dWs = nullptr, *dRs;
+  double* dSq;
+  CK(cudaMalloc(&dA, hA.size() * 4));
+  CK(cudaMalloc(&dB, hB.size() * 4));
+  CK(cudaMalloc(&dO, (size_t)M * ldo * 4));
+  CK(cudaMalloc(&dC1, hC1.size() * 4));
+  CK(cudaMalloc(&dC2, hC2.size() * 4));
+  CK(cudaMalloc(&dBias, hBias.size() * 4));
+  CK(cudaMalloc(&dRs, 8));
+  CK(cudaMalloc(&dSq, 16));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dC1, hC1.data(), hC1.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dC2, hC2.data(), hC2.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dBias, hBias.data(), hBias.size() * 4, cudaMemcpyHostToDevice));
+  const float hRs[2] = {1.5f, -0.5f};
+  CK(cudaMemcpy(dRs, hRs, 8, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dSq, 0, 16));
+  CK(cudaMemset(dO, 0xff, (size_t)M * ldo * 4));
+  if (splits > 1) CK(cudaMalloc(&dWs, (size_t)splits * M * rup(N, 4) * 4));
+
+  ganmf::TcGemmCall c;
+  c.A = dA; c.lda = lda; c.a_mn = a_mn;
+  c.B = dB; c.ldb = ldb; c.b_mn = b_mn;
+  c.M = M; c.N = N; c.K = K;
+  c.splits = splits; c.ws = dWs; c.bn = bn; c.tmap_dtype = tmap_dtype;
+  c.ep.out = dO; c.ep.ldo = ldo;
+  const int row_split = M / 3;
+  if (epi) {
+    c.ep.alpha = 0.5f;
+    c.ep.row_scale2 = dRs; c.ep.row_split = row_split;
+    c.ep.bias = dBias;
+    c.ep.c1 = dC1; c.ep.ldc1 = ldo; c.ep.beta1 = -1.f;
+    c.ep.c2 = dC2; c.ep.ldc2 = ldo; c.ep.beta2 = 2.f;
+    c.ep.sumsq2 = dSq;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  CK(ganmf::tc_gemm(c, 0));
+  CK(cudaDeviceSynchronize());
+  const int reps = 5;
+  cudaEventRecord(e0);
+  for (int i = 0; i < reps; ++i) CK(ganmf::tc_gemm(c, 0));
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= reps;
+
+  std::vector<float> hO((size_t)M * ldo);
+  CK(cudaMemcpy(hO.data(), dO, hO.size() * 4, cudaMemcpyDeviceToHost));
+  double hSq[2];
+  CK(cudaMemcpy(hSq, dSq, 16, cudaMemcpyDeviceToHost));
+
+  if (probe) {
+    printf("PROBE tmap_dtype=%d  D[0,0]/K = %.10f  (trunc -> 1.0000000000, rna -> %.10f, exact fp32 -> %.10f)\n",
+           tmap_dtype, hO[0] / K, 1.0 + ldexp(1.0, -10), (double)(1.0f + ldexpf(1.f, -11) + ldexpf(1.f, -12)));
+    return 0;
+  }
+
+  double max_err = 0, ref_sq[2] = {0, 0};
+  int bad = 0;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double acc = 0;
+      for (int k = 0; k < K; ++k) {
+        const float a = a_mn ? hA[(size_t)k * lda + m] : hA[(size_t)m * lda + k];
+        const float b = b_mn ? hB[(size_t)k * ldb + n] : hB[(size_t)n * ldb + k];
+        acc += (double)a * b;
+      }
+      double v = acc;
+      if (epi) {
+        v = 0.5 * hRs[m >= row_split] * acc + hBias[n] - hC1[(size_t)m * ldo + n] +
+            2.0 * hC2[(size_t)m * ldo + n];
+        ref_sq[m >= row_split] += v * v;
+      }
+      const double err = fabs(v - (double)hO[(size_t)m * ldo + n]);
+      if (!(err <= 1e-3)) {
+        if (bad < 5) printf("  mismatch m=%d n=%d ref=%f got=%f\n", m, n, v, hO[(size_t)m * ldo + n]);
+        ++bad;
+      }
+      if (err > max_err || err != err) max_err = err;
+    }
+  const double tflops = 2.0 * M * N * K / (ms * 1e-3) / 1e12;
+  // epi reps accumulate sumsq: (1 + reps) launches
+  bool sq_ok = true;
+  if (epi) {
+    for (int i = 0; i < 2; ++i) {
+      const double want = ref_sq[i] * (1 + reps);
+      if (fabs(hSq[i] - want) > 1e-4 * (1.0 + fabs(want))) sq_ok = false;
+    }
+  }
+  printf("%s M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d splits=%d epi=%d max_err=%.3g bad=%d sumsq_ok=%d  %.3f ms %.1f TF/s\n",
+         (bad == 0 && sq_ok) ? "PASS" : "FAIL", M, N, K, a_mn, b_mn, bn, splits, epi, max_err, bad,
+         (int)sq_ok, ms, tflops);
+  return (bad == 0 && sq_ok) ? 0 : 3;
+}
