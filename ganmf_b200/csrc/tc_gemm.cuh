@@ -59,6 +59,7 @@ struct TcGemmArgs {
   float* ws;               // split-K partials [splits][M][ws_ld] (splits > 1)
   int ws_ld;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;   // smem descriptor strides, bytes >> 4
+  uint32_t a_layout, b_layout;           // UMMA LayoutType of each operand's smem tile
   uint32_t a_kstep, b_kstep;             // start-address advance per UMMA_K, bytes >> 4
   uint32_t idesc;
   Epilogue ep;
@@ -74,15 +75,18 @@ __device__ __forceinline__ float apply_epilogue(const Epilogue& ep, float acc, i
   return v;
 }
 
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo,
+                                                   uint32_t layout_type) {
   // cute::UMMA::SmemDescriptor layout (sm_100): start[0,14) lbo[16,30) sbo[32,46)
-  // version=1 [46,48) layout_type[61,64) with SWIZZLE_128B = 2.
+  // version=1 [46,48) layout_type[61,64): SWIZZLE_128B = 2 (16-byte swizzle atoms, used for
+  // K-major tiles), SWIZZLE_128B_BASE32B = 1 (32-byte atoms: the only swizzled layout the
+  // hardware accepts for MN-major 32-bit operands).
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)(lbo & 0x3FFF) << 16;
   d |= (uint64_t)(sbo & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout_type & 7) << 61;
   return d;
 }
 
@@ -175,8 +179,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(smem + s * S::STAGE_BYTES);
         const uint32_t sb = sa + S::A_BYTES;
-        const uint64_t da = make_smem_desc(sa, args.a_lbo, args.a_sbo);
-        const uint64_t db = make_smem_desc(sb, args.b_lbo, args.b_sbo);
+        const uint64_t da = make_smem_desc(sa, args.a_lbo, args.a_sbo, args.a_layout);
+        const uint64_t db = make_smem_desc(sb, args.b_lbo, args.b_sbo, args.b_layout);
 #pragma unroll
         for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
           ptx::mma_tf32_ss(tmem_base, da + (uint64_t)(k * args.a_kstep),
@@ -306,7 +310,8 @@ inline PFN_encodeTiled get_encode_fn() {
 // fp32 row-major matrix [rows][cols] with leading dimension ld (elements);
 // box = {box_cols (contiguous), box_rows}; 128B swizzle; OOB reads give zeros.
 inline int make_tmap_2d(CUtensorMap* map, const float* ptr, int rows, int cols, int ld,
-                        int box_cols, int box_rows, int tmap_dtype) {
+                        int box_cols, int box_rows, int tmap_dtype,
+                        int swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return 1;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -314,7 +319,7 @@ inline int make_tmap_2d(CUtensorMap* map, const float* ptr, int rows, int cols, 
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, (CUtensorMapDataType)tmap_dtype, 2, const_cast<float*>(ptr), gdim, gstr,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 2;
 }
@@ -327,7 +332,11 @@ struct TcGemmCall {
   int splits = 1;          // > 1 needs ws
   float* ws = nullptr;     // >= splits * M * roundup(N,4) floats
   int bn = 128;            // 128 or 256
-  int tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  // TFLOAT32 makes TMA round fp32 -> tf32 to nearest on the way into shared memory
+  // (measured: FLOAT32 maps leave the bits alone and the MMA then truncates).
+  int tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  // bring-up overrides for the MN-major tile encoding (0 = use the defaults below)
+  int dbg_mn_layout = 0, dbg_mn_sbo = 0, dbg_mn_lbo = 0, dbg_mn_swizzle = 0;
 };
 
 inline uint32_t make_idesc_tf32(int bn, int a_mn, int b_mn) {
@@ -369,11 +378,12 @@ inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   const int bn = c.bn == 256 ? 256 : 128;
   CUtensorMap ma, mb;
   int rc;
+  const int mn_swz = c.dbg_mn_swizzle ? c.dbg_mn_swizzle : (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   if (!c.a_mn) rc = make_tmap_2d(&ma, c.A, c.M, c.K, c.lda, TC_BK, TC_BM, c.tmap_dtype);
-  else         rc = make_tmap_2d(&ma, c.A, c.K, c.M, c.lda, 32, TC_BK, c.tmap_dtype);
+  else         rc = make_tmap_2d(&ma, c.A, c.K, c.M, c.lda, 32, TC_BK, c.tmap_dtype, mn_swz);
   if (rc) return cudaErrorUnknown;
   if (!c.b_mn) rc = make_tmap_2d(&mb, c.B, c.N, c.K, c.ldb, TC_BK, bn, c.tmap_dtype);
-  else         rc = make_tmap_2d(&mb, c.B, c.K, c.N, c.ldb, 32, TC_BK, c.tmap_dtype);
+  else         rc = make_tmap_2d(&mb, c.B, c.K, c.N, c.ldb, 32, TC_BK, c.tmap_dtype, mn_swz);
   if (rc) return cudaErrorUnknown;
 
   TcGemmArgs args;
@@ -388,14 +398,20 @@ inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   args.kb_per_split = kbps;
   args.ws = c.ws;
   args.ws_ld = (c.N + 3) & ~3;
-  // shared-memory matrix descriptors (bytes >> 4), 128B swizzle:
-  //  K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (=1).
-  //  MN-major: 32-element (128 B) chunks of MN, chunk stride LBO = TC_BK*128 B,
-  //            8-k groups 1024 B apart (SBO).
-  args.a_lbo = c.a_mn ? (TC_BK * 128) >> 4 : 1;
-  args.a_sbo = 1024 >> 4;
-  args.b_lbo = c.b_mn ? (TC_BK * 128) >> 4 : 1;
-  args.b_sbo = 1024 >> 4;
+  // shared-memory matrix descriptors (bytes >> 4):
+  //  K-major : SWIZZLE_128B; rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (=1).
+  //  MN-major: SWIZZLE_128B_BASE32B (TMA 128B_ATOM_32B); each TMA box is 32 k-rows of 128 B
+  //            (= 32 MN elements); 4-k groups 512 B apart (SBO); 32-element MN chunks one
+  //            box = TC_BK*128 B apart (LBO); one UMMA (K=8) consumes 1024 B of a box.
+  const uint32_t mn_layout = c.dbg_mn_layout ? c.dbg_mn_layout : 1;
+  const uint32_t mn_sbo = (c.dbg_mn_sbo ? c.dbg_mn_sbo : 512) >> 4;
+  const uint32_t mn_lbo = (c.dbg_mn_lbo ? c.dbg_mn_lbo : TC_BK * 128) >> 4;
+  args.a_layout = c.a_mn ? mn_layout : 2;
+  args.b_layout = c.b_mn ? mn_layout : 2;
+  args.a_lbo = c.a_mn ? mn_lbo : 1;
+  args.a_sbo = c.a_mn ? mn_sbo : 1024 >> 4;
+  args.b_lbo = c.b_mn ? mn_lbo : 1;
+  args.b_sbo = c.b_mn ? mn_sbo : 1024 >> 4;
   args.a_kstep = c.a_mn ? (1024 >> 4) : (TC_UMMA_K * 4) >> 4;
   args.b_kstep = c.b_mn ? (1024 >> 4) : (TC_UMMA_K * 4) >> 4;
   args.idesc = make_idesc_tf32(bn, c.a_mn, c.b_mn);
