@@ -1,0 +1,115 @@
+"""EvaluatorHoldout of the reference (Base/Evaluation/Evaluator.py:219-414) with the hot loop on the GPU.
+
+Same constructor, same `evaluateRecommender(recommender) -> (results_dict, results_string)`, same
+metric keys, averaging and F1 rule.  What changed underneath: instead of the per-user Python loop
+over 20 metric updates (Evaluator.py:291-335, ~85 % of the reference's evaluation time) each user
+block is scored, seen-masked, top-k'ed and reduced to metric sums on the device; only the sums and the
+per-item recommendation histograms come back."""
+import numpy as np
+import scipy.sparse as sps
+
+from ... import _lib as L
+from .metrics import finalize_count_metrics
+
+# key order of the reference's EvaluatorMetrics enum (Evaluator.py:21-43) minus DIVERSITY_SIMILARITY,
+# which only exists when a diversity_object is passed
+RESULT_KEYS = ["ROC_AUC", "PRECISION", "PRECISION_RECALL_MIN_DEN", "RECALL", "MAP", "MRR", "NDCG", "F1",
+               "HIT_RATE", "ARHR", "RMSE", "NOVELTY", "AVERAGE_POPULARITY", "DIVERSITY_MEAN_INTER_LIST",
+               "DIVERSITY_HERFINDAHL", "COVERAGE_ITEM", "COVERAGE_USER", "DIVERSITY_GINI", "SHANNON_ENTROPY"]
+
+
+def get_result_string(results_run, n_decimals=7):                      # Evaluator.py:95-110
+    output_str = ""
+    for cutoff in results_run.keys():
+        output_str += "CUTOFF: {} - ".format(cutoff)
+        for metric in results_run[cutoff].keys():
+            output_str += "{}: {:.{n_decimals}f}, ".format(metric, results_run[cutoff][metric], n_decimals=n_decimals)
+        output_str += "\n"
+    return output_str
+
+
+class Evaluator(object):
+    EVALUATOR_NAME = "Evaluator_Base_Class"
+
+    def __init__(self, URM_test_list, cutoff_list, minRatingsPerUser=1, exclude_seen=True, diversity_object=None,
+                 ignore_items=None, ignore_users=None):
+        super(Evaluator, self).__init__()
+        if ignore_items is None:                                       # Evaluator.py:128-134
+            self.ignore_items_flag = False
+            self.ignore_items_ID = np.array([])
+        else:
+            print("Ignoring {} Items".format(len(ignore_items)))
+            self.ignore_items_flag = True
+            self.ignore_items_ID = np.array(ignore_items)
+        self.cutoff_list = cutoff_list.copy()
+        self.max_cutoff = max(self.cutoff_list)
+        self.minRatingsPerUser = minRatingsPerUser
+        self.exclude_seen = exclude_seen
+        if isinstance(URM_test_list, list):
+            raise ValueError("List of URM_test not supported")
+        if diversity_object is not None:
+            raise NotImplementedError("DIVERSITY_SIMILARITY (diversity_object) is outside the GANMF hot path")
+        self.diversity_object = None
+        self.URM_test = sps.csr_matrix(URM_test_list.copy(), dtype=np.float32)
+        self.URM_test.sort_indices()
+        self.n_users, self.n_items = self.URM_test.shape
+        numRatings = np.ediff1d(self.URM_test.indptr)
+        self.usersToEvaluate = np.arange(self.n_users)[numRatings >= minRatingsPerUser]
+        if ignore_users is not None:
+            print("Ignoring {} Users".format(len(ignore_users)))
+            self.ignore_users_ID = np.array(ignore_users)
+            self.usersToEvaluate = sorted(set(self.usersToEvaluate) - set(ignore_users))
+        else:
+            self.ignore_users_ID = np.array([])
+        self.usersToEvaluate = list(self.usersToEvaluate)
+
+    def get_user_relevant_items(self, user_id):
+        return self.URM_test.indices[self.URM_test.indptr[user_id]:self.URM_test.indptr[user_id + 1]]
+
+    def get_user_test_ratings(self, user_id):
+        return self.URM_test.data[self.URM_test.indptr[user_id]:self.URM_test.indptr[user_id + 1]]
+
+
+class EvaluatorHoldout(Evaluator):
+    EVALUATOR_NAME = "EvaluatorHoldout"
+
+    def __init__(self, URM_test_list, cutoff_list, minRatingsPerUser=1, exclude_seen=True, diversity_object=None,
+                 ignore_items=None, ignore_users=None):
+        super(EvaluatorHoldout, self).__init__(URM_test_list, cutoff_list, diversity_object=diversity_object,
+                                               minRatingsPerUser=minRatingsPerUser, exclude_seen=exclude_seen,
+                                               ignore_items=ignore_items, ignore_users=ignore_users)
+
+    # ------------------------------------------------------------------------------------------
+    def _device_sums(self, recommender_object, users):
+        """(sums[n_cut, MC_NCOL], counts[n_cut, n_items]) over `users` in ascending order."""
+        if self.ignore_items_flag:
+            raise NotImplementedError("ignore_items is outside the GANMF hot path (Evaluator.py:369-370)")
+        eng = getattr(recommender_object, "_engine", None)
+        URM_train = recommender_object.get_URM_train()
+        if eng is None:
+            raise NotImplementedError("evaluating a recommender without a ganmf_b200 device engine is a 'next' row "
+                                      "(SURVEY.md section 8f); there is no CPU evaluation path")
+        eng.set_test(self.URM_test, URM_train)
+        return eng.evaluate(users, self.cutoff_list, remove_seen=self.exclude_seen)
+
+    def evaluateRecommender(self, recommender_object):
+        users = np.asarray(self.usersToEvaluate, dtype=np.int32)
+        n_eval = len(users)
+        results_dict = {}
+        if n_eval > 0:
+            sums, counts = self._device_sums(recommender_object, users)
+            for ci, cutoff in enumerate(self.cutoff_list):
+                s = dict(zip(L.MC_NAMES, sums[ci]))
+                res = {k: s[k] / n_eval for k in ("ROC_AUC", "PRECISION", "PRECISION_RECALL_MIN_DEN", "RECALL", "MAP",
+                                                  "MRR", "NDCG", "HIT_RATE", "ARHR", "RMSE", "NOVELTY",
+                                                  "AVERAGE_POPULARITY")}
+                res.update(finalize_count_metrics(counts[ci], n_eval, cutoff, self.n_items))
+                res["COVERAGE_USER"] = s["COVERED"] / self.n_users     # metrics.py:57-80
+                p_, r_ = res["PRECISION"], res["RECALL"]
+                res["F1"] = 2 * (p_ * r_) / (p_ + r_) if p_ + r_ != 0 else 0.0   # Evaluator.py:392-397
+                results_dict[cutoff] = {k: res[k] for k in RESULT_KEYS}
+        else:
+            print("WARNING: No users had a sufficient number of relevant items")
+            for cutoff in self.cutoff_list:
+                results_dict[cutoff] = {k: 0.0 for k in RESULT_KEYS}
+        return results_dict, get_result_string(results_dict)

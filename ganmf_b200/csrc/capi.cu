@@ -1,0 +1,1124 @@
+// C ABI of ganmf_b200 (include/ganmf_b200.h): device-resident model state + the step, scoring
+// and evaluation drivers that sequence the sm_100a kernels.  No CPU compute path exists here.
+#include "../../include/ganmf_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "eval_kernels.cuh"
+#include "kernels.cuh"
+#include "tc_gemm.cuh"
+
+using namespace ganmf;
+
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CU(x)                                                                              \
+  do {                                                                                     \
+    cudaError_t e_ = (x);                                                                  \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_));       \
+  } while (0)
+#define RC(x)                \
+  do {                       \
+    int r_ = (x);            \
+    if (r_) return r_;       \
+  } while (0)
+
+static inline int rup(int x, int a) { return (x + a - 1) / a * a; }
+
+struct Mat {
+  float* p = nullptr;
+  int rows = 0, cols = 0, ld = 0;
+  size_t elems() const { return (size_t)rows * ld; }
+  float* row(int r) const { return p + (size_t)r * ld; }
+};
+struct Param {
+  std::string name;
+  Mat w;                       // view into the optimiser group's slab
+  float *m = nullptr, *v = nullptr, *g = nullptr, *best = nullptr;
+  int is_gen = 0;
+};
+struct Csr {
+  int* indptr = nullptr;
+  int* indices = nullptr;
+  float* data = nullptr;
+  int n_rows = 0, n_cols = 0;
+  long long nnz = 0;
+};
+
+struct ganmf_ctx {
+  ganmf_config cfg;
+  cudaStream_t st = 0;
+  std::vector<Param> params;           // discriminator tensors first, then P, V
+  int n_d = 0;                         // number of discriminator tensors
+  // slabs: [theta | m | v | grad | best] for D; P and V separate (P can be very large)
+  float* d_slab = nullptr; size_t d_elems = 0;
+  float* p_slab = nullptr; size_t p_elems = 0;     // theta, m, v, best (no dense grad)
+  float* v_slab = nullptr; size_t v_elems = 0;     // theta, m, v, grad, best
+  bool have_best = false;
+  // activations / workspaces
+  int B = 0, W = 0, Wp = 0, k = 0, kp = 0, E = 0, Ep = 0;
+  Mat X2, H2, H2s, Res2, dH2, dF, Pb, dPb;
+  // DisGANMF: per layer activations h[l] [2B, Hp], dz [2B, Hp], out2/dout2 [2B]
+  std::vector<Mat> hs, dzs;
+  Mat dhtmp;
+  float *out2 = nullptr, *dout2 = nullptr, *idf = nullptr;
+  float* ws = nullptr; size_t ws_floats = 0;
+  StepScalars* sc = nullptr;
+  float* losses = nullptr; int losses_cap = 0;
+  int* ids = nullptr; int ids_cap = 0;
+  int* slot = nullptr;
+  Csr csr[3];
+  float b1p[2] = {ADAM_B1, ADAM_B1}, b2p[2] = {ADAM_B2, ADAM_B2};   // [0]=D optimiser, [1]=G
+  // evaluator
+  EvalTables tb{};
+  float *tb_gain = nullptr, *tb_gain_desc = nullptr, *tb_logtab = nullptr;
+  double *tb_nov = nullptr, *tb_popn = nullptr;
+  unsigned char* tb_haspop = nullptr;
+  float* rmse_scratch = nullptr;
+  bool have_tables = false;
+  float* scores = nullptr; size_t scores_elems = 0;   // [block][items_ld]
+  Mat Fb;                                              // gathered factor rows for scoring
+  int* topk_idx = nullptr; float* topk_val = nullptr; size_t topk_cap = 0;
+  double* uvals = nullptr; size_t uvals_cap = 0;
+  double* usums = nullptr; int* icounts = nullptr; size_t icounts_cap = 0;
+  int* cut_dev = nullptr;
+  int* eval_users = nullptr; int eval_users_cap = 0;
+  long long launches = 0;
+  int last_ids_offset = 0;
+};
+
+const char* ganmf_last_error(void) { return g_err; }
+
+template <typename T>
+static int dalloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes) -> %s", n * sizeof(T), cudaGetErrorString(e));
+  e = cudaMemset(*p, 0, n * sizeof(T));
+  if (e != cudaSuccess) return fail("cudaMemset -> %s", cudaGetErrorString(e));
+  return 0;
+}
+static int mat_alloc(Mat* m, int rows, int cols) {
+  m->rows = rows; m->cols = cols; m->ld = rup(cols, 32);
+  return dalloc(&m->p, m->elems());
+}
+static Mat mat_view(float* p, int rows, int cols) {
+  Mat m; m.p = p; m.rows = rows; m.cols = cols; m.ld = rup(cols, 32);
+  return m;
+}
+
+// ------------------------------------------------------------------------------ GEMM dispatch
+// out[M,N] = epilogue(A . B^T), A logical [M,K], B logical [N,K]; *_mn = stored transposed.
+static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn,
+                int M, int N, int K, const Epilogue& ep, int force_path = GANMF_GEMM_AUTO) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  int path = force_path != GANMF_GEMM_AUTO ? force_path : c->cfg.gemm_path;
+  const bool aligned = !(lda & 3) && !(ldb & 3) && !((uintptr_t)A & 15) && !((uintptr_t)B & 15);
+  if (path == GANMF_GEMM_AUTO)
+    path = (aligned && (double)M * N * K >= (double)(1 << 18)) ? GANMF_GEMM_TC : GANMF_GEMM_SIMT;
+  if (path == GANMF_GEMM_TC && !aligned) return fail("tcgen05 GEMM needs 16-byte aligned operands");
+  if (path == GANMF_GEMM_SIMT) {
+    c->launches += 1;
+    CU(simt_gemm(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, c->st));
+    return 0;
+  }
+  TcGemmCall g;
+  g.A = A; g.lda = lda; g.a_mn = a_mn;
+  g.B = B; g.ldb = ldb; g.b_mn = b_mn;
+  g.M = M; g.N = N; g.K = K;
+  g.ep = ep;
+  g.bn = N > 128 ? 256 : 128;
+  const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + g.bn - 1) / g.bn);
+  const int total_kb = (K + TC_BK - 1) / TC_BK;
+  int splits = 1;
+  if (tiles < 148 && total_kb >= 16) {
+    splits = std::min((2 * 148 + tiles - 1) / tiles, total_kb / 8);
+    const size_t per = (size_t)M * rup(N, 4);
+    if ((size_t)splits * per > c->ws_floats) splits = (int)(c->ws_floats / per);
+    if (splits < 1) splits = 1;
+  }
+  g.splits = splits;
+  g.ws = c->ws;
+  c->launches += splits > 1 ? 2 : 1;
+  cudaError_t e = tc_gemm(g, c->st);
+  if (e != cudaSuccess) return fail("tc_gemm(M=%d N=%d K=%d) -> %s", M, N, K, cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ create/destroy
+static void add_param(ganmf_ctx* c, const char* name, int rows, int cols, int is_gen) {
+  Param p;
+  p.name = name;
+  p.w.rows = rows; p.w.cols = cols; p.w.ld = rup(cols, 32);
+  p.is_gen = is_gen;
+  c->params.push_back(p);
+}
+
+int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
+  if (!cfg || !out) return fail("null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: ganmf_b200 has no CPU path (%s)", cudaGetErrorString(e));
+  CU(cudaSetDevice(cfg->device));
+  if (cfg->n_rows <= 0 || cfg->width <= 0 || cfg->num_factors <= 0 || cfg->max_batch <= 0)
+    return fail("bad config");
+  ganmf_ctx* c = new ganmf_ctx();
+  c->cfg = *cfg;
+  c->B = cfg->max_batch; c->W = cfg->width; c->Wp = rup(cfg->width, 32);
+  c->k = cfg->num_factors; c->kp = rup(c->k, 32);
+  if (cfg->kind == GANMF_KIND_GANMF) {
+    if (cfg->emb_dim <= 0) { delete c; return fail("emb_dim must be > 0"); }
+    c->E = cfg->emb_dim; c->Ep = rup(c->E, 32);
+    add_param(c, "autoencoder/encoding/kernel", c->W, c->E, 0);
+    add_param(c, "autoencoder/encoding/bias", 1, c->E, 0);
+    add_param(c, "autoencoder/decoding/kernel", c->E, c->W, 0);
+    add_param(c, "autoencoder/decoding/bias", 1, c->W, 0);
+  } else if (cfg->kind == GANMF_KIND_DISGANMF) {
+    if (cfg->d_layers < 1 || cfg->d_nodes < 1) { delete c; return fail("bad discriminator shape"); }
+    c->E = cfg->d_nodes; c->Ep = rup(c->E, 32);
+    int fan_in = c->W + 1;
+    char nm[96];
+    for (int l = 0; l < cfg->d_layers; ++l) {
+      snprintf(nm, sizeof nm, "discriminator/layer_%d/kernel", l);
+      add_param(c, nm, fan_in, cfg->d_nodes, 0);
+      snprintf(nm, sizeof nm, "discriminator/layer_%d/bias", l);
+      add_param(c, nm, 1, cfg->d_nodes, 0);
+      fan_in = cfg->d_nodes;
+    }
+    add_param(c, "discriminator/D_output/kernel", fan_in, 1, 0);
+    add_param(c, "discriminator/D_output/bias", 1, 1, 0);
+  } else {
+    delete c;
+    return fail("unknown kind %d", cfg->kind);
+  }
+  c->n_d = (int)c->params.size();
+  add_param(c, "generator/user_embeddings", cfg->n_rows, c->k, 1);
+  add_param(c, "generator/item_embeddings", c->W, c->k, 1);
+
+  // discriminator slab: theta | m | v | grad | best, each d_elems floats, tensors back to back
+  for (int i = 0; i < c->n_d; ++i) c->d_elems += c->params[i].w.elems();
+  RC(dalloc(&c->d_slab, 5 * c->d_elems));
+  size_t off = 0;
+  for (int i = 0; i < c->n_d; ++i) {
+    Param& p = c->params[i];
+    p.w.p = c->d_slab + off;
+    p.m = c->d_slab + c->d_elems + off;
+    p.v = c->d_slab + 2 * c->d_elems + off;
+    p.g = c->d_slab + 3 * c->d_elems + off;
+    p.best = c->d_slab + 4 * c->d_elems + off;
+    off += p.w.elems();
+  }
+  Param& P = c->params[c->n_d];
+  Param& V = c->params[c->n_d + 1];
+  c->p_elems = P.w.elems();
+  RC(dalloc(&c->p_slab, 4 * c->p_elems));
+  P.w.p = c->p_slab; P.m = c->p_slab + c->p_elems; P.v = c->p_slab + 2 * c->p_elems;
+  P.best = c->p_slab + 3 * c->p_elems;
+  c->v_elems = V.w.elems();
+  RC(dalloc(&c->v_slab, 5 * c->v_elems));
+  V.w.p = c->v_slab; V.m = c->v_slab + c->v_elems; V.v = c->v_slab + 2 * c->v_elems;
+  V.g = c->v_slab + 3 * c->v_elems; V.best = c->v_slab + 4 * c->v_elems;
+
+  const int B = c->B;
+  RC(mat_alloc(&c->X2, 2 * B, c->W));
+  RC(mat_alloc(&c->Pb, B, c->k));
+  RC(mat_alloc(&c->dPb, B, c->k));
+  RC(mat_alloc(&c->dF, B, c->W));
+  if (cfg->kind == GANMF_KIND_GANMF) {
+    RC(mat_alloc(&c->H2, 2 * B, c->E));
+    RC(mat_alloc(&c->H2s, 2 * B, c->E));
+    RC(mat_alloc(&c->dH2, 2 * B, c->E));
+    RC(mat_alloc(&c->Res2, 2 * B, c->W));
+  } else {
+    c->hs.resize(cfg->d_layers);
+    c->dzs.resize(cfg->d_layers);
+    for (int l = 0; l < cfg->d_layers; ++l) {
+      RC(mat_alloc(&c->hs[l], 2 * B, cfg->d_nodes));
+      RC(mat_alloc(&c->dzs[l], 2 * B, cfg->d_nodes));
+    }
+    RC(mat_alloc(&c->dhtmp, 2 * B, cfg->d_nodes));
+    RC(dalloc(&c->out2, (size_t)rup(2 * B, 32)));
+    RC(dalloc(&c->dout2, (size_t)rup(2 * B, 32)));
+    RC(dalloc(&c->idf, (size_t)rup(2 * B, 32)));
+  }
+  c->ws_floats = (size_t)48 << 20;     // 192 MB of split-K partials
+  RC(dalloc(&c->ws, c->ws_floats));
+  RC(dalloc(&c->sc, 1));
+  c->losses_cap = 1 << 16;
+  RC(dalloc(&c->losses, (size_t)c->losses_cap));
+  c->ids_cap = std::max(cfg->n_rows, 2 * B);
+  RC(dalloc(&c->ids, (size_t)c->ids_cap));
+  RC(dalloc(&c->slot, (size_t)cfg->n_rows));
+  fill_int_kernel<<<(cfg->n_rows + 255) / 256, 256>>>(c->slot, -1, (size_t)cfg->n_rows);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  *out = c;
+  return 0;
+}
+
+static void csr_free(Csr& m) {
+  cudaFree(m.indptr); cudaFree(m.indices); cudaFree(m.data);
+  m = Csr();
+}
+
+void ganmf_destroy(ganmf_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaDeviceSynchronize();
+  cudaFree(c->d_slab); cudaFree(c->p_slab); cudaFree(c->v_slab);
+  for (Mat* m : {&c->X2, &c->H2, &c->H2s, &c->Res2, &c->dH2, &c->dF, &c->Pb, &c->dPb, &c->dhtmp, &c->Fb})
+    cudaFree(m->p);
+  for (auto& m : c->hs) cudaFree(m.p);
+  for (auto& m : c->dzs) cudaFree(m.p);
+  cudaFree(c->out2); cudaFree(c->dout2); cudaFree(c->idf);
+  cudaFree(c->ws); cudaFree(c->sc); cudaFree(c->losses); cudaFree(c->ids); cudaFree(c->slot);
+  for (int i = 0; i < 3; ++i) csr_free(c->csr[i]);
+  cudaFree(c->tb_gain); cudaFree(c->tb_gain_desc); cudaFree(c->tb_logtab); cudaFree(c->tb_nov);
+  cudaFree(c->tb_popn); cudaFree(c->tb_haspop); cudaFree(c->rmse_scratch);
+  cudaFree(c->scores); cudaFree(c->topk_idx); cudaFree(c->topk_val); cudaFree(c->uvals);
+  cudaFree(c->usums); cudaFree(c->icounts); cudaFree(c->cut_dev); cudaFree(c->eval_users);
+  delete c;
+}
+
+int ganmf_set_stream(ganmf_ctx* c, void* s) {
+  if (!c) return fail("null ctx");
+  c->st = (cudaStream_t)s;
+  return 0;
+}
+int ganmf_synchronize(ganmf_ctx* c) {
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+int64_t ganmf_launch_count(ganmf_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------ data
+int ganmf_set_csr(ganmf_ctx* c, int which, int n_rows, int n_cols, const int32_t* indptr,
+                  const int32_t* indices, const float* data) {
+  if (!c || which < 0 || which > 2 || !indptr) return fail("bad argument");
+  if (which == GANMF_CSR_TRAIN && (n_rows != c->cfg.n_rows || n_cols != c->W))
+    return fail("train CSR is %dx%d, context expects %dx%d", n_rows, n_cols, c->cfg.n_rows, c->W);
+  Csr& m = c->csr[which];
+  csr_free(m);
+  m.n_rows = n_rows; m.n_cols = n_cols; m.nnz = indptr[n_rows];
+  RC(dalloc(&m.indptr, (size_t)n_rows + 1));
+  RC(dalloc(&m.indices, (size_t)m.nnz));
+  CU(cudaMemcpy(m.indptr, indptr, ((size_t)n_rows + 1) * 4, cudaMemcpyHostToDevice));
+  if (m.nnz) CU(cudaMemcpy(m.indices, indices, (size_t)m.nnz * 4, cudaMemcpyHostToDevice));
+  if (data) {
+    RC(dalloc(&m.data, (size_t)m.nnz));
+    if (m.nnz) CU(cudaMemcpy(m.data, data, (size_t)m.nnz * 4, cudaMemcpyHostToDevice));
+  }
+  if (which == GANMF_CSR_TEST) c->have_tables = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ parameters
+static Param* find_param(ganmf_ctx* c, const char* name) {
+  for (auto& p : c->params)
+    if (p.name == name) return &p;
+  return nullptr;
+}
+int ganmf_param_count(ganmf_ctx* c) { return c ? (int)c->params.size() : 0; }
+int ganmf_param_info(ganmf_ctx* c, int i, char* name, int cap, int* rows, int* cols, int* is_gen) {
+  if (!c || i < 0 || i >= (int)c->params.size()) return fail("bad index");
+  const Param& p = c->params[i];
+  if (name && cap > 0) { strncpy(name, p.name.c_str(), cap - 1); name[cap - 1] = 0; }
+  if (rows) *rows = p.w.rows;
+  if (cols) *cols = p.w.cols;
+  if (is_gen) *is_gen = p.is_gen;
+  return 0;
+}
+int ganmf_set_param(ganmf_ctx* c, const char* name, const float* host, int64_t count) {
+  Param* p = c ? find_param(c, name) : nullptr;
+  if (!p) return fail("unknown parameter %s", name ? name : "(null)");
+  if (count != (int64_t)p->w.rows * p->w.cols) return fail("%s: expected %d x %d", name, p->w.rows, p->w.cols);
+  CU(cudaStreamSynchronize(c->st));
+  CU(cudaMemcpy2D(p->w.p, (size_t)p->w.ld * 4, host, (size_t)p->w.cols * 4, (size_t)p->w.cols * 4,
+                  p->w.rows, cudaMemcpyHostToDevice));
+  return 0;
+}
+int ganmf_get_param(ganmf_ctx* c, const char* name, float* host, int64_t count) {
+  Param* p = c ? find_param(c, name) : nullptr;
+  if (!p) return fail("unknown parameter %s", name ? name : "(null)");
+  if (count != (int64_t)p->w.rows * p->w.cols) return fail("%s: expected %d x %d", name, p->w.rows, p->w.cols);
+  CU(cudaStreamSynchronize(c->st));
+  CU(cudaMemcpy2D(host, (size_t)p->w.cols * 4, p->w.p, (size_t)p->w.ld * 4, (size_t)p->w.cols * 4,
+                  p->w.rows, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// counter-based uniform generator (splitmix64 finaliser): U(-lim, lim) on the real columns only
+__global__ void glorot_kernel(float* w, int rows, int cols, int ld, float lim, unsigned long long seed) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  const int r = (int)(i / cols), cc = (int)(i % cols);
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);     // [0, 1)
+  w[(size_t)r * ld + cc] = (2.f * u - 1.f) * lim;
+}
+int ganmf_init_params(ganmf_ctx* c, uint64_t seed) {
+  if (!c) return fail("null ctx");
+  int i = 0;
+  for (auto& p : c->params) {
+    CU(cudaMemsetAsync(p.w.p, 0, p.w.elems() * 4, c->st));
+    if (p.w.rows > 1 || p.name.find("kernel") != std::string::npos) {     // matrices; biases stay zero
+      const float lim = sqrtf(6.0f / (float)(p.w.rows + p.w.cols));
+      const size_t n = (size_t)p.w.rows * p.w.cols;
+      glorot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(p.w.p, p.w.rows, p.w.cols, p.w.ld, lim,
+                                                                   seed * 1000003ull + 7919ull * (++i));
+      CU(cudaGetLastError());
+      c->launches++;
+    }
+  }
+  return ganmf_reset_optimizers(c);
+}
+int ganmf_reset_optimizers(ganmf_ctx* c) {
+  if (!c) return fail("null ctx");
+  CU(cudaMemsetAsync(c->d_slab + c->d_elems, 0, 3 * c->d_elems * 4, c->st));   // m, v, grad
+  CU(cudaMemsetAsync(c->p_slab + c->p_elems, 0, 2 * c->p_elems * 4, c->st));
+  CU(cudaMemsetAsync(c->v_slab + c->v_elems, 0, 3 * c->v_elems * 4, c->st));
+  c->b1p[0] = c->b1p[1] = ADAM_B1;
+  c->b2p[0] = c->b2p[1] = ADAM_B2;
+  return 0;
+}
+int ganmf_snapshot(ganmf_ctx* c) {
+  CU(cudaMemcpyAsync(c->d_slab + 4 * c->d_elems, c->d_slab, c->d_elems * 4, cudaMemcpyDeviceToDevice, c->st));
+  CU(cudaMemcpyAsync(c->p_slab + 3 * c->p_elems, c->p_slab, c->p_elems * 4, cudaMemcpyDeviceToDevice, c->st));
+  CU(cudaMemcpyAsync(c->v_slab + 4 * c->v_elems, c->v_slab, c->v_elems * 4, cudaMemcpyDeviceToDevice, c->st));
+  c->have_best = true;
+  return 0;
+}
+int ganmf_restore(ganmf_ctx* c) {
+  // the reference's shadow variables exist from graph construction with their own random init
+  // (GANMF.py:123-128); restoring before any snapshot is therefore refused instead of guessed
+  if (!c->have_best) return fail("load_model() before any save_current_model()");
+  CU(cudaMemcpyAsync(c->d_slab, c->d_slab + 4 * c->d_elems, c->d_elems * 4, cudaMemcpyDeviceToDevice, c->st));
+  CU(cudaMemcpyAsync(c->p_slab, c->p_slab + 3 * c->p_elems, c->p_elems * 4, cudaMemcpyDeviceToDevice, c->st));
+  CU(cudaMemcpyAsync(c->v_slab, c->v_slab + 4 * c->v_elems, c->v_elems * 4, cudaMemcpyDeviceToDevice, c->st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ training
+int ganmf_upload_ids(ganmf_ctx* c, const int32_t* ids, int n) {
+  if (!c || n < 0 || n > c->ids_cap) return fail("upload_ids: n=%d exceeds capacity %d", n, c ? c->ids_cap : 0);
+  CU(cudaMemcpyAsync(c->ids, ids, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+  return 0;
+}
+
+static float adam_alpha(ganmf_ctx* c, int which, float lr) {
+  // TF: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), beta powers kept as fp32 variables
+  const float a = lr * sqrtf(1.f - c->b2p[which]) / (1.f - c->b1p[which]);
+  c->b1p[which] *= ADAM_B1;
+  c->b2p[which] *= ADAM_B2;
+  return a;
+}
+
+static int check_batch(ganmf_ctx* c, int ids_offset, int B) {
+  if (!c) return fail("null ctx");
+  if (B <= 0 || B > c->B) return fail("batch %d outside (0, %d]", B, c->B);
+  if (ids_offset < 0 || ids_offset + B > c->ids_cap) return fail("ids range out of bounds");
+  if (!c->csr[GANMF_CSR_TRAIN].indptr) return fail("train CSR not set");
+  return 0;
+}
+
+// real profiles -> X2[0:B], P[ids] -> Pb, fake profiles F = Pb . V^T -> X2[B:2B]
+static int forward_generator(ganmf_ctx* c, int ids_offset, int B) {
+  const Csr& tr = c->csr[GANMF_CSR_TRAIN];
+  const int* ids = c->ids + ids_offset;
+  CU(csr_gather_dense(tr.indptr, tr.indices, tr.data, ids, B, c->X2.p, c->X2.ld, 0, c->st));
+  const Param& P = c->params[c->n_d];
+  const Param& V = c->params[c->n_d + 1];
+  gather_rows_kernel<<<B, 64, 0, c->st>>>(P.w.p, ids, c->Pb.p, c->Pb.ld);
+  CU(cudaGetLastError());
+  c->launches += 2;
+  Epilogue ep;
+  ep.out = c->X2.row(B); ep.ldo = c->X2.ld;
+  return gemm(c, c->Pb.p, c->Pb.ld, 0, V.w.p, V.w.ld, 0, B, c->W, c->k, ep);      // G1
+}
+
+static int adam_group(ganmf_ctx* c, int first, int count, float alpha, float reg, int slot_param) {
+  AdamArgs a;
+  memset(&a, 0, sizeof a);
+  a.nseg = count;
+  for (int i = 0; i < count; ++i) {
+    Param& p = c->params[first + i];
+    AdamSeg& s = a.seg[i];
+    s.theta = p.w.p; s.m = p.m; s.v = p.v; s.g = p.g; s.slot = nullptr; s.ld = p.w.ld;
+    s.n4 = p.w.elems() / 4;
+    if (first + i == slot_param) { s.g = c->dPb.p; s.slot = c->slot; }
+  }
+  a.alpha = alpha; a.reg = reg;
+  a.l2_out = &c->sc->l2;
+  c->launches++;
+  CU(fused_adam(a, c->st));
+  return 0;
+}
+
+// ---- GANMF ---------------------------------------------------------------------------------
+static int ganmf_d_forward_impl(ganmf_ctx* c, int ids_offset, int B) {
+  RC(forward_generator(c, ids_offset, B));
+  Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
+  CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
+  Epilogue e2;                                                                     // G2
+  e2.out = c->H2.p; e2.ldo = c->H2.ld; e2.bias = be->w.p;
+  RC(gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, 2 * B, c->E, c->W, e2));
+  Epilogue e3;                                                                     // G3
+  e3.out = c->Res2.p; e3.ldo = c->Res2.ld; e3.bias = bd->w.p;
+  e3.c1 = c->X2.p; e3.ldc1 = c->X2.ld; e3.beta1 = -1.f;
+  e3.sumsq2 = c->sc->sumsq; e3.row_split = B;
+  return gemm(c, c->H2.p, c->H2.ld, 0, Wd->w.p, Wd->w.ld, 1, 2 * B, c->W, c->E, e3);
+}
+
+static int ganmf_d_backward_impl(ganmf_ctx* c, int B, int n_global, float m_hinge) {
+  Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
+  const double n_elems = (double)n_global * c->W;
+  hinge_gate_kernel<<<1, 1, 0, c->st>>>(c->sc, m_hinge, n_elems);
+  CU(cudaGetLastError());
+  const float* rs = c->sc->row_scale;
+  scale_rows_kernel<<<dim3(std::max(1, c->H2.ld / 4 / 128), 2 * B), 128, 0, c->st>>>(
+      c->H2.p, c->H2s.p, c->H2.ld / 4, rs, B);
+  CU(cudaGetLastError());
+  Epilogue e4;                                                                     // G4: dWd
+  e4.out = Wd->g; e4.ldo = Wd->w.ld;
+  RC(gemm(c, c->H2s.p, c->H2s.ld, 1, c->Res2.p, c->Res2.ld, 1, c->E, c->W, 2 * B, e4));
+  colsum_kernel<<<(c->W + 31) / 32, dim3(32, 8), 0, c->st>>>(c->Res2.p, 2 * B, c->W, c->Res2.ld, rs, B,
+                                                            nullptr, bd->g);   // dbd
+  CU(cudaGetLastError());
+  Epilogue e5;                                                                     // G5: dH2
+  e5.out = c->dH2.p; e5.ldo = c->dH2.ld; e5.row_scale2 = rs; e5.row_split = B;
+  RC(gemm(c, c->Res2.p, c->Res2.ld, 0, Wd->w.p, Wd->w.ld, 0, 2 * B, c->E, c->W, e5));
+  colsum_kernel<<<(c->E + 31) / 32, dim3(32, 8), 0, c->st>>>(c->dH2.p, 2 * B, c->E, c->dH2.ld, nullptr,
+                                                            0x7fffffff, nullptr, be->g);   // dbe
+  CU(cudaGetLastError());
+  Epilogue e6;                                                                     // G6: dWe
+  e6.out = We->g; e6.ldo = We->w.ld;
+  RC(gemm(c, c->X2.p, c->X2.ld, 1, c->dH2.p, c->dH2.ld, 1, c->W, c->E, 2 * B, e6));
+  c->launches += 4;
+  return 0;
+}
+
+static int d_apply_impl(ganmf_ctx* c, float lr, float reg, int loss_slot) {
+  if (loss_slot < 0 || loss_slot >= c->losses_cap) return fail("loss slot out of range");
+  RC(adam_group(c, 0, c->n_d, adam_alpha(c, 0, lr), reg, -1));
+  finalize_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, reg, c->losses, loss_slot);
+  CU(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+static int ganmf_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float alpha) {
+  RC(forward_generator(c, ids_offset, B));
+  Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
+  Param& V = c->params[c->n_d + 1];
+  CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
+  Epilogue e2;                                                                     // G2 (real + fake codes)
+  e2.out = c->H2.p; e2.ldo = c->H2.ld; e2.bias = be->w.p;
+  RC(gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, 2 * B, c->E, c->W, e2));
+  Epilogue e3;                                                                     // G3': fake residual
+  e3.out = c->Res2.row(B); e3.ldo = c->Res2.ld; e3.bias = bd->w.p;
+  e3.c1 = c->X2.row(B); e3.ldc1 = c->X2.ld; e3.beta1 = -1.f;
+  e3.sumsq2 = c->sc->sumsq;
+  RC(gemm(c, c->H2.row(B), c->H2.ld, 0, Wd->w.p, Wd->w.ld, 1, B, c->W, c->E, e3));
+  sqdiff_kernel<<<std::min(B, 296), 256, 0, c->st>>>(c->H2.p, c->H2.row(B), B, c->E, c->H2.ld, &c->sc->fm);
+  CU(cudaGetLastError());
+  const double N = (double)n_global * c->W, M = (double)n_global * c->E;
+  const float c1 = (float)((1.0 - alpha) * 2.0 / N), c2 = (float)(alpha * 2.0 / M);
+  Epilogue e5;                                                                     // G5': dHf
+  e5.out = c->dH2.row(B); e5.ldo = c->dH2.ld; e5.alpha = c1;
+  e5.c1 = c->H2.row(B); e5.ldc1 = c->H2.ld; e5.beta1 = c2;
+  e5.c2 = c->H2.p; e5.ldc2 = c->H2.ld; e5.beta2 = -c2;
+  RC(gemm(c, c->Res2.row(B), c->Res2.ld, 0, Wd->w.p, Wd->w.ld, 0, B, c->E, c->W, e5));
+  Epilogue e7;                                                                     // G7: dF
+  e7.out = c->dF.p; e7.ldo = c->dF.ld;
+  e7.c1 = c->Res2.row(B); e7.ldc1 = c->Res2.ld; e7.beta1 = -c1;
+  RC(gemm(c, c->dH2.row(B), c->dH2.ld, 0, We->w.p, We->w.ld, 0, B, c->W, c->E, e7));
+  Epilogue e8;                                                                     // G8: dV
+  e8.out = V.g; e8.ldo = V.w.ld;
+  RC(gemm(c, c->dF.p, c->dF.ld, 1, c->Pb.p, c->Pb.ld, 1, c->W, c->k, B, e8));
+  Epilogue e9;                                                                     // G9: dPb
+  e9.out = c->dPb.p; e9.ldo = c->dPb.ld;
+  RC(gemm(c, c->dF.p, c->dF.ld, 0, V.w.p, V.w.ld, 1, B, c->k, c->W, e9));
+  c->launches += 1;
+  return 0;
+}
+
+static int g_apply_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float lr, float reg, float alpha,
+                        int loss_slot) {
+  if (loss_slot < 0 || loss_slot >= c->losses_cap) return fail("loss slot out of range");
+  if (c->cfg.kind == GANMF_KIND_GANMF)
+    gloss_kernel<<<1, 1, 0, c->st>>>(c->sc, alpha, (double)n_global * c->W, (double)n_global * c->E);
+  else
+    dis_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, 1, alpha, (double)n_global, (double)n_global * c->E);
+  CU(cudaGetLastError());
+  const int* ids = c->ids + ids_offset;
+  set_slots_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(c->slot, ids, B, 0);
+  CU(cudaGetLastError());
+  RC(adam_group(c, c->n_d, 2, adam_alpha(c, 1, lr), reg, c->n_d));
+  set_slots_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(c->slot, ids, B, 1);
+  CU(cudaGetLastError());
+  finalize_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, reg, c->losses, loss_slot);
+  CU(cudaGetLastError());
+  c->launches += 4;
+  return 0;
+}
+
+// ---- DisGANMF ------------------------------------------------------------------------------
+// discriminator on [float(id) | profile] for the stacked [real ; fake] rows (DisGANMF.py:57-65)
+static int dis_forward(ganmf_ctx* c, int ids_offset, int B) {
+  const int L = c->cfg.d_layers, H = c->cfg.d_nodes, act = c->cfg.d_act;
+  const int* ids = c->ids + ids_offset;
+  ids_to_float_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(ids, c->idf, B);
+  ids_to_float_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(ids, c->idf + B, B);
+  CU(cudaGetLastError());
+  if (c->cfg.row_id_offset != 0) return fail("row_id_offset for DisGANMF shards is not wired yet");
+  c->launches += 2;
+  for (int l = 0; l < L; ++l) {
+    Param& Wl = c->params[2 * l];
+    Param& bl = c->params[2 * l + 1];
+    Epilogue e;
+    e.out = c->hs[l].p; e.ldo = c->hs[l].ld; e.bias = bl.w.p; e.act = act;
+    if (l == 0) {
+      // x . W0 = profile . W0[1:, :] + id_f (x) W0[0, :]
+      e.r1_row = c->idf; e.r1_col = Wl.w.p;
+      RC(gemm(c, c->X2.p, c->X2.ld, 0, Wl.w.row(1), Wl.w.ld, 1, 2 * B, H, c->W, e));
+    } else {
+      RC(gemm(c, c->hs[l - 1].p, c->hs[l - 1].ld, 0, Wl.w.p, Wl.w.ld, 1, 2 * B, H, H, e));
+    }
+  }
+  Param& Wo = c->params[2 * L];
+  Param& bo = c->params[2 * L + 1];
+  Epilogue eo;
+  eo.out = c->out2; eo.ldo = 1; eo.bias = bo.w.p;
+  return gemm(c, c->hs[L - 1].p, c->hs[L - 1].ld, 0, Wo.w.p, Wo.w.ld, 1, 2 * B, 1, H, eo, GANMF_GEMM_SIMT);
+}
+
+// back-propagate dout2 (+ optional extra gradient already in dhtmp) through the MLP.
+// want_param_grads: accumulate into the D gradient buffers; want_dx: dF (fake half only).
+static int dis_backward(ganmf_ctx* c, int B, bool want_param_grads, bool extra_in_dhtmp, bool want_dx) {
+  const int L = c->cfg.d_layers, H = c->cfg.d_nodes, act = c->cfg.d_act;
+  Param& Wo = c->params[2 * L];
+  Param& bo = c->params[2 * L + 1];
+  const int R0 = want_param_grads ? 0 : B;          // G step only needs the fake rows
+  const int R = want_param_grads ? 2 * B : B;
+  if (want_param_grads) {
+    Epilogue e;                                       // dWo = feat^T . dout
+    e.out = Wo.g; e.ldo = Wo.w.ld;
+    RC(gemm(c, c->hs[L - 1].p, c->hs[L - 1].ld, 1, c->dout2, 1, 1, H, 1, 2 * B, e, GANMF_GEMM_SIMT));
+    colsum_kernel<<<1, dim3(32, 8), 0, c->st>>>(c->dout2, 2 * B, 1, 1, nullptr, 0x7fffffff, nullptr, bo.g);
+    CU(cudaGetLastError());
+    c->launches++;
+  }
+  // dh = dout . wo^T (+ extra)
+  Epilogue eh;
+  eh.out = c->dhtmp.row(R0); eh.ldo = c->dhtmp.ld;
+  if (extra_in_dhtmp) { eh.c1 = c->dhtmp.row(R0); eh.ldc1 = c->dhtmp.ld; eh.beta1 = 1.f; }
+  RC(gemm(c, c->dout2 + R0, 1, 0, Wo.w.p, Wo.w.ld, 0, R, H, 1, eh, GANMF_GEMM_SIMT));
+  for (int l = L - 1; l >= 0; --l) {
+    Param& Wl = c->params[2 * l];
+    Param& bl = c->params[2 * l + 1];
+    act_bwd_kernel<<<dim3((H + 127) / 128, R), 128, 0, c->st>>>(c->dhtmp.row(R0), c->hs[l].row(R0),
+                                                              c->dzs[l].row(R0), R, H, c->dhtmp.ld, act);
+    CU(cudaGetLastError());
+    c->launches++;
+    if (want_param_grads) {
+      if (l == 0) {
+        // dW0[1:, :] = profile^T . dz ; dW0[0, :] = sum_m id_f[m] dz[m, :]
+        Epilogue e;
+        e.out = Wl.g + Wl.w.ld; e.ldo = Wl.w.ld;
+        RC(gemm(c, c->X2.p, c->X2.ld, 1, c->dzs[0].p, c->dzs[0].ld, 1, c->W, H, 2 * B, e));
+        colsum_kernel<<<(H + 31) / 32, dim3(32, 8), 0, c->st>>>(c->dzs[0].p, 2 * B, H, c->dzs[0].ld, nullptr,
+                                                               0x7fffffff, c->idf, Wl.g);
+      } else {
+        Epilogue e;
+        e.out = Wl.g; e.ldo = Wl.w.ld;
+        RC(gemm(c, c->hs[l - 1].p, c->hs[l - 1].ld, 1, c->dzs[l].p, c->dzs[l].ld, 1, H, H, 2 * B, e));
+      }
+      colsum_kernel<<<(H + 31) / 32, dim3(32, 8), 0, c->st>>>(c->dzs[l].p, 2 * B, H, c->dzs[l].ld, nullptr,
+                                                             0x7fffffff, nullptr, bl.g);
+      CU(cudaGetLastError());
+      c->launches += 2;
+    }
+    if (l > 0) {
+      Epilogue e;                                     // dh_{l-1} = dz_l . W_l^T
+      e.out = c->dhtmp.row(R0); e.ldo = c->dhtmp.ld;
+      RC(gemm(c, c->dzs[l].row(R0), c->dzs[l].ld, 0, Wl.w.p, Wl.w.ld, 0, R, H, H, e));
+    } else if (want_dx) {
+      Epilogue e;                                     // dF = dz_0[fake] . W0[1:, :]^T
+      e.out = c->dF.p; e.ldo = c->dF.ld;
+      RC(gemm(c, c->dzs[0].row(B), c->dzs[0].ld, 0, Wl.w.row(1), Wl.w.ld, 0, B, c->W, H, e));
+    }
+  }
+  return 0;
+}
+
+static int dis_d_forward_impl(ganmf_ctx* c, int ids_offset, int B) {
+  RC(forward_generator(c, ids_offset, B));
+  CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
+  return dis_forward(c, ids_offset, B);
+}
+static int dis_d_backward_impl(ganmf_ctx* c, int B, int n_global) {
+  if (n_global != B) return fail("DisGANMF data-parallel normalisation is not wired yet");
+  bce_kernel<<<std::max(1, std::min(64, (2 * B + 255) / 256)), 256, 0, c->st>>>(c->out2, c->dout2, B, 0, c->sc);
+  dis_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, 0, 0.f, (double)n_global, 1.0);
+  CU(cudaGetLastError());
+  c->launches += 2;
+  return dis_backward(c, B, true, false, false);
+}
+static int dis_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float alpha) {
+  if (n_global != B) return fail("DisGANMF data-parallel normalisation is not wired yet");
+  const int L = c->cfg.d_layers, H = c->cfg.d_nodes;
+  RC(forward_generator(c, ids_offset, B));
+  CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
+  RC(dis_forward(c, ids_offset, B));
+  bce_kernel<<<std::max(1, std::min(64, (2 * B + 255) / 256)), 256, 0, c->st>>>(c->out2, c->dout2, B, 1, c->sc);
+  const Mat& ft = c->hs[L - 1];
+  sqdiff_kernel<<<std::min(B, 296), 256, 0, c->st>>>(ft.p, ft.row(B), B, H, ft.ld, &c->sc->fm);
+  CU(cudaGetLastError());
+  // extra gradient on the fake features: alpha * 2/(B*H) * (feat_f - feat_r) -> dhtmp[fake rows]
+  const float c2 = (float)(alpha * 2.0 / ((double)n_global * H));
+  axpby_kernel<<<dim3((H + 127) / 128, B), 128, 0, c->st>>>(ft.row(B), ft.p, c->dhtmp.row(B), B, H, ft.ld, c2,
+                                                           -c2);
+  CU(cudaGetLastError());
+  c->launches += 2;
+  RC(dis_backward(c, B, false, true, true));
+  Param& V = c->params[c->n_d + 1];
+  Epilogue e8;
+  e8.out = V.g; e8.ldo = V.w.ld;
+  RC(gemm(c, c->dF.p, c->dF.ld, 1, c->Pb.p, c->Pb.ld, 1, c->W, c->k, B, e8));
+  Epilogue e9;
+  e9.out = c->dPb.p; e9.ldo = c->dPb.ld;
+  return gemm(c, c->dF.p, c->dF.ld, 0, V.w.p, V.w.ld, 1, B, c->k, c->W, e9);
+}
+
+// ---- public step API -------------------------------------------------------------------------
+int ganmf_d_forward(ganmf_ctx* c, int ids_offset, int B) {
+  RC(check_batch(c, ids_offset, B));
+  return c->cfg.kind == GANMF_KIND_GANMF ? ganmf_d_forward_impl(c, ids_offset, B)
+                                         : dis_d_forward_impl(c, ids_offset, B);
+}
+int ganmf_d_backward(ganmf_ctx* c, int B, int n_global, float m_hinge) {
+  if (!c) return fail("null ctx");
+  return c->cfg.kind == GANMF_KIND_GANMF ? ganmf_d_backward_impl(c, B, n_global, m_hinge)
+                                         : dis_d_backward_impl(c, B, n_global);
+}
+int ganmf_d_apply(ganmf_ctx* c, float lr, float reg, int loss_slot) {
+  if (!c) return fail("null ctx");
+  return d_apply_impl(c, lr, reg, loss_slot);
+}
+int ganmf_g_forward_backward(ganmf_ctx* c, int ids_offset, int B, int n_global, float alpha) {
+  RC(check_batch(c, ids_offset, B));
+  c->last_ids_offset = ids_offset;
+  return c->cfg.kind == GANMF_KIND_GANMF ? ganmf_g_fb_impl(c, ids_offset, B, n_global, alpha)
+                                         : dis_g_fb_impl(c, ids_offset, B, n_global, alpha);
+}
+int ganmf_g_apply(ganmf_ctx* c, int B, int n_global, float lr, float reg, float alpha, int loss_slot) {
+  if (!c) return fail("null ctx");
+  return g_apply_impl(c, c->last_ids_offset, B, n_global, lr, reg, alpha, loss_slot);
+}
+int ganmf_d_step(ganmf_ctx* c, int ids_offset, int B, int n_global, float lr, float reg, float m_hinge,
+                 int loss_slot) {
+  RC(ganmf_d_forward(c, ids_offset, B));
+  RC(ganmf_d_backward(c, B, n_global, m_hinge));
+  return d_apply_impl(c, lr, reg, loss_slot);
+}
+int ganmf_g_step(ganmf_ctx* c, int ids_offset, int B, int n_global, float lr, float reg, float alpha,
+                 int loss_slot) {
+  RC(ganmf_g_forward_backward(c, ids_offset, B, n_global, alpha));
+  return g_apply_impl(c, ids_offset, B, n_global, lr, reg, alpha, loss_slot);
+}
+
+int ganmf_read_losses(ganmf_ctx* c, float* host, int n) {
+  if (!c || n < 0 || n > c->losses_cap) return fail("bad loss count");
+  CU(cudaMemcpyAsync(host, c->losses, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int ganmf_train_epoch(ganmf_ctx* c, const int32_t* perm, int n_ids, int batch, int d_steps, int g_steps,
+                      float d_lr, float g_lr, float d_reg, float g_reg, float m_hinge, float alpha,
+                      float* d_losses, float* g_losses) {
+  if (!c || !perm || n_ids <= 0 || batch <= 0) return fail("bad argument");
+  if (batch > c->B) return fail("batch_size %d exceeds max_batch %d", batch, c->B);
+  const int nb = (n_ids + batch - 1) / batch;
+  if ((long long)nb * (d_steps + g_steps) > c->losses_cap) return fail("loss log too small");
+  RC(ganmf_upload_ids(c, perm, n_ids));
+  int slot = 0;
+  for (int s = 0; s < d_steps; ++s)
+    for (int b = 0; b < nb; ++b) {
+      const int off = b * batch, B = std::min(batch, n_ids - off);
+      RC(ganmf_d_step(c, off, B, B, d_lr, d_reg, m_hinge, slot++));
+    }
+  const int n_d = slot;
+  for (int s = 0; s < g_steps; ++s)
+    for (int b = 0; b < nb; ++b) {
+      const int off = b * batch, B = std::min(batch, n_ids - off);
+      RC(ganmf_g_step(c, off, B, B, g_lr, g_reg, alpha, slot++));
+    }
+  std::vector<float> tmp((size_t)slot);
+  RC(ganmf_read_losses(c, tmp.data(), slot));
+  if (d_losses) memcpy(d_losses, tmp.data(), (size_t)n_d * 4);
+  if (g_losses) memcpy(g_losses, tmp.data() + n_d, (size_t)(slot - n_d) * 4);
+  return 0;
+}
+
+int ganmf_device_buffer(ganmf_ctx* c, const char* name, void** ptr, int64_t* n) {
+  if (!c || !name || !ptr || !n) return fail("null argument");
+  if (!strcmp(name, "d_grads")) { *ptr = c->d_slab + 3 * c->d_elems; *n = (int64_t)c->d_elems; return 0; }
+  if (!strcmp(name, "g_shared_grad")) { *ptr = c->v_slab + 3 * c->v_elems; *n = (int64_t)c->v_elems; return 0; }
+  if (!strcmp(name, "step_scalars")) { *ptr = c->sc; *n = 6; return 0; }
+  return fail("unknown buffer %s", name);
+}
+
+// ------------------------------------------------------------------------------ scoring / eval
+static int ensure_eval_buffers(ganmf_ctx* c, int block, int K, int n_cut) {
+  const int n_items = c->cfg.item_mode ? c->cfg.n_rows : c->W;
+  const int ild = rup(n_items, 32);
+  const size_t need = (size_t)block * ild;
+  if (need > c->scores_elems) {
+    cudaFree(c->scores);
+    RC(dalloc(&c->scores, need));
+    c->scores_elems = need;
+  }
+  if (c->Fb.rows < block) {
+    cudaFree(c->Fb.p);
+    RC(mat_alloc(&c->Fb, block, c->k));
+  }
+  if (c->eval_users_cap < block) {
+    cudaFree(c->eval_users);
+    RC(dalloc(&c->eval_users, (size_t)block));
+    c->eval_users_cap = block;
+  }
+  if ((size_t)block * K > c->topk_cap) {
+    cudaFree(c->topk_idx); cudaFree(c->topk_val);
+    RC(dalloc(&c->topk_idx, (size_t)block * K));
+    RC(dalloc(&c->topk_val, (size_t)block * K));
+    c->topk_cap = (size_t)block * K;
+  }
+  if (n_cut > 0) {
+    const size_t uv = (size_t)block * n_cut * MC_NCOL;
+    if (uv > c->uvals_cap) {
+      cudaFree(c->uvals);
+      RC(dalloc(&c->uvals, uv));
+      c->uvals_cap = uv;
+    }
+    const size_t ic = (size_t)n_cut * n_items;
+    if (ic > c->icounts_cap) {
+      cudaFree(c->icounts); cudaFree(c->usums); cudaFree(c->cut_dev);
+      RC(dalloc(&c->icounts, ic));
+      RC(dalloc(&c->usums, (size_t)64 * MC_NCOL));
+      RC(dalloc(&c->cut_dev, (size_t)64));
+      c->icounts_cap = ic;
+    }
+  }
+  return 0;
+}
+
+// scores[n, items] for the users already in c->eval_users (device)
+static int score_block(ganmf_ctx* c, int n) {
+  const Param& P = c->params[c->n_d];
+  const Param& V = c->params[c->n_d + 1];
+  const Param& rows_of = c->cfg.item_mode ? V : P;      // factors of the queried users
+  const Param& other = c->cfg.item_mode ? P : V;        // factors of the ranked items
+  const int n_items = other.w.rows;
+  gather_rows_kernel<<<n, 64, 0, c->st>>>(rows_of.w.p, c->eval_users, c->Fb.p, c->Fb.ld);
+  CU(cudaGetLastError());
+  c->launches++;
+  Epilogue e;
+  e.out = c->scores; e.ldo = rup(n_items, 32);
+  return gemm(c, c->Fb.p, c->Fb.ld, 0, other.w.p, other.w.ld, 0, n, n_items, c->k, e);
+}
+
+static int n_items_of(ganmf_ctx* c) { return c->cfg.item_mode ? c->cfg.n_rows : c->W; }
+static int n_users_of(ganmf_ctx* c) { return c->cfg.item_mode ? c->W : c->cfg.n_rows; }
+
+static int check_users(ganmf_ctx* c, const int32_t* u, int n) {
+  const int nu = n_users_of(c);
+  for (int i = 0; i < n; ++i)
+    if (u[i] < 0 || u[i] >= nu) return fail("user id %d outside [0, %d)", u[i], nu);
+  return 0;
+}
+
+int ganmf_score(ganmf_ctx* c, const int32_t* users, int n, float* scores_host) {
+  if (!c || !users || !scores_host || n <= 0) return fail("bad argument");
+  RC(check_users(c, users, n));
+  RC(ensure_eval_buffers(c, n, 1, 0));
+  const int n_items = n_items_of(c), ild = rup(n_items, 32);
+  CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+  RC(score_block(c, n));
+  CU(cudaMemcpy2DAsync(scores_host, (size_t)n_items * 4, c->scores, (size_t)ild * 4, (size_t)n_items * 4, n,
+                       cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+static int mask_and_topk(ganmf_ctx* c, int n, int n_items, int remove_seen, int K) {
+  if (K < 1 || K > TK_MAXK) return fail("top-K supports 1 <= K <= %d (got %d)", TK_MAXK, K);
+  const int ild = rup(n_items, 32);
+  if (remove_seen) {
+    const Csr& seen = c->csr[GANMF_CSR_SEEN];
+    if (!seen.indptr) return fail("seen CSR not set");
+    if (seen.n_cols != n_items) return fail("seen CSR has %d columns, scores have %d", seen.n_cols, n_items);
+    mask_seen_kernel<<<n, 128, 0, c->st>>>(c->scores, ild, c->eval_users, seen.indptr, seen.indices);
+    CU(cudaGetLastError());
+    c->launches++;
+  }
+  topk_rows_kernel<<<n, TK_THREADS, 0, c->st>>>(c->scores, ild, n_items, K, c->topk_idx, c->topk_val);
+  CU(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+int ganmf_mask_topk(ganmf_ctx* c, float* scores_host, int n, int n_items, const int32_t* users, int remove_seen,
+                    int K, int32_t* idx_host, float* val_host, int write_back) {
+  if (!c || !scores_host || n <= 0 || n_items <= 0) return fail("bad argument");
+  if (remove_seen && !users) return fail("user ids required for the seen mask");
+  const int ild = rup(n_items, 32);
+  const size_t need = (size_t)n * ild;
+  if (need > c->scores_elems) {
+    cudaFree(c->scores);
+    RC(dalloc(&c->scores, need));
+    c->scores_elems = need;
+  }
+  if (c->eval_users_cap < n) {
+    cudaFree(c->eval_users);
+    RC(dalloc(&c->eval_users, (size_t)n));
+    c->eval_users_cap = n;
+  }
+  if ((size_t)n * K > c->topk_cap) {
+    cudaFree(c->topk_idx); cudaFree(c->topk_val);
+    RC(dalloc(&c->topk_idx, (size_t)n * K));
+    RC(dalloc(&c->topk_val, (size_t)n * K));
+    c->topk_cap = (size_t)n * K;
+  }
+  CU(cudaMemcpy2DAsync(c->scores, (size_t)ild * 4, scores_host, (size_t)n_items * 4, (size_t)n_items * 4, n,
+                       cudaMemcpyHostToDevice, c->st));
+  if (users) CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+  RC(mask_and_topk(c, n, n_items, remove_seen, K));
+  CU(cudaMemcpyAsync(idx_host, c->topk_idx, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaMemcpyAsync(val_host, c->topk_val, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->st));
+  if (write_back)
+    CU(cudaMemcpy2DAsync(scores_host, (size_t)n_items * 4, c->scores, (size_t)ild * 4, (size_t)n_items * 4, n,
+                         cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int ganmf_recommend(ganmf_ctx* c, const int32_t* users, int n, int remove_seen, int K, int32_t* idx_host,
+                    float* val_host, float* masked_scores_host) {
+  if (!c || !users || n <= 0) return fail("bad argument");
+  RC(check_users(c, users, n));
+  RC(ensure_eval_buffers(c, n, K, 0));
+  const int n_items = n_items_of(c), ild = rup(n_items, 32);
+  CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+  RC(score_block(c, n));
+  RC(mask_and_topk(c, n, n_items, remove_seen, K));
+  CU(cudaMemcpyAsync(idx_host, c->topk_idx, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->st));
+  if (val_host) CU(cudaMemcpyAsync(val_host, c->topk_val, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->st));
+  if (masked_scores_host)
+    CU(cudaMemcpy2DAsync(masked_scores_host, (size_t)n_items * 4, c->scores, (size_t)ild * 4,
+                         (size_t)n_items * 4, n, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+template <typename T>
+static int upload(T** dev, const T* host, size_t n) {
+  cudaFree(*dev);
+  RC(dalloc(dev, n));
+  CU(cudaMemcpy(*dev, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int ganmf_set_eval_tables(ganmf_ctx* c, const float* gain, const float* gain_desc, const float* logtab,
+                          int logtab_n, const double* nov, const uint8_t* haspop, const double* popn) {
+  if (!c) return fail("null ctx");
+  const Csr& te = c->csr[GANMF_CSR_TEST];
+  if (!te.indptr) return fail("test CSR not set");
+  if (logtab_n < TK_MAXK) return fail("logtab needs >= %d entries", TK_MAXK);
+  const int n_items = te.n_cols;
+  RC(upload(&c->tb_gain, gain, (size_t)te.nnz));
+  RC(upload(&c->tb_gain_desc, gain_desc, (size_t)te.nnz));
+  RC(upload(&c->tb_logtab, logtab, (size_t)logtab_n));
+  RC(upload(&c->tb_nov, nov, (size_t)n_items));
+  RC(upload(&c->tb_popn, popn, (size_t)n_items));
+  RC(upload((uint8_t**)&c->tb_haspop, haspop, (size_t)n_items));
+  cudaFree(c->rmse_scratch);
+  RC(dalloc(&c->rmse_scratch, (size_t)te.nnz));
+  c->tb.test_indptr = te.indptr; c->tb.test_indices = te.indices;
+  c->tb.test_gain = c->tb_gain; c->tb.test_gain_desc = c->tb_gain_desc; c->tb.logtab = c->tb_logtab;
+  c->tb.item_novelty = c->tb_nov; c->tb.item_has_pop = c->tb_haspop; c->tb.item_popnorm = c->tb_popn;
+  c->have_tables = true;
+  return 0;
+}
+
+// metric stage for n rows whose lists are in c->topk_idx and users in c->eval_users
+static int metrics_block(ganmf_ctx* c, int n, int K, int n_cut, int n_items, bool with_rmse) {
+  const int total = n * n_cut;
+  user_metrics_kernel<<<(total + 127) / 128, 128, 0, c->st>>>(c->topk_idx, K, c->eval_users, n, c->cut_dev,
+                                                            n_cut, c->tb, c->uvals, c->icounts, n_items);
+  CU(cudaGetLastError());
+  if (with_rmse) {
+    const Csr& te = c->csr[GANMF_CSR_TEST];
+    user_rmse_kernel<<<(n + 63) / 64, 64, 0, c->st>>>(c->scores, rup(n_items, 32), c->eval_users, n, n_cut,
+                                                    c->tb, te.data, c->rmse_scratch, c->uvals);
+    CU(cudaGetLastError());
+    c->launches++;
+  }
+  const int ncols = n_cut * MC_NCOL;
+  ordered_accumulate_kernel<<<(ncols + 63) / 64, 64, 0, c->st>>>(c->uvals, n, ncols, c->usums);
+  CU(cudaGetLastError());
+  c->launches += 2;
+  return 0;
+}
+
+static int eval_prologue(ganmf_ctx* c, const int32_t* cutoffs, int n_cut, int* Kout) {
+  if (!c->have_tables) return fail("call ganmf_set_eval_tables first");
+  if (n_cut < 1 || n_cut > 32) return fail("1..32 cutoffs supported");
+  int K = 0;
+  for (int i = 0; i < n_cut; ++i) K = std::max(K, cutoffs[i]);
+  if (K > TK_MAXK) return fail("cutoff %d > %d", K, TK_MAXK);
+  *Kout = K;
+  return 0;
+}
+
+int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_t* cutoffs, int n_cut,
+                   int remove_seen, int block, double* sums_host, int64_t* counts_host) {
+  if (!c || !users || !cutoffs || !sums_host || n_users < 0) return fail("bad argument");
+  int K;
+  RC(eval_prologue(c, cutoffs, n_cut, &K));
+  RC(check_users(c, users, n_users));
+  const int n_items = n_items_of(c);
+  if (c->csr[GANMF_CSR_TEST].n_cols != n_items) return fail("test CSR column count mismatch");
+  if (!c->csr[GANMF_CSR_TEST].data) return fail("test CSR needs ratings (data) for RMSE");
+  if (block <= 0) block = std::min(1000, std::max(1, (int)(1e8 / n_items)));   // Evaluator.py:238
+  block = std::min(block, std::max(n_users, 1));
+  RC(ensure_eval_buffers(c, block, K, n_cut));
+  CU(cudaMemcpyAsync(c->cut_dev, cutoffs, (size_t)n_cut * 4, cudaMemcpyHostToDevice, c->st));
+  CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
+  CU(cudaMemsetAsync(c->icounts, 0, (size_t)n_cut * n_items * 4, c->st));
+  for (int s = 0; s < n_users; s += block) {
+    const int n = std::min(block, n_users - s);
+    CU(cudaMemcpyAsync(c->eval_users, users + s, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    RC(score_block(c, n));
+    RC(mask_and_topk(c, n, n_items, remove_seen, K));
+    RC(metrics_block(c, n, K, n_cut, n_items, true));
+  }
+  CU(cudaMemcpyAsync(sums_host, c->usums, (size_t)n_cut * MC_NCOL * 8, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (counts_host) {
+    std::vector<int> tmp((size_t)n_cut * n_items);
+    CU(cudaMemcpy(tmp.data(), c->icounts, tmp.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < tmp.size(); ++i) counts_host[i] = tmp[i];
+  }
+  return 0;
+}
+
+int ganmf_metrics_from_topk(ganmf_ctx* c, const int32_t* topk, int K, const int32_t* users, int n,
+                            const int32_t* cutoffs, int n_cut, double* per_user, double* sums_host,
+                            int64_t* counts_host) {
+  if (!c || !topk || !users || !cutoffs || !sums_host || n <= 0) return fail("bad argument");
+  int Kmax;
+  RC(eval_prologue(c, cutoffs, n_cut, &Kmax));
+  if (K < Kmax) return fail("lists have K=%d < largest cutoff %d", K, Kmax);
+  const int n_items = c->csr[GANMF_CSR_TEST].n_cols;
+  // buffers sized without touching the model's score workspace
+  if (c->eval_users_cap < n) {
+    cudaFree(c->eval_users);
+    RC(dalloc(&c->eval_users, (size_t)n));
+    c->eval_users_cap = n;
+  }
+  if ((size_t)n * K > c->topk_cap) {
+    cudaFree(c->topk_idx); cudaFree(c->topk_val);
+    RC(dalloc(&c->topk_idx, (size_t)n * K));
+    RC(dalloc(&c->topk_val, (size_t)n * K));
+    c->topk_cap = (size_t)n * K;
+  }
+  const size_t uv = (size_t)n * n_cut * MC_NCOL;
+  if (uv > c->uvals_cap) {
+    cudaFree(c->uvals);
+    RC(dalloc(&c->uvals, uv));
+    c->uvals_cap = uv;
+  }
+  const size_t ic = (size_t)n_cut * n_items;
+  if (ic > c->icounts_cap) {
+    cudaFree(c->icounts); cudaFree(c->usums); cudaFree(c->cut_dev);
+    RC(dalloc(&c->icounts, ic));
+    RC(dalloc(&c->usums, (size_t)64 * MC_NCOL));
+    RC(dalloc(&c->cut_dev, (size_t)64));
+    c->icounts_cap = ic;
+  }
+  CU(cudaMemcpyAsync(c->cut_dev, cutoffs, (size_t)n_cut * 4, cudaMemcpyHostToDevice, c->st));
+  CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+  CU(cudaMemcpyAsync(c->topk_idx, topk, (size_t)n * K * 4, cudaMemcpyHostToDevice, c->st));
+  CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
+  CU(cudaMemsetAsync(c->icounts, 0, ic * 4, c->st));
+  CU(cudaMemsetAsync(c->uvals, 0, uv * 8, c->st));
+  RC(metrics_block(c, n, K, n_cut, n_items, false));
+  CU(cudaMemcpyAsync(sums_host, c->usums, (size_t)n_cut * MC_NCOL * 8, cudaMemcpyDeviceToHost, c->st));
+  if (per_user) CU(cudaMemcpyAsync(per_user, c->uvals, uv * 8, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (counts_host) {
+    std::vector<int> tmp(ic);
+    CU(cudaMemcpy(tmp.data(), c->icounts, ic * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < ic; ++i) counts_host[i] = tmp[i];
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ primitives
+int ganmf_k_gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, int M, int N,
+                 int K, float* out, int ldo, int path) {
+  if (!c) return fail("null ctx");
+  Epilogue e;
+  e.out = out; e.ldo = ldo;
+  return gemm(c, A, lda, a_mn, B, ldb, b_mn, M, N, K, e, path);
+}
+int ganmf_k_csr_gather_dense(ganmf_ctx* c, int ids_offset, int B, float* out, int ld) {
+  if (!c) return fail("null ctx");
+  const Csr& tr = c->csr[GANMF_CSR_TRAIN];
+  if (!tr.indptr) return fail("train CSR not set");
+  if (ld < c->W || (ld & 3)) return fail("ld must be >= width and a multiple of 4");
+  c->launches++;
+  CU(csr_gather_dense(tr.indptr, tr.indices, tr.data, c->ids + ids_offset, B, out, ld, 0, c->st));
+  return 0;
+}
+int ganmf_k_adam(ganmf_ctx* c, float* theta, float* m, float* v, const float* g, int64_t n, float alpha,
+                 float reg) {
+  if (!c || (n & 3)) return fail("n must be a multiple of 4");
+  AdamArgs a;
+  memset(&a, 0, sizeof a);
+  a.nseg = 1;
+  a.seg[0].theta = theta; a.seg[0].m = m; a.seg[0].v = v; a.seg[0].g = g; a.seg[0].n4 = (unsigned long long)n / 4;
+  a.seg[0].ld = 4;
+  a.alpha = alpha; a.reg = reg; a.l2_out = nullptr;
+  c->launches++;
+  CU(fused_adam(a, c->st));
+  return 0;
+}
+int ganmf_k_topk(ganmf_ctx* c, const float* scores, int ld, int n, int n_items, int K, int32_t* idx, float* val) {
+  if (!c || K < 1 || K > TK_MAXK) return fail("bad K");
+  topk_rows_kernel<<<n, TK_THREADS, 0, c->st>>>(scores, ld, n_items, K, idx, val);
+  CU(cudaGetLastError());
+  c->launches++;
+  return 0;
+}

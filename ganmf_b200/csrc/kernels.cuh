@@ -283,15 +283,6 @@ __global__ void finalize_loss_kernel(const StepScalars* s, float reg, float* los
 }
 
 // ----------------------------------------------------------------------------- activations
-enum Act { ACT_LINEAR = 0, ACT_TANH = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
-__device__ __forceinline__ float act_fwd(int act, float z) {
-  switch (act) {
-    case ACT_TANH: return tanhf(z);
-    case ACT_RELU: return fmaxf(z, 0.f);
-    case ACT_SIGMOID: return 1.f / (1.f + expf(-z));
-    default: return z;
-  }
-}
 __device__ __forceinline__ float act_bwd_from_out(int act, float h) {
   switch (act) {
     case ACT_TANH: return 1.f - h * h;
@@ -309,6 +300,12 @@ __global__ void act_fwd_kernel(float* X, int M, int N, int ld, int act) {
 __global__ void act_bwd_kernel(const float* dH, const float* H, float* dZ, int M, int N, int ld, int act) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
   if (n < N) dZ[(size_t)m * ld + n] = dH[(size_t)m * ld + n] * act_bwd_from_out(act, H[(size_t)m * ld + n]);
+}
+
+// Z = a*X + b*Y over [M, N] (same ld)
+__global__ void axpby_kernel(const float* X, const float* Y, float* Z, int M, int N, int ld, float a, float b) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+  if (n < N) Z[(size_t)m * ld + n] = a * X[(size_t)m * ld + n] + b * Y[(size_t)m * ld + n];
 }
 
 // DisGANMF output losses and their gradients (DisGANMF.py:114-117).
@@ -344,15 +341,10 @@ __global__ void dis_loss_kernel(StepScalars* s, int mode, float alpha, double B,
 // Exact-fp32 (FMA) GEMM with the same epilogue as the tensor-core kernel, for shapes where a
 // 128-wide MMA tile would be almost empty (DisGANMF layers with 1..64 units, out layer N=1).
 // A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk].
-struct SimtExtra {
-  const float* r1_row = nullptr;   // rank-1 term: v += r1_row[m] * r1_col[n]
-  const float* r1_col = nullptr;
-  int act = ACT_LINEAR;            // applied last
-};
 constexpr int SG_T = 64, SG_K = 16;
 __global__ void __launch_bounds__(256)
 simt_gemm_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B,
-                 long long sbn, long long sbk, int M, int N, int K, Epilogue ep, SimtExtra ex) {
+                 long long sbn, long long sbk, int M, int N, int K, Epilogue ep) {
   __shared__ float sA[SG_K][SG_T + 1], sB[SG_K][SG_T + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
@@ -392,10 +384,7 @@ simt_gemm_kernel(const float* __restrict__ A, long long sam, long long sak, cons
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
-      float a = acc[i][j];
-      if (ex.r1_row) a = fmaf(ex.r1_row[m], ex.r1_col[n], a);   // part of the contraction (concat column)
-      float v = apply_epilogue(ep, a, m, n, rs);
-      v = act_fwd(ex.act, v);
+      const float v = apply_epilogue(ep, acc[i][j], m, n, rs);
       ep.out[(size_t)m * ep.ldo + n] = v;
       if (m < ep.row_split) sq0 += v * v; else sq1 += v * v;
     }
@@ -411,11 +400,11 @@ simt_gemm_kernel(const float* __restrict__ A, long long sam, long long sak, cons
 }
 
 inline cudaError_t simt_gemm(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, int M,
-                             int N, int K, const Epilogue& ep, const SimtExtra& ex, cudaStream_t st) {
+                             int N, int K, const Epilogue& ep, cudaStream_t st) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   dim3 grid((N + SG_T - 1) / SG_T, (M + SG_T - 1) / SG_T);
   simt_gemm_kernel<<<grid, 256, 0, st>>>(A, a_mn ? 1 : lda, a_mn ? lda : 1, B, b_mn ? 1 : ldb,
-                                         b_mn ? ldb : 1, M, N, K, ep, ex);
+                                         b_mn ? ldb : 1, M, N, K, ep);
   return cudaGetLastError();
 }
 

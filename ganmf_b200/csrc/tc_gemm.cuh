@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 #include <stdio.h>
 #include "ptx.cuh"
 
@@ -29,8 +30,19 @@ constexpr int TC_BK = 32;          // fp32 elements of K per stage (128 bytes)
 constexpr int TC_UMMA_K = 8;       // tf32: 32 bytes of K per instruction
 constexpr int TC_THREADS = 192;
 
+enum Act { ACT_LINEAR = 0, ACT_TANH = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
+__device__ __forceinline__ float act_fwd(int act, float z) {
+  switch (act) {
+    case ACT_TANH: return tanhf(z);
+    case ACT_RELU: return fmaxf(z, 0.f);
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+    default: return z;
+  }
+}
+
 // Fused epilogue applied to every accumulator element (m, n):
-//   v = alpha * rs(m) * acc + bias[n] + beta1 * C1[m,n] + beta2 * C2[m,n]
+//   acc' = acc + r1_row[m] * r1_col[n]        (rank-1 term: the id column of DisGANMF's concat input)
+//   v = act( alpha * rs(m) * acc' + bias[n] + beta1 * C1[m,n] + beta2 * C2[m,n] )
 //   rs(m) = row_scale2 ? row_scale2[m >= row_split] : 1      (device-side scalars:
 //           the hinge-gate coefficients are only known on the device)
 //   out[m,n] = round_out ? rna_tf32(v) : v
@@ -50,6 +62,9 @@ struct Epilogue {
   float beta2 = 0.f;
   int round_out = 0;
   double* sumsq2 = nullptr;
+  const float* r1_row = nullptr;
+  const float* r1_col = nullptr;
+  int act = ACT_LINEAR;
 };
 
 struct TcGemmArgs {
@@ -67,10 +82,12 @@ struct TcGemmArgs {
 
 __device__ __forceinline__ float apply_epilogue(const Epilogue& ep, float acc, int m, int n,
                                                 float rs) {
+  if (ep.r1_row) acc = fmaf(__ldg(ep.r1_row + m), __ldg(ep.r1_col + n), acc);
   float v = ep.alpha * rs * acc;
   if (ep.bias) v += __ldg(ep.bias + n);
   if (ep.c1) v += ep.beta1 * __ldg(ep.c1 + (size_t)m * ep.ldc1 + n);
   if (ep.c2) v += ep.beta2 * __ldg(ep.c2 + (size_t)m * ep.ldc2 + n);
+  if (ep.act != ACT_LINEAR) v = act_fwd(ep.act, v);
   if (ep.round_out) v = ptx::round_tf32(v);
   return v;
 }

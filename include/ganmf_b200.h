@@ -1,0 +1,159 @@
+/* ganmf_b200 -- C ABI of the B200-native GANMF / DisGANMF hot path.
+ *
+ * Drop-in boundary.  The reference (edervishaj/GANMF) is Python over TensorFlow 1.12; the
+ * "FFI" it crosses for this path is tf.Session.run() on the graph built in
+ *   GANRec/GANMF.py:53-139 / GANRec/DisGANMF.py:51-140           (build + losses + minimize)
+ * plus numpy inside Base/BaseRecommender.py:155-247 (recommend) and the Python loop of
+ *   Base/Evaluation/Evaluator.py:234-414 (EvaluatorHoldout).
+ * Each entry point below names the reference call it replaces.  Plain pointers and sizes only;
+ * all *_host pointers are host memory, everything else lives in the context on the GPU.
+ * Every function returns 0 on success, non-zero on error (ganmf_last_error() has the text).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Storage convention: matrices are row-major fp32 [rows][cols]; inside the context they are
+ * padded to a leading dimension of roundup(cols, 32) floats, at the ABI they are dense.
+ */
+#ifndef GANMF_B200_H
+#define GANMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ganmf_ctx ganmf_ctx;
+
+enum { GANMF_KIND_GANMF = 0, GANMF_KIND_DISGANMF = 1 };
+enum { GANMF_ACT_LINEAR = 0, GANMF_ACT_TANH = 1, GANMF_ACT_RELU = 2, GANMF_ACT_SIGMOID = 3 };
+enum { GANMF_CSR_TRAIN = 0,   /* rows of the TRAINING orientation (items x users in --item mode) */
+       GANMF_CSR_SEEN = 1,    /* users x items, masks seen items in recommend()                   */
+       GANMF_CSR_TEST = 2 };  /* users x items held-out interactions (evaluator)                  */
+enum { GANMF_GEMM_AUTO = 0, GANMF_GEMM_SIMT = 1, GANMF_GEMM_TC = 2 };
+
+/* Per-(user, cutoff) metric columns produced by the device evaluator. */
+enum { GANMF_MC_PRECISION = 0, GANMF_MC_RECALL, GANMF_MC_PRMD, GANMF_MC_MAP, GANMF_MC_NDCG,
+       GANMF_MC_MRR, GANMF_MC_ARHR, GANMF_MC_ROC_AUC, GANMF_MC_HIT, GANMF_MC_NOVELTY,
+       GANMF_MC_AVGPOP, GANMF_MC_COVERED, GANMF_MC_RMSE, GANMF_MC_NCOL };
+
+typedef struct ganmf_config {
+  int kind;            /* GANMF_KIND_*                                                         */
+  int n_rows;          /* rows of the training matrix held by THIS context (user shard)         */
+  int width;           /* profile width (columns of the training matrix)                        */
+  int num_factors;     /* k            (GANMF.py:53 build(num_factors, emb_dim))                */
+  int emb_dim;         /* GANMF: autoencoder code size E                                        */
+  int d_layers;        /* DisGANMF: hidden layers          (DisGANMF.py:51)                     */
+  int d_nodes;         /* DisGANMF: units per hidden layer                                      */
+  int d_act;           /* DisGANMF: GANMF_ACT_*                                                 */
+  int max_batch;       /* largest minibatch (rows per step on this GPU)                         */
+  int item_mode;       /* 1: rows are items; scoring uses V[u] . P^T (GANMF.py:288-290)         */
+  int row_id_offset;   /* global id of local row 0 (data-parallel shards; DisGANMF id feature)  */
+  int device;          /* CUDA device ordinal                                                   */
+  int gemm_path;       /* GANMF_GEMM_*; AUTO picks tcgen05 unless the shape is tiny             */
+} ganmf_config;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+const char* ganmf_last_error(void);
+int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out);       /* ~ GANMF.build + Session   */
+void ganmf_destroy(ganmf_ctx* ctx);
+int ganmf_set_stream(ganmf_ctx* ctx, void* cuda_stream);          /* cudaStream_t, NULL = default */
+int ganmf_synchronize(ganmf_ctx* ctx);
+
+/* ---- data ------------------------------------------------------------------------------- */
+/* ~ URM_train[uids].toarray() source (GANMF.py:184) / seen filter (BaseRecommender.py:93-100) /
+ *   URM_test (Evaluator.py:196-207).  data_host may be NULL (all ones).  Indices of a row must be
+ *   sorted for GANMF_CSR_TEST. */
+int ganmf_set_csr(ganmf_ctx* ctx, int which, int n_rows, int n_cols, const int32_t* indptr_host,
+                  const int32_t* indices_host, const float* data_host);
+
+/* ---- parameters (TF variable names, GANMF.py:119-121 / DisGANMF.py:58-64) ---------------- */
+int ganmf_param_count(ganmf_ctx* ctx);
+int ganmf_param_info(ganmf_ctx* ctx, int i, char* name_out, int name_cap, int* rows, int* cols,
+                     int* is_generator);
+int ganmf_set_param(ganmf_ctx* ctx, const char* name, const float* host, int64_t count);
+int ganmf_get_param(ganmf_ctx* ctx, const char* name, float* host, int64_t count);
+int ganmf_init_params(ganmf_ctx* ctx, uint64_t seed);   /* glorot_uniform + zero biases (GANMF.py:57) */
+int ganmf_reset_optimizers(ganmf_ctx* ctx);             /* zero Adam moments, t = 0 (new fit())      */
+int ganmf_snapshot(ganmf_ctx* ctx);                     /* save_current_model (GANMF.py:249-251)     */
+int ganmf_restore(ganmf_ctx* ctx);                      /* load_model         (GANMF.py:253-255)     */
+
+/* ---- training --------------------------------------------------------------------------- */
+/* One sess.run([dtrain, dloss]) / sess.run([gtrain, gloss]) (GANMF.py:186-187,200-201;
+ * DisGANMF.py:187-188,201).  row_ids are LOCAL row indices already resident on the device
+ * (ganmf_upload_ids) at offset ids_offset.  The loss goes to the device-side loss log at
+ * loss_slot; nothing is copied back, nothing synchronises.  n_rows_global is the row count of the
+ * whole (all-GPU) minibatch: it normalises the mean losses under data parallelism.
+ * m_hinge is ignored by DisGANMF. */
+int ganmf_upload_ids(ganmf_ctx* ctx, const int32_t* ids_host, int n);
+int ganmf_d_step(ganmf_ctx* ctx, int ids_offset, int B, int n_rows_global, float lr, float reg,
+                 float m_hinge, int loss_slot);
+int ganmf_g_step(ganmf_ctx* ctx, int ids_offset, int B, int n_rows_global, float lr, float reg,
+                 float recon_coefficient, int loss_slot);
+/* The same steps cut at the points where data-parallel ranks must exchange sums:
+ *   d_forward -> allreduce(step scalars) -> d_backward -> allreduce(d grads) -> d_apply
+ *   g_forward_backward -> allreduce(g shared grad + step scalars) -> g_apply */
+int ganmf_d_forward(ganmf_ctx* ctx, int ids_offset, int B);
+int ganmf_d_backward(ganmf_ctx* ctx, int B, int n_rows_global, float m_hinge);
+int ganmf_d_apply(ganmf_ctx* ctx, float lr, float reg, int loss_slot);
+int ganmf_g_forward_backward(ganmf_ctx* ctx, int ids_offset, int B, int n_rows_global,
+                             float recon_coefficient);
+int ganmf_g_apply(ganmf_ctx* ctx, int B, int n_rows_global, float lr, float reg,
+                  float recon_coefficient, int loss_slot);
+/* One epoch of the reference schedule (GANMF.py:172-203): shuffled row ids in, d_steps full D
+ * passes then g_steps full G passes over the same batches, per-batch losses out (host).
+ * H2D: n_rows ids; D2H: the losses.  Synchronises once at the end. */
+int ganmf_train_epoch(ganmf_ctx* ctx, const int32_t* perm_host, int n_ids, int batch_size,
+                      int d_steps, int g_steps, float d_lr, float g_lr, float d_reg, float g_reg,
+                      float m_hinge, float recon_coefficient, float* d_losses_host,
+                      float* g_losses_host);
+int ganmf_read_losses(ganmf_ctx* ctx, float* host, int n);        /* loss log [0, n) -> host    */
+/* Raw device buffers for the collectives (wrap with __cuda_array_interface__; fp32 unless noted):
+ * "d_grads" (all discriminator gradients, contiguous), "g_shared_grad" (item-factor gradient),
+ * "step_scalars" (6 float64: sumsq_real, sumsq_fake, feature-matching, l2, bce_real, bce_fake). */
+int ganmf_device_buffer(ganmf_ctx* ctx, const char* name, void** dev_ptr, int64_t* n_elems);
+
+/* ---- scoring / recommendation / evaluation ---------------------------------------------- */
+/* ~ _compute_item_score (GANMF.py:285-292): scores_host[n][n_items], user ids in scoring
+ * orientation.  H2D: ids; D2H: n * n_items floats. */
+int ganmf_score(ganmf_ctx* ctx, const int32_t* user_ids_host, int n, float* scores_host);
+/* ~ BaseRecommender.recommend (:155-247) on a given fp32 score matrix: optional seen mask from
+ * GANMF_CSR_SEEN, then top-K (descending score, ties -> lowest index).  idx = -1 where the score is
+ * -inf.  scores_host is updated in place with the mask when write_back != 0. */
+int ganmf_mask_topk(ganmf_ctx* ctx, float* scores_host, int n, int n_items,
+                    const int32_t* user_ids_host, int remove_seen, int K, int32_t* idx_host,
+                    float* val_host, int write_back);
+/* score -> mask -> top-K without leaving the device; only ids/values come back. */
+int ganmf_recommend(ganmf_ctx* ctx, const int32_t* user_ids_host, int n, int remove_seen, int K,
+                    int32_t* idx_host, float* val_host, float* masked_scores_host /* nullable */);
+/* ~ EvaluatorHoldout._run_evaluation_on_selected_users (Evaluator.py:234-357): for the given users
+ * (ascending, each with >= 1 test item) computes, per cutoff, float64 sums over users IN ORDER of
+ * the GANMF_MC_* columns, and per-item recommendation counts.  Tables: see ganmf_set_eval_tables.
+ * sums_host[n_cutoffs][GANMF_MC_NCOL]; item_counts_host[n_cutoffs][n_items] (nullable). */
+int ganmf_set_eval_tables(ganmf_ctx* ctx, const float* test_gain_host, const float* test_gain_desc_host,
+                          const float* logtab_host, int logtab_n, const double* item_novelty_host,
+                          const uint8_t* item_has_pop_host, const double* item_popnorm_host);
+int ganmf_evaluate(ganmf_ctx* ctx, const int32_t* user_ids_host, int n_users, const int32_t* cutoffs_host,
+                   int n_cutoffs, int remove_seen, int block_size, double* sums_host,
+                   int64_t* item_counts_host);
+/* Same metric stage on caller-supplied top-K lists (bit-exact contract tests). */
+int ganmf_metrics_from_topk(ganmf_ctx* ctx, const int32_t* topk_idx_host, int K,
+                            const int32_t* user_ids_host, int n_users, const int32_t* cutoffs_host,
+                            int n_cutoffs, double* per_user_host /* [n][n_cut][NCOL] nullable */,
+                            double* sums_host, int64_t* item_counts_host);
+
+/* ---- primitive kernels (unit tests, ncu) ------------------------------------------------- */
+/* All pointers are DEVICE pointers here. */
+int ganmf_k_gemm(ganmf_ctx* ctx, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn,
+                 int M, int N, int K, float* out, int ldo, int path);
+int ganmf_k_csr_gather_dense(ganmf_ctx* ctx, int ids_offset, int B, float* out, int ld);
+int ganmf_k_adam(ganmf_ctx* ctx, float* theta, float* m, float* v, const float* g, int64_t n,
+                 float alpha, float reg);
+int ganmf_k_topk(ganmf_ctx* ctx, const float* scores, int ld, int n, int n_items, int K,
+                 int32_t* idx, float* val);
+/* number of kernels this library has launched since ganmf_create (bench.py's gpu_launches) */
+int64_t ganmf_launch_count(ganmf_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANMF_B200_H */

@@ -1,0 +1,127 @@
+"""Kernel-level parity on the B200 (through the C ABI): GEMM (tcgen05 and SIMT) vs fp64, CSR gather
+vs scipy, fused Adam vs the oracle's TF-Adam, top-k vs the oracle (bit-exact, ties -> lowest index)."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    e = Engine(L.KIND_GANMF, 64, 96, 8, emb_dim=8, max_batch=16)
+    yield e
+    e.close()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rup(x, a=32):
+    return (x + a - 1) // a * a
+
+
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("shape", [(200, 300, 100), (64, 3706, 250), (257, 130, 1100), (128, 4, 3000)])
+def test_gemm_paths_match_fp64(eng, a_mn, b_mn, shape):
+    from ganmf_b200 import _lib as L
+    M, N, K = shape
+    rs = np.random.RandomState(M + N + K + a_mn * 2 + b_mn)
+    A = rs.standard_normal((M, K)).astype(np.float32)
+    B = rs.standard_normal((N, K)).astype(np.float32)
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+
+    def padded(x):          # row-major with ld = roundup(cols, 32), padding poisoned
+        out = np.full((x.shape[0], rup(x.shape[1])), 1e30, dtype=np.float32)
+        out[:, :x.shape[1]] = x
+        return out
+    As = padded(A.T if a_mn else A)
+    Bs = padded(B.T if b_mn else B)
+    dA, dB = dev(As), dev(Bs)
+    ldo = rup(N)
+    for path, tol in ((L.GEMM_SIMT, 2e-6), (L.GEMM_TC, 2e-3)):
+        out = torch.zeros((M, ldo), dtype=torch.float32, device="cuda")
+        L.check(eng.lib.ganmf_k_gemm(eng.ctx, dA.data_ptr(), As.shape[1], a_mn, dB.data_ptr(), Bs.shape[1], b_mn,
+                                     M, N, K, out.data_ptr(), ldo, path))
+        got = out.cpu().numpy()[:, :N].astype(np.float64)
+        scale = np.sqrt(K)          # |A||B| row norms ~ sqrt(K)
+        assert np.max(np.abs(got - want)) / scale < tol, (path, np.max(np.abs(got - want)) / scale)
+        assert np.all(out.cpu().numpy()[:, N:] == 0)      # padding columns untouched
+
+
+def test_csr_gather_dense_matches_scipy():
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    rs = np.random.RandomState(0)
+    for n_rows, width, B in [(300, 3706, 64), (50, 70, 24), (40, 5000, 7)]:
+        urm = sps.random(n_rows, width, 0.05, format="csr", dtype=np.float32, random_state=rs)
+        urm.data[:] = rs.randint(1, 6, size=urm.nnz)
+        e = Engine(L.KIND_GANMF, n_rows, width, 4, emb_dim=4, max_batch=B)
+        e.set_csr(L.CSR_TRAIN, urm)
+        ids = rs.permutation(n_rows)[:B].astype(np.int32)
+        e.upload_ids(ids)
+        ld = rup(width)
+        out = torch.full((B, ld), 7.0, dtype=torch.float32, device="cuda")
+        L.check(e.lib.ganmf_k_csr_gather_dense(e.ctx, 0, B, out.data_ptr(), ld))
+        got = out.cpu().numpy()
+        assert np.array_equal(got[:, :width], urm[ids].toarray())
+        assert np.all(got[:, width:] == 0)
+        e.close()
+
+
+def test_fused_adam_matches_tf_adam_oracle(eng):
+    from ganmf_b200 import _lib as L
+    from oracle.train_oracle import TFAdam
+    rs = np.random.RandomState(1)
+    n = 4096 + 64
+    theta = rs.standard_normal(n).astype(np.float32) * 0.05
+    params = {"w": theta.copy()}
+    opt = TFAdam(params, ["w"], 1e-3, np.float32)
+    t, m, v = dev(theta), dev(np.zeros(n, np.float32)), dev(np.zeros(n, np.float32))
+    b1p, b2p = np.float32(0.9), np.float32(0.999)
+    reg = 1e-2
+    for step in range(20):
+        g = rs.standard_normal(n).astype(np.float32) * (0.1 if step % 3 else 1e-4)
+        alpha = np.float32(np.float32(1e-3) * np.sqrt(np.float32(1) - b2p) / (np.float32(1) - b1p))
+        L.check(eng.lib.ganmf_k_adam(eng.ctx, t.data_ptr(), m.data_ptr(), v.data_ptr(), dev(g).data_ptr(), n,
+                                     float(alpha), reg))
+        opt.apply(params, {"w": g + np.float32(reg) * params["w"]})
+        b1p, b2p = np.float32(b1p * np.float32(0.9)), np.float32(b2p * np.float32(0.999))
+    got = t.cpu().numpy()
+    # same formula, fp32; FMA contraction on the device moves last bits only
+    np.testing.assert_allclose(got, params["w"], rtol=2e-5, atol=2e-7)
+
+
+@pytest.mark.parametrize("n_items,K", [(3706, 50), (500, 5), (40, 50), (17632, 20), (200000, 10), (1000, 128)])
+def test_topk_bit_exact_vs_oracle(eng, n_items, K):
+    from ganmf_b200 import _lib as L
+    from oracle.eval_oracle import topk_lowest_index
+    rs = np.random.RandomState(n_items + K)
+    n = 37
+    s = rs.standard_normal((n, n_items)).astype(np.float32)
+    s[3] = np.round(s[3] * 2) / 2                      # heavy ties
+    s[4] = 0.0                                         # all equal -> indices 0..K-1
+    s[5, rs.permutation(n_items)[: n_items - 3]] = -np.inf    # only 3 finite entries
+    s[6] = -np.inf
+    s[7] = np.sort(s[7])                               # ascending: worst case for threshold filters
+    s[8] = np.sort(s[8])[::-1]
+    ld = rup(n_items)
+    sp = np.zeros((n, ld), dtype=np.float32)
+    sp[:, :n_items] = s
+    d = dev(sp)
+    idx = torch.zeros((n, K), dtype=torch.int32, device="cuda")
+    val = torch.zeros((n, K), dtype=torch.float32, device="cuda")
+    L.check(eng.lib.ganmf_k_topk(eng.ctx, d.data_ptr(), ld, n, n_items, K, idx.data_ptr(), val.data_ptr()))
+    gi, gv = idx.cpu().numpy(), val.cpu().numpy()
+    kk = min(K, n_items)
+    wi, wv = topk_lowest_index(s, kk)
+    wi = np.where(np.isinf(wv) & (wv < 0), -1, wi)
+    assert np.array_equal(gi[:, :kk], wi)
+    assert np.array_equal(gv[:, :kk], wv)
+    assert np.all(gi[:, kk:] == -1)

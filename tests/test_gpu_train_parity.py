@@ -1,0 +1,142 @@
+"""Training parity on the B200: identical initial weights and minibatch index stream, per-step
+D/G losses and parameters after N steps against the fp32 oracle (oracle/train_oracle.py).
+Tolerance (north_star): relative <= 1e-3 on every loss and on ||theta - theta_ref|| / ||theta_ref||
+per tensor (TF32 tensor-core inputs, fp32 accumulation)."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from oracle import train_oracle as to
+
+pytestmark = pytest.mark.gpu
+REL = 1e-3
+
+
+def make_urm(n_rows, width, density, seed):
+    rs = np.random.RandomState(seed)
+    m = sps.random(n_rows, width, density, format="csr", dtype=np.float32, random_state=rs)
+    m.data[:] = 1.0
+    return m
+
+
+def rel_err(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) /
+                 max(np.linalg.norm(b.astype(np.float64)), 1e-30))
+
+
+def run_ganmf(n_rows, width, k, E, B, epochs, hp, gemm_path, density=0.05, seed=0):
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    urm = make_urm(n_rows, width, density, seed)
+    p0 = to.init_ganmf_params(n_rows, width, k, E, seed=seed + 1)
+    rs = np.random.RandomState(seed + 2)
+    p0["autoencoder/encoding/bias"] = (rs.standard_normal(E) * 0.01).astype(np.float32)
+    p0["autoencoder/decoding/bias"] = (rs.standard_normal(width) * 0.01).astype(np.float32)
+    eng = Engine(L.KIND_GANMF, n_rows, width, k, emb_dim=E, max_batch=B, gemm_path=gemm_path)
+    eng.set_csr(L.CSR_TRAIN, urm)
+    eng.set_params(p0)
+    eng.reset_optimizers()
+    orc = to.GanmfOracle(p0, hp["d_lr"], hp["g_lr"], dtype=np.float32)
+    dl_all, gl_all, odl, ogl = [], [], [], []
+    for _, batches in to.epoch_index_stream(n_rows, B, epochs, seed=1337):
+        perm = np.concatenate(batches)
+        dl, gl = eng.train_epoch(perm, B, 1, 1, hp["d_lr"], hp["g_lr"], hp["d_reg"], hp["g_reg"], hp["m"],
+                                 hp["alpha"])
+        dl_all += list(dl)
+        gl_all += list(gl)
+        for b in batches:
+            odl.append(orc.d_step(b, to.csr_rows_to_dense(urm, b), d_reg=hp["d_reg"], m=hp["m"]))
+        for b in batches:
+            ogl.append(orc.g_step(b, to.csr_rows_to_dense(urm, b), g_reg=hp["g_reg"], recon_coefficient=hp["alpha"]))
+    got = eng.get_params()
+    eng.close()
+    return np.array(dl_all), np.array(gl_all), np.array(odl), np.array(ogl), got, orc.p
+
+
+HP = dict(d_lr=1e-4, g_lr=2e-4, d_reg=1e-4, g_reg=0.0, m=10.0, alpha=0.01)
+
+
+@pytest.mark.parametrize("path_name", ["simt", "tc"])
+@pytest.mark.parametrize("hp", [HP, dict(HP, m=0.05, g_reg=1e-3, alpha=0.3)])     # gate open / closed
+def test_ganmf_100_steps_parity(path_name, hp):
+    from ganmf_b200 import _lib as L
+    path = {"simt": L.GEMM_SIMT, "tc": L.GEMM_TC}[path_name]
+    # 300 rows, B=64 -> 5 batches/epoch (last one short: 44 rows); 10 epochs = 50 D + 50 G steps
+    dl, gl, odl, ogl, got, want = run_ganmf(300, 517, 24, 40, 64, 10, hp, path)
+    assert len(dl) == 50 and len(gl) == 50
+    np.testing.assert_allclose(dl, odl, rtol=REL)
+    np.testing.assert_allclose(gl, ogl, rtol=REL)
+    for n in want:
+        assert rel_err(got[n], want[n]) <= REL, (n, rel_err(got[n], want[n]))
+
+
+def test_ganmf_ml1m_shape_steps_parity():
+    """cfg1 shape (GANMF-u ML-1M: I=3706, k=250, E=992, B=64) on the committed split, best params."""
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    from tests.helpers import load_split
+    urm = load_split("Movielens1M")["train"]
+    n_rows, width = urm.shape
+    k, E, B = 250, 992, 64
+    hp = dict(d_lr=1e-4, g_lr=1.653241474168571e-4, d_reg=1e-4, g_reg=0.0, m=10.0, alpha=0.01)
+    p0 = to.init_ganmf_params(n_rows, width, k, E, seed=5)
+    eng = Engine(L.KIND_GANMF, n_rows, width, k, emb_dim=E, max_batch=B)
+    eng.set_csr(L.CSR_TRAIN, urm)
+    eng.set_params(p0)
+    eng.reset_optimizers()
+    orc = to.GanmfOracle(p0, hp["d_lr"], hp["g_lr"], dtype=np.float32)
+    _, batches = next(iter(to.epoch_index_stream(n_rows, B, 1, seed=1337)))
+    batches = batches[:12] + [batches[-1]]              # 13 batches incl. the short last one (24 rows)
+    perm = np.concatenate(batches)
+    eng.upload_ids(perm)
+    off, slot = 0, 0
+    for b in batches:
+        eng.d_step(off, len(b), hp["d_lr"], hp["d_reg"], hp["m"], loss_slot=slot)
+        off += len(b)
+        slot += 1
+    off = 0
+    for b in batches:
+        eng.g_step(off, len(b), hp["g_lr"], hp["g_reg"], hp["alpha"], loss_slot=slot)
+        off += len(b)
+        slot += 1
+    losses = eng.read_losses(slot)
+    want = [orc.d_step(b, to.csr_rows_to_dense(urm, b), d_reg=hp["d_reg"], m=hp["m"]) for b in batches]
+    want += [orc.g_step(b, to.csr_rows_to_dense(urm, b), g_reg=hp["g_reg"], recon_coefficient=hp["alpha"])
+             for b in batches]
+    np.testing.assert_allclose(losses, want, rtol=REL)
+    got = eng.get_params()
+    for n in orc.p:
+        assert rel_err(got[n], orc.p[n]) <= REL, (n, rel_err(got[n], orc.p[n]))
+    eng.close()
+
+
+@pytest.mark.parametrize("act,layers,nodes", [("linear", 1, 4), ("tanh", 2, 48), ("relu", 3, 33), ("sigmoid", 2, 130)])
+def test_disganmf_steps_parity(act, layers, nodes):
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    n_rows, width, k, B = 200, 310, 12, 32
+    urm = make_urm(n_rows, width, 0.06, 3)
+    p0 = to.init_disganmf_params(n_rows, width, k, layers, nodes, seed=9)
+    hp = dict(d_lr=1e-3, g_lr=2e-4, d_reg=1e-5, g_reg=1e-4, alpha=0.3)
+    eng = Engine(L.KIND_DISGANMF, n_rows, width, k, d_layers=layers, d_nodes=nodes, d_act=act, max_batch=B)
+    eng.set_csr(L.CSR_TRAIN, urm)
+    eng.set_params(p0)
+    eng.reset_optimizers()
+    orc = to.DisGanmfOracle(p0, layers, act, hp["d_lr"], hp["g_lr"], dtype=np.float32)
+    dl_all, gl_all, odl, ogl = [], [], [], []
+    for _, batches in to.epoch_index_stream(n_rows, B, 4, seed=1337):
+        perm = np.concatenate(batches)
+        dl, gl = eng.train_epoch(perm, B, 1, 1, hp["d_lr"], hp["g_lr"], hp["d_reg"], hp["g_reg"], 1.0, hp["alpha"])
+        dl_all += list(dl)
+        gl_all += list(gl)
+        for b in batches:
+            odl.append(orc.d_step(b, to.csr_rows_to_dense(urm, b), d_reg=hp["d_reg"]))
+        for b in batches:
+            ogl.append(orc.g_step(b, to.csr_rows_to_dense(urm, b), g_reg=hp["g_reg"], recon_coefficient=hp["alpha"]))
+    # ids up to 200 are an input FEATURE of the discriminator (DisGANMF.py:110): TF32 keeps them exact
+    np.testing.assert_allclose(dl_all, odl, rtol=REL)
+    np.testing.assert_allclose(gl_all, ogl, rtol=REL)
+    got = eng.get_params()
+    for n in orc.p:
+        assert rel_err(got[n], orc.p[n]) <= REL, (n, rel_err(got[n], orc.p[n]))
+    eng.close()
