@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the GANMF hot path on B200 (driver contract: see the round brief).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path, one rank per GPU
+    python bench.py --impl reference --steps K --warmup W    # the reference's arithmetic on the host CPU
+
+Workload (BASELINE.json configs[3]): synthetic 138 000 x 27 000 implicit matrix at 0.5 % density,
+GANMF --user, k=250, emb_dim=1024, batch 1024 PER GPU (weak scaling: every GPU owns 138 000 users).
+A "step" = one D update + one G update on one 1024-row minibatch (each row gets one D pass and one G
+pass, which is how BASELINE.md turns epochs into user-rows/s).
+value  = rows/s with the CSR, ids and weights already resident in HBM.
+e2e    = the same through ganmf_train_epoch() (the call GANMF.fit makes): host ids in, losses out.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import scipy.sparse as sps
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG4 = dict(name="cfg4: synthetic 138000x27000 d=0.5% GANMF-u k=250 E=1024 B=1024/GPU", users=138000, items=27000,
+            density=0.005, k=250, E=1024, B=1024)
+HP = dict(d_lr=1e-4, g_lr=1e-4, d_reg=1e-4, g_reg=0.0, m=10.0, alpha=0.01)
+
+
+def synthetic_urm(n_users, n_items, density, seed):
+    """Implicit interaction matrix: round(density*n_items) distinct uniform items per user."""
+    rs = np.random.RandomState(seed)
+    per = max(1, int(round(density * n_items)))
+    cols = rs.randint(0, n_items, size=(n_users, per)).astype(np.int32)
+    cols.sort(axis=1)
+    keep = np.ones_like(cols, dtype=bool)
+    keep[:, 1:] = cols[:, 1:] != cols[:, :-1]
+    indptr = np.zeros(n_users + 1, dtype=np.int64)
+    np.cumsum(keep.sum(1), out=indptr[1:])
+    m = sps.csr_matrix((np.ones(int(indptr[-1]), np.float32), cols[keep], indptr.astype(np.int32)),
+                       shape=(n_users, n_items))
+    m.has_sorted_indices = True
+    return m
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
+                          ("sw_power_cap", 6)):
+            if any(len(r) >= 7 and r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def flops_per_row(c):
+    return c["items"] * (8 * c["k"] + 30 * c["E"])
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU path for this metric: its TF-1.12 graph restated in NumPy (TensorFlow cannot
+    be installed here), all host threads, same shapes and hyper-parameters."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import train_oracle as to
+    c = CFG4
+    B = 256                                                   # bounded sample: 256-row minibatches
+    n_users = 4096                                            # user-factor rows kept small: P is not the cost driver
+    urm = synthetic_urm(n_users, c["items"], c["density"], 1337)
+    p0 = to.init_ganmf_params(n_users, c["items"], c["k"], c["E"], seed=1234)
+    orc = to.GanmfOracle(p0, HP["d_lr"], HP["g_lr"], dtype=np.float32)
+    rs = np.random.RandomState(1337)
+
+    def step():
+        ids = rs.permutation(n_users)[:B]
+        R = to.csr_rows_to_dense(urm, ids)
+        orc.d_step(ids, R, d_reg=HP["d_reg"], m=HP["m"])
+        orc.g_step(ids, R, g_reg=HP["g_reg"], recon_coefficient=HP["alpha"])
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = B * args.steps / dt
+    cores = os.cpu_count()
+    sample = "NumPy restatement of the TF graph, %d steps of B=%d rows at 27000 items, k=250, E=1024 " \
+             "(user-factor table cut to %d rows)" % (args.steps, B, n_users)
+    line = {"impl": "reference", "metric": "GANMF-u train user-rows/s", "value": v, "unit": "rows/s", "n_gpus": 0,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": c["name"]},
+            "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-users", type=int, default=8192)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: ganmf_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from ganmf_b200 import _lib as L
+    from ganmf_b200 import build as _build
+    _build.build()
+    from ganmf_b200.engine import Engine
+    from ganmf_b200.parallel import DataParallelTrainer
+
+    c = CFG4
+    K, W, B = args.steps, args.warmup, c["B"]
+    urm = synthetic_urm(c["users"], c["items"], c["density"], 1337 + rank)      # this rank's user shard
+    eng = Engine(L.KIND_GANMF, c["users"], c["items"], c["k"], emb_dim=c["E"], max_batch=B, device=local_rank)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.set_csr(L.CSR_TRAIN, urm)
+    eng.set_csr(L.CSR_SEEN, urm, with_data=False)
+    eng.init_params(1234)                                     # same seed on every rank: replicated D and V
+    trainer = DataParallelTrainer(eng, world) if world > 1 else None
+    rs = np.random.RandomState(1337 + rank)
+    n_ids = (W + K) * B
+    perm = rs.permutation(c["users"])[:n_ids].astype(np.int32)
+    eng.upload_ids(perm)
+
+    def run_steps(first, count, slot0=0):
+        """reference schedule on `count` batches: all D updates, then all G updates, same batches"""
+        for i in range(count):
+            off = (first + i) * B
+            if trainer:
+                trainer.d_step(off, B, HP["d_lr"], HP["d_reg"], HP["m"], slot0 + i)
+            else:
+                eng.d_step(off, B, HP["d_lr"], HP["d_reg"], HP["m"], loss_slot=slot0 + i)
+        for i in range(count):
+            off = (first + i) * B
+            if trainer:
+                trainer.g_step(off, B, HP["g_lr"], HP["g_reg"], HP["alpha"], slot0 + count + i)
+            else:
+                eng.g_step(off, B, HP["g_lr"], HP["g_reg"], HP["alpha"], loss_slot=slot0 + count + i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput --------------------------------------------------------
+    run_steps(0, W)
+    barrier()
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record()
+        run_steps(W, K)
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launch_count() - launches0
+    value = world * B * K / (ms * 1e-3)
+    losses = eng.read_losses(2 * K)
+    if not np.all(np.isfinite(losses)):
+        raise SystemExit("non-finite losses in the timed region: %r" % losses[:8])
+
+    # ---- live roofline of the dominant kernel (tcgen05 GEMM), CUDA events around every launch --
+    eng.profile(True)
+    run_steps(W, K)
+    gemm_ms, gemm_flops, gemm_launches = eng.profile_read()
+    eng.profile(False)
+    pk = peaks()
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"kernel": "tc_gemm_kernel (tcgen05 kind::tf32, TMA, TMEM)", "bound": "tensor", "achieved": achieved,
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": None,
+                "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json); kind::tf32 issues at half the "
+                "bf16 rate, so frac <= 0.5 by construction", "frac_of_tf32_rate": 2 * achieved / pk["tf_sust"],
+                "gemm_launches_per_step": gemm_launches / K, "gemm_share_of_step": gemm_ms / (ms if world == 1 else
+                                                                                             max(ms, 1e-9)),
+                "step_algorithmic_tflops": flops_per_row(c) * B * K / (ms * 1e-3) / 1e12}
+
+    # ---- end to end through the public call (host ids in, losses out) -------------------------
+    e2e = None
+    if world == 1:
+        hp = (B, 1, 1, HP["d_lr"], HP["g_lr"], HP["d_reg"], HP["g_reg"], HP["m"], HP["alpha"])
+        pin = torch.from_numpy(rs.permutation(c["users"])[:K * B].astype(np.int32)).pin_memory()
+        eng.train_epoch(pin.numpy()[:W * B], *hp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dl, gl = eng.train_epoch(pin.numpy(), *hp)             # H2D ids + all steps + D2H losses + sync
+        dt = time.perf_counter() - t0
+        e2e = {"value": B * K / dt, "unit": "rows/s", "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 8,
+               "api": "ganmf_train_epoch (GANMF.fit's per-epoch call): pinned host row ids in, per-step losses out"}
+    else:
+        e2e = trainer.e2e_epoch(rs, c["users"], K, B, HP)
+        e2e["value"] = world * B * K / (max_over_ranks(e2e.pop("ms")) * 1e-3)
+
+    # ---- evaluator: score -> seen mask -> top-10 -> metric sums, users sharded by rank ---------
+    n_eval = min(args.eval_users, c["users"])
+    test = synthetic_urm(c["users"], c["items"], c["density"] / 4, 4242 + rank)
+    test = sps.csr_matrix(test - test.multiply(urm))
+    test.eliminate_zeros()
+    test.sort_indices()
+    eng.set_test(test, urm)
+    users = np.flatnonzero(np.diff(test.indptr) > 0)[:n_eval].astype(np.int32)
+    eng.evaluate(users[:1024], [10], remove_seen=True, want_counts=False)
+    barrier()
+    t0 = time.perf_counter()
+    sums, _ = eng.evaluate(users, [10], remove_seen=True, want_counts=False)
+    torch.cuda.synchronize()
+    ev_s = time.perf_counter() - t0
+    ev_ms = max_over_ranks(ev_s * 1e3)
+    eval_users_s = world * len(users) / (ev_ms * 1e-3)
+    eval_info = {"metric": "top-10 eval users/s (score -> seen mask -> top-10 -> metric sums)", "value": eval_users_s,
+                 "unit": "users/s", "users": int(len(users)) * world, "hbm_frac_4I_bytes_per_user":
+                 eval_users_s / world * 4 * c["items"] / 1e9 / pk["hbm"], "e2e": True,
+                 "precision_at_10": float(sums[0, 0] / max(len(users), 1))}
+
+    line = {"metric": "GANMF-u train user-rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": c["name"], "l2": "per-step working set (weights 221 MB + activations) exceeds the "
+                       "126 MB L2", "parallelism": "dp%d over users; D and item factors replicated, NCCL allreduce" %
+                       world if world > 1 else "single GPU"},
+            "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e, "roofline": roofline,
+            "eval": eval_info, "loss_last": [float(losses[K - 1]), float(losses[2 * K - 1])]}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(c)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline(c):
+    """Oracle port of the reference graph on the host cores, bounded sample (about 10-30 s)."""
+    from oracle import train_oracle as to
+    B, n_users = 256, 4096
+    urm = synthetic_urm(n_users, c["items"], c["density"], 1337)
+    orc = to.GanmfOracle(to.init_ganmf_params(n_users, c["items"], c["k"], c["E"], seed=1234), HP["d_lr"], HP["g_lr"],
+                         dtype=np.float32)
+    rs = np.random.RandomState(0)
+
+    def step():
+        ids = rs.permutation(n_users)[:B]
+        R = to.csr_rows_to_dense(urm, ids)
+        orc.d_step(ids, R, d_reg=HP["d_reg"], m=HP["m"])
+        orc.g_step(ids, R, g_reg=HP["g_reg"], recon_coefficient=HP["alpha"])
+    step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 or (time.perf_counter() - t0 < 12 and n < 40):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": B * n / dt, "unit": "rows/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d D+G steps of B=%d rows, 27000 items, k=250, E=1024 (NumPy/BLAS, all host threads; "
+                      "user-factor table cut to %d rows)" % (n, B, n_users)}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

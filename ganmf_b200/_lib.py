@@ -74,6 +74,8 @@ SIGNATURES = {
     "ganmf_k_adam": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
                                C.c_float]),
     "ganmf_k_topk": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ganmf_profile": (C.c_int, [_ctx, C.c_int]),
+    "ganmf_profile_read": (C.c_int, [_ctx, _f64p, _f64p, _i64p]),
     "ganmf_launch_count": (C.c_int64, [_ctx]),
 }
 

@@ -91,7 +91,8 @@ struct ganmf_ctx {
   float* rmse_scratch = nullptr;
   bool have_tables = false;
   float* scores = nullptr; size_t scores_elems = 0;   // [block][items_ld]
-  Mat Fb;                                              // gathered factor rows for scoring
+  Mat Fb;                                              // gathered query rows, split-TF32 [hi|hi|lo]
+  Mat Ob;                                              // ranked-item factors, split-TF32 [hi|lo|hi]
   int* topk_idx = nullptr; float* topk_val = nullptr; size_t topk_cap = 0;
   double* uvals = nullptr; size_t uvals_cap = 0;
   double* usums = nullptr; int* icounts = nullptr; size_t icounts_cap = 0;
@@ -99,6 +100,12 @@ struct ganmf_ctx {
   int* eval_users = nullptr; int eval_users_cap = 0;
   long long launches = 0;
   int last_ids_offset = 0;
+  // live GEMM timing (bench roofline)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  double prof_flops = 0;
+  long long prof_launches = 0;
 };
 
 const char* ganmf_last_error(void) { return g_err; }
@@ -155,8 +162,24 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   g.splits = splits;
   g.ws = c->ws;
   c->launches += splits > 1 ? 2 : 1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (c->profile) {
+    while (c->ev_pool.size() < c->ev_used + 2) {
+      cudaEvent_t ev;
+      CU(cudaEventCreate(&ev));
+      c->ev_pool.push_back(ev);
+    }
+    ev0 = c->ev_pool[c->ev_used++];
+    ev1 = c->ev_pool[c->ev_used++];
+    CU(cudaEventRecord(ev0, c->st));
+  }
   cudaError_t e = tc_gemm(g, c->st);
   if (e != cudaSuccess) return fail("tc_gemm(M=%d N=%d K=%d) -> %s", M, N, K, cudaGetErrorString(e));
+  if (c->profile) {
+    CU(cudaEventRecord(ev1, c->st));
+    c->prof_flops += 2.0 * M * N * K;
+    c->prof_launches += 1;
+  }
   return 0;
 }
 
@@ -283,7 +306,7 @@ void ganmf_destroy(ganmf_ctx* c) {
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
   cudaFree(c->d_slab); cudaFree(c->p_slab); cudaFree(c->v_slab);
-  for (Mat* m : {&c->X2, &c->H2, &c->H2s, &c->Res2, &c->dH2, &c->dF, &c->Pb, &c->dPb, &c->dhtmp, &c->Fb})
+  for (Mat* m : {&c->X2, &c->H2, &c->H2s, &c->Res2, &c->dH2, &c->dF, &c->Pb, &c->dPb, &c->dhtmp, &c->Fb, &c->Ob})
     cudaFree(m->p);
   for (auto& m : c->hs) cudaFree(m.p);
   for (auto& m : c->dzs) cudaFree(m.p);
@@ -294,6 +317,7 @@ void ganmf_destroy(ganmf_ctx* c) {
   cudaFree(c->tb_popn); cudaFree(c->tb_haspop); cudaFree(c->rmse_scratch);
   cudaFree(c->scores); cudaFree(c->topk_idx); cudaFree(c->topk_val); cudaFree(c->uvals);
   cudaFree(c->usums); cudaFree(c->icounts); cudaFree(c->cut_dev); cudaFree(c->eval_users);
+  for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
   delete c;
 }
 
@@ -307,6 +331,28 @@ int ganmf_synchronize(ganmf_ctx* c) {
   return 0;
 }
 int64_t ganmf_launch_count(ganmf_ctx* c) { return c ? c->launches : 0; }
+int ganmf_profile(ganmf_ctx* c, int enable) {
+  if (!c) return fail("null ctx");
+  CU(cudaStreamSynchronize(c->st));
+  c->profile = enable != 0;
+  c->ev_used = 0; c->prof_flops = 0; c->prof_launches = 0;
+  return 0;
+}
+int ganmf_profile_read(ganmf_ctx* c, double* ms, double* flops, int64_t* launches) {
+  if (!c) return fail("null ctx");
+  CU(cudaStreamSynchronize(c->st));
+  double total = 0;
+  for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, c->ev_pool[i], c->ev_pool[i + 1]));
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (flops) *flops = c->prof_flops;
+  if (launches) *launches = c->prof_launches;
+  c->ev_used = 0; c->prof_flops = 0; c->prof_launches = 0;
+  return 0;
+}
 
 // ------------------------------------------------------------------------------ data
 int ganmf_set_csr(ganmf_ctx* c, int which, int n_rows, int n_cols, const int32_t* indptr,
@@ -507,8 +553,8 @@ static int ganmf_d_backward_impl(ganmf_ctx* c, int B, int n_global, float m_hing
   Epilogue e5;                                                                     // G5: dH2
   e5.out = c->dH2.p; e5.ldo = c->dH2.ld; e5.row_scale2 = rs; e5.row_split = B;
   RC(gemm(c, c->Res2.p, c->Res2.ld, 0, Wd->w.p, Wd->w.ld, 0, 2 * B, c->E, c->W, e5));
-  colsum_kernel<<<(c->E + 31) / 32, dim3(32, 8), 0, c->st>>>(c->dH2.p, 2 * B, c->E, c->dH2.ld, nullptr,
-                                                            0x7fffffff, nullptr, be->g);   // dbe
+  // dbe = colsum(dH2) = dbd . Wd^T, evaluated in fp32 from the fp32 column sums (no tensor-core rounding)
+  rowdot_kernel<<<(c->E + 7) / 8, 256, 0, c->st>>>(Wd->w.p, c->E, c->W, Wd->w.ld, bd->g, be->g);
   CU(cudaGetLastError());
   Epilogue e6;                                                                     // G6: dWe
   e6.out = We->g; e6.ldo = We->w.ld;
@@ -801,8 +847,9 @@ static int ensure_eval_buffers(ganmf_ctx* c, int block, int K, int n_cut) {
   }
   if (c->Fb.rows < block) {
     cudaFree(c->Fb.p);
-    RC(mat_alloc(&c->Fb, block, c->k));
+    RC(mat_alloc(&c->Fb, block, 3 * c->k));
   }
+  if (!c->Ob.p) RC(mat_alloc(&c->Ob, n_items, 3 * c->k));
   if (c->eval_users_cap < block) {
     cudaFree(c->eval_users);
     RC(dalloc(&c->eval_users, (size_t)block));
@@ -833,19 +880,25 @@ static int ensure_eval_buffers(ganmf_ctx* c, int block, int K, int n_cut) {
   return 0;
 }
 
-// scores[n, items] for the users already in c->eval_users (device)
+// Ranking needs fp32-accurate scores (near-ties decide the order), so scoring runs the tensor cores
+// on split-TF32 operands: one GEMM over K' = 3k (see split3_rows_kernel).
+static int prepare_item_factors(ganmf_ctx* c) {
+  const Param& other = c->cfg.item_mode ? c->params[c->n_d] : c->params[c->n_d + 1];
+  split3_rows_kernel<<<other.w.rows, 64, 0, c->st>>>(other.w.p, other.w.ld, nullptr, c->Ob.p, c->Ob.ld, c->k, 1);
+  CU(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+// scores[n, items] for the users already in c->eval_users (device); prepare_item_factors() first
 static int score_block(ganmf_ctx* c, int n) {
-  const Param& P = c->params[c->n_d];
-  const Param& V = c->params[c->n_d + 1];
-  const Param& rows_of = c->cfg.item_mode ? V : P;      // factors of the queried users
-  const Param& other = c->cfg.item_mode ? P : V;        // factors of the ranked items
-  const int n_items = other.w.rows;
-  gather_rows_kernel<<<n, 64, 0, c->st>>>(rows_of.w.p, c->eval_users, c->Fb.p, c->Fb.ld);
+  const Param& rows_of = c->cfg.item_mode ? c->params[c->n_d + 1] : c->params[c->n_d];
+  const int n_items = c->Ob.rows;
+  split3_rows_kernel<<<n, 64, 0, c->st>>>(rows_of.w.p, rows_of.w.ld, c->eval_users, c->Fb.p, c->Fb.ld, c->k, 0);
   CU(cudaGetLastError());
   c->launches++;
   Epilogue e;
   e.out = c->scores; e.ldo = rup(n_items, 32);
-  return gemm(c, c->Fb.p, c->Fb.ld, 0, other.w.p, other.w.ld, 0, n, n_items, c->k, e);
+  return gemm(c, c->Fb.p, c->Fb.ld, 0, c->Ob.p, c->Ob.ld, 0, n, n_items, 3 * c->k, e);
 }
 
 static int n_items_of(ganmf_ctx* c) { return c->cfg.item_mode ? c->cfg.n_rows : c->W; }
@@ -864,6 +917,7 @@ int ganmf_score(ganmf_ctx* c, const int32_t* users, int n, float* scores_host) {
   RC(ensure_eval_buffers(c, n, 1, 0));
   const int n_items = n_items_of(c), ild = rup(n_items, 32);
   CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+  RC(prepare_item_factors(c));
   RC(score_block(c, n));
   CU(cudaMemcpy2DAsync(scores_host, (size_t)n_items * 4, c->scores, (size_t)ild * 4, (size_t)n_items * 4, n,
                        cudaMemcpyDeviceToHost, c->st));
@@ -930,6 +984,7 @@ int ganmf_recommend(ganmf_ctx* c, const int32_t* users, int n, int remove_seen, 
   RC(ensure_eval_buffers(c, n, K, 0));
   const int n_items = n_items_of(c), ild = rup(n_items, 32);
   CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+  RC(prepare_item_factors(c));
   RC(score_block(c, n));
   RC(mask_and_topk(c, n, n_items, remove_seen, K));
   CU(cudaMemcpyAsync(idx_host, c->topk_idx, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->st));
@@ -1016,6 +1071,7 @@ int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_
   CU(cudaMemcpyAsync(c->cut_dev, cutoffs, (size_t)n_cut * 4, cudaMemcpyHostToDevice, c->st));
   CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
   CU(cudaMemsetAsync(c->icounts, 0, (size_t)n_cut * n_items * 4, c->st));
+  RC(prepare_item_factors(c));
   for (int s = 0; s < n_users; s += block) {
     const int n = std::min(block, n_users - s);
     CU(cudaMemcpyAsync(c->eval_users, users + s, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));

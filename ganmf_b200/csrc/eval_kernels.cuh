@@ -26,7 +26,7 @@ __global__ void mask_seen_kernel(float* __restrict__ scores, int ld, const int* 
 // ----------------------------------------------------------------------------- top-K
 // Total order key: higher score first, then lower index.  NaN sorts last (numpy argsort).
 __device__ __forceinline__ unsigned long long topk_key(float f, int idx) {
-  unsigned u = __float_as_uint(f);
+  unsigned u = f == 0.f ? 0u : __float_as_uint(f);          // -0.0 == +0.0, as in numpy's comparison
   u = (f != f) ? 0u : (u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u));
   return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
 }

@@ -72,6 +72,25 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __r
   for (int c = threadIdx.x; c < ld / 4; c += blockDim.x) d[c] = s[c];
 }
 
+// Split-TF32 operands for fp32-accurate scoring on the tensor cores: x = hi + lo with hi = tf32(x),
+// lo = tf32(x - hi).  A rows become [hi | hi | lo], B rows [hi | lo | hi] (3k columns), so one GEMM
+// over K' = 3k yields hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-22 relative).
+// src = base[ids[r]] when ids != nullptr (gather fused), else base[r].
+__global__ void split3_rows_kernel(const float* __restrict__ src, int ld_src, const int* __restrict__ ids,
+                                   float* __restrict__ dst, int ld_dst, int k, int b_layout) {
+  const int r = blockIdx.x;
+  const float* s = src + (size_t)(ids ? ids[r] : r) * ld_src;
+  float* d = dst + (size_t)r * ld_dst;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const float x = s[j];
+    const float hi = ptx::round_tf32(x);
+    const float lo = ptx::round_tf32(x - hi);
+    d[j] = hi;
+    d[k + j] = b_layout ? lo : hi;
+    d[2 * k + j] = b_layout ? hi : lo;
+  }
+}
+
 // first column of the DisGANMF discriminator input: float(row id)  (DisGANMF.py:110-111)
 __global__ void ids_to_float_kernel(const int* __restrict__ ids, float* __restrict__ out, int B) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,6 +231,27 @@ __global__ void colsum_kernel(const float* __restrict__ X, int M, int N, int ld,
     for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
     out[n] = t;
   }
+}
+
+// out[e] = sum_i W[e, i] * x[i]   (fp32, one warp per row of W; ld multiple of 4).
+// Bias gradient of the encoder without tensor-core rounding: dbe = dbd . Wd^T, because
+// colsum(rs * Res2 . Wd^T) = (sum_m rs(m) Res2[m, :]) . Wd^T  and the bracket IS dbd (GANMF.py:64-68).
+__global__ void rowdot_kernel(const float* __restrict__ W, int rows, int cols, int ld,
+                              const float* __restrict__ x, float* __restrict__ out) {
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)e * ld);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float acc = 0.f;
+  const int n4 = cols >> 2;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 a = w4[i], b = x4[i];
+    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+  }
+  for (int i = (n4 << 2) + lane; i < cols; i += 32) acc = fmaf(W[(size_t)e * ld + i], x[i], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[e] = acc;
 }
 
 // Y[m, :] = X[m, :] * row_scale2[m >= row_split]

@@ -54,6 +54,14 @@ class Engine(object):
     def launch_count(self):
         return int(self.lib.ganmf_launch_count(self.ctx))
 
+    def profile(self, enable):
+        L.check(self.lib.ganmf_profile(self.ctx, int(enable)))
+
+    def profile_read(self):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        L.check(self.lib.ganmf_profile_read(self.ctx, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, n.value
+
     def device_buffer(self, name):
         ptr, n = C.c_void_p(), C.c_int64()
         L.check(self.lib.ganmf_device_buffer(self.ctx, name.encode(), C.byref(ptr), C.byref(n)))

@@ -1,0 +1,98 @@
+"""Data parallelism over users (one process per GPU, torch.distributed / NCCL for the plumbing).
+
+Partitioning: rank g owns a contiguous shard of the training rows -- its CSR
+rows, its rows of the user-factor matrix P and their Adam moments.  The item factors V and the
+discriminator are replicated.  Per step every rank takes its own minibatch from its own shard; the
+exchanged quantities are sums:
+  D step: [sum (Dr-R)^2, sum (Df-F)^2] (hinge gate needs the GLOBAL batch means), then all
+          discriminator gradients (one contiguous buffer);
+  G step: the item-factor gradient and the loss scalars.  dP rows never leave their owner.
+Gradients are already normalised by the global element count, so the collective is a plain SUM."""
+import time
+
+import numpy as np
+
+
+class DataParallelTrainer(object):
+    def __init__(self, engine, world_size, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.eng, self.world, self.group = engine, world_size, group
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.d_grads = torch.as_tensor(engine.device_buffer("d_grads"), device=dev)
+        self.g_shared = torch.as_tensor(engine.device_buffer("g_shared_grad"), device=dev)
+        self.scalars = torch.as_tensor(engine.device_buffer("step_scalars"), device=dev)
+        engine.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def _sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def d_step(self, ids_offset, B, lr, reg, m_hinge, loss_slot):
+        n_global = B * self.world
+        self.eng.d_forward(ids_offset, B)
+        self._sum(self.scalars)
+        self.eng.d_backward(B, n_global, m_hinge)
+        self._sum(self.d_grads)
+        self.eng.d_apply(lr, reg, loss_slot)
+
+    def g_step(self, ids_offset, B, lr, reg, recon_coefficient, loss_slot):
+        n_global = B * self.world
+        self.eng.g_forward_backward(ids_offset, B, n_global, recon_coefficient)
+        self._sum(self.g_shared)
+        self._sum(self.scalars)
+        self.eng.g_apply(B, n_global, lr, reg, recon_coefficient, loss_slot)
+
+    def train_epoch(self, perm_local, batch_size, d_steps, g_steps, hp):
+        """Reference schedule (GANMF.py:172-203) on this rank's shard; every rank must pass the same
+        number of ids.  Returns (d_losses, g_losses): the GLOBAL per-step losses."""
+        n = len(perm_local)
+        nb = (n + batch_size - 1) // batch_size
+        self.eng.upload_ids(perm_local)
+        slot = 0
+        for _ in range(d_steps):
+            for b in range(nb):
+                off = b * batch_size
+                self.d_step(off, min(batch_size, n - off), hp["d_lr"], hp["d_reg"], hp["m"], slot)
+                slot += 1
+        nd = slot
+        for _ in range(g_steps):
+            for b in range(nb):
+                off = b * batch_size
+                self.g_step(off, min(batch_size, n - off), hp["g_lr"], hp["g_reg"], hp["alpha"], slot)
+                slot += 1
+        losses = self.eng.read_losses(slot)
+        return losses[:nd], losses[nd:]
+
+    def e2e_epoch(self, rs, n_rows, K, B, hp):
+        """bench.py: host ids in, losses out, wall clock around the whole call (ms)."""
+        perm = rs.permutation(n_rows)[:K * B].astype(np.int32)
+        self.dist.barrier()
+        self.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        self.train_epoch(perm, B, 1, 1, hp)
+        self.torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        return {"ms": ms, "unit": "rows/s", "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 8,
+                "api": "DataParallelTrainer.train_epoch: host row ids in, per-step losses out"}
+
+
+def shard_rows(n_rows, world_size, rank):
+    """Contiguous row range [lo, hi) owned by `rank`."""
+    base, rem = divmod(n_rows, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def sharded_eval_sums(engine, users_local, cutoffs, remove_seen, dist=None, group=None):
+    """Evaluation sharded by user rows: only the metric sums (and the per-item histograms) cross GPUs."""
+    import torch
+    sums, counts = engine.evaluate(users_local, cutoffs, remove_seen=remove_seen)
+    n = np.array([len(users_local)], dtype=np.float64)
+    if dist is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        for a in (sums, counts, n):
+            t = torch.from_numpy(a).to(dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            a[...] = t.cpu().numpy()
+    return sums, counts, int(n[0])

@@ -150,6 +150,11 @@ int ganmf_k_adam(ganmf_ctx* ctx, float* theta, float* m, float* v, const float* 
                  float alpha, float reg);
 int ganmf_k_topk(ganmf_ctx* ctx, const float* scores, int ld, int n, int n_items, int K,
                  int32_t* idx, float* val);
+/* Live CUDA-event timing of the tensor-core GEMM launches on the context's stream (bench.py's
+ * roofline): enable, run steps, then read the summed device time, algorithmic FLOPs (2*M*N*K) and
+ * launch count of those GEMMs since the last read. */
+int ganmf_profile(ganmf_ctx* ctx, int enable);
+int ganmf_profile_read(ganmf_ctx* ctx, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
 /* number of kernels this library has launched since ganmf_create (bench.py's gpu_launches) */
 int64_t ganmf_launch_count(ganmf_ctx* ctx);
 

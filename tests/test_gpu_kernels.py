@@ -45,7 +45,7 @@ def test_gemm_paths_match_fp64(eng, a_mn, b_mn, shape):
     Bs = padded(B.T if b_mn else B)
     dA, dB = dev(As), dev(Bs)
     ldo = rup(N)
-    for path, tol in ((L.GEMM_SIMT, 2e-6), (L.GEMM_TC, 2e-3)):
+    for path, tol in ((L.GEMM_SIMT, 2e-5), (L.GEMM_TC, 2e-3)):
         out = torch.zeros((M, ldo), dtype=torch.float32, device="cuda")
         L.check(eng.lib.ganmf_k_gemm(eng.ctx, dA.data_ptr(), As.shape[1], a_mn, dB.data_ptr(), Bs.shape[1], b_mn,
                                      M, N, K, out.data_ptr(), ldo, path))
