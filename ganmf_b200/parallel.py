@@ -14,16 +14,20 @@ import numpy as np
 
 
 class DataParallelTrainer(object):
-    def __init__(self, engine, world_size, group=None):
+    def __init__(self, engine, world_size, group=None, buffers=None):
+        """buffers: optional {"d_grads", "g_shared_grad", "step_scalars"} tensors (the CPU/gloo tests pass
+        host tensors of a stand-in engine); by default the engine's device buffers are wrapped zero-copy."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.eng, self.world, self.group = engine, world_size, group
-        dev = torch.device("cuda", torch.cuda.current_device())
-        self.d_grads = torch.as_tensor(engine.device_buffer("d_grads"), device=dev)
-        self.g_shared = torch.as_tensor(engine.device_buffer("g_shared_grad"), device=dev)
-        self.scalars = torch.as_tensor(engine.device_buffer("step_scalars"), device=dev)
-        engine.set_stream(torch.cuda.current_stream().cuda_stream)
+        if buffers is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            buffers = {n: torch.as_tensor(engine.device_buffer(n), device=dev)
+                       for n in ("d_grads", "g_shared_grad", "step_scalars")}
+            engine.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.d_grads, self.g_shared, self.scalars = (buffers["d_grads"], buffers["g_shared_grad"],
+                                                     buffers["step_scalars"])
 
     def _sum(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
