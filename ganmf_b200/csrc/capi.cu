@@ -152,12 +152,21 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   g.bn = N > 128 ? 256 : 128;
   const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + g.bn - 1) / g.bn);
   const int total_kb = (K + TC_BK - 1) / TC_BK;
+  // Split K when the output has too few tiles to fill the 148 SMs: pick the split count with the best
+  // wave efficiency units / (ceil(units / 148) * 148), at least 8 k-blocks per split.
   int splits = 1;
   if (tiles < 148 && total_kb >= 16) {
-    splits = std::min((2 * 148 + tiles - 1) / tiles, total_kb / 8);
     const size_t per = (size_t)M * rup(N, 4);
-    if ((size_t)splits * per > c->ws_floats) splits = (int)(c->ws_floats / per);
-    if (splits < 1) splits = 1;
+    int smax = std::min(std::min(total_kb / 8, 64), (int)std::min<size_t>(c->ws_floats / per, 64));
+    double best = (double)tiles / 148.0;
+    for (int sp = 2; sp <= smax; ++sp) {
+      const int kbps = (total_kb + sp - 1) / sp;
+      const int real = (total_kb + kbps - 1) / kbps;
+      if (real != sp) continue;
+      const int units = tiles * sp;
+      const double eff = (double)units / (((units + 147) / 148) * 148.0);
+      if (eff > best + 0.02) { best = eff; splits = sp; }
+    }
   }
   g.splits = splits;
   g.ws = c->ws;
@@ -936,8 +945,7 @@ static int mask_and_topk(ganmf_ctx* c, int n, int n_items, int remove_seen, int 
     CU(cudaGetLastError());
     c->launches++;
   }
-  topk_rows_kernel<<<n, TK_THREADS, 0, c->st>>>(c->scores, ild, n_items, K, c->topk_idx, c->topk_val);
-  CU(cudaGetLastError());
+  CU(topk_rows(c->scores, ild, n, n_items, K, c->topk_idx, c->topk_val, c->st));
   c->launches++;
   return 0;
 }
@@ -1173,8 +1181,7 @@ int ganmf_k_adam(ganmf_ctx* c, float* theta, float* m, float* v, const float* g,
 }
 int ganmf_k_topk(ganmf_ctx* c, const float* scores, int ld, int n, int n_items, int K, int32_t* idx, float* val) {
   if (!c || K < 1 || K > TK_MAXK) return fail("bad K");
-  topk_rows_kernel<<<n, TK_THREADS, 0, c->st>>>(scores, ld, n_items, K, idx, val);
-  CU(cudaGetLastError());
+  CU(topk_rows(scores, ld, n, n_items, K, idx, val, c->st));
   c->launches++;
   return 0;
 }

@@ -38,76 +38,104 @@ __device__ __forceinline__ float topk_key_score(unsigned long long k) {
 
 constexpr int TK_WARPS = 8;
 constexpr int TK_THREADS = TK_WARPS * 32;
-constexpr int TK_CAP = 512;          // per-warp candidate buffer (keys)
 constexpr int TK_MAXK = 128;
 
-// descending bitonic sort of buf[0..n) (n power of two) by one warp
-__device__ __forceinline__ void warp_bitonic_desc(unsigned long long* buf, int n, int lane) {
-  for (int size = 2; size <= n; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = lane; t < (n >> 1); t += 32) {
-        const int lo = ((t / stride) * stride * 2) + (t % stride);
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const unsigned long long a = buf[lo], b = buf[hi];
-        if ((a < b) == desc) { buf[lo] = b; buf[hi] = a; }
-      }
-      __syncwarp();
-    }
+// Warp-level selection: the warp keeps its running top-K as ONE sorted list spread over the lanes'
+// registers (lane l holds ranks l*J .. l*J+J-1, J = ceil(K/32)).  Streaming a row, an element is
+// looked at in detail only if its score bits reach the current K-th best; after the first few tiles
+// that is rare (about K*ln(n/K) insertions per warp), so the kernel runs at the speed of the loads.
+template <int J>
+__device__ __forceinline__ void tk_insert(unsigned long long (&lst)[J], unsigned long long x, int lane) {
+  unsigned long long left_last = __shfl_up_sync(0xffffffffu, lst[J - 1], 1);
+  if (lane == 0) left_last = ~0ull;
+#pragma unroll
+  for (int j = J - 1; j >= 0; --j) {
+    const unsigned long long left = j == 0 ? left_last : lst[j - 1];
+    lst[j] = lst[j] > x ? lst[j] : (left > x ? x : left);
   }
 }
-
-// sort the warp's candidates, keep the best K, return the new admission threshold
-__device__ __forceinline__ unsigned long long warp_prune(unsigned long long* buf, int& cnt, int K, int lane) {
-  int n2 = 64;
-  while (n2 < cnt) n2 <<= 1;
-  for (int i = cnt + lane; i < n2; i += 32) buf[i] = 0ull;
-  __syncwarp();
-  warp_bitonic_desc(buf, n2, lane);
-  if (cnt > K) cnt = K;
-  return cnt == K ? buf[K - 1] : 0ull;
+template <int J>
+__device__ __forceinline__ unsigned long long tk_kth(const unsigned long long (&lst)[J], int K) {
+  const int slot = (K - 1) % J, owner = (K - 1) / J;
+  unsigned long long v = lst[0];
+#pragma unroll
+  for (int j = 1; j < J; ++j) v = slot == j ? lst[j] : v;
+  return __shfl_sync(0xffffffffu, v, owner);
 }
 
-// One CTA per score row.  Each warp streams an interleaved share of the row with 16-byte loads,
-// admits only elements that beat its current K-th best, and sorts its small buffer when it fills.
-// Algorithmic bytes: 4*n_items read + 8*K written per row.
+// One CTA per score row, 8 warps stream interleaved 512-byte tiles with 16-byte loads; the per-warp
+// winners are merged by rank.  Algorithmic bytes: 4*n_items read + 8*K written per row.
+template <int J>
 __global__ void __launch_bounds__(TK_THREADS)
 topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, int* __restrict__ out_idx,
                  float* __restrict__ out_val) {
-  __shared__ unsigned long long sbuf[TK_WARPS][TK_CAP];
+  __shared__ unsigned long long sbuf[TK_WARPS][32 * J];
   __shared__ int scnt[TK_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* row = scores + (size_t)blockIdx.x * ld;
-  unsigned long long* buf = sbuf[warp];
-  int cnt = 0;
+  unsigned long long lst[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) lst[j] = 0ull;
   unsigned long long thr = 0ull;
+  unsigned thr_hi = 0u;
   const int n_tiles = (n_items + 127) / 128;
-  for (int t = warp; t < n_tiles; t += TK_WARPS) {
+  const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  auto load_tile = [&](int t) -> float4 {
     const int c = t * 128 + lane * 4;
-    float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    if (c + 3 < n_items) {
-      v = *reinterpret_cast<const float4*>(row + c);
-    } else {
-      if (c < n_items) v.x = row[c];
-      if (c + 1 < n_items) v.y = row[c + 1];
-      if (c + 2 < n_items) v.z = row[c + 2];
-    }
+    if (t >= n_tiles) return ninf4;
+    if (c + 3 < n_items) return *reinterpret_cast<const float4*>(row + c);
+    float4 v = ninf4;
+    if (c < n_items) v.x = row[c];
+    if (c + 1 < n_items) v.y = row[c + 1];
+    if (c + 2 < n_items) v.z = row[c + 2];
+    return v;
+  };
+  float4 nxt = load_tile(warp);
+  for (int t = warp; t < n_tiles; t += TK_WARPS) {
+    const float4 v = nxt;
+    nxt = load_tile(t + TK_WARPS);                      // prefetch the warp's next tile
+    const int c = t * 128 + lane * 4;
     const float vs[4] = {v.x, v.y, v.z, v.w};
+    unsigned hi[4];
+    bool any = false;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const unsigned long long key = topk_key(vs[e], c + e);
-      const bool pass = (c + e < n_items) && key > thr;
-      const unsigned bal = __ballot_sync(0xffffffffu, pass);
-      if (pass) buf[cnt + __popc(bal & ((1u << lane) - 1))] = key;
-      cnt += __popc(bal);
+      const float f = vs[e];
+      unsigned u = f == 0.f ? 0u : __float_as_uint(f);
+      u = (f != f) ? 0u : (u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u));
+      hi[e] = u;
+      any |= (u >= thr_hi) && (c + e < n_items);
     }
-    __syncwarp();
-    if (cnt > TK_CAP - 128) thr = warp_prune(buf, cnt, K, lane);
+    if (!__any_sync(0xffffffffu, any)) continue;        // fast path: nothing can beat the K-th best
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned long long key =
+          ((unsigned long long)hi[e] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(c + e));
+      bool pass = (c + e < n_items) && key > thr;
+      unsigned bal;
+      while ((bal = __ballot_sync(0xffffffffu, pass)) != 0u) {
+        const int src = __ffs(bal) - 1;
+        const unsigned long long x = __shfl_sync(0xffffffffu, key, src);
+        tk_insert<J>(lst, x, lane);
+        thr = tk_kth<J>(lst, K);
+        thr_hi = (unsigned)(thr >> 32);
+        if (lane == src) pass = false;
+        pass = pass && key > thr;
+      }
+    }
   }
-  warp_prune(buf, cnt, K, lane);
-  // Merge the per-warp sorted winners by rank: keys are unique (they embed the item index), so the
-  // final position of a key is its own position plus the number of larger keys in the other lists.
-  if (lane == 0) scnt[warp] = cnt;
+  // per-warp winners (ranks < K, zeros = empty) -> smem, then merge by rank: keys are unique (they embed
+  // the item index), so a key's final position is its own rank plus the number of larger keys elsewhere
+  int mine = 0;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int p = lane * J + j;
+    sbuf[warp][p] = lst[j];
+    mine += (p < K && lst[j] != 0ull) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane == 0) scnt[warp] = mine;
   __syncthreads();
   int total = 0;
 #pragma unroll
@@ -119,10 +147,10 @@ topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, i
     int rank = p;
     for (int w2 = 0; w2 < TK_WARPS; ++w2) {
       if (w2 == w) continue;
-      int lo = 0, hi = scnt[w2];               // first position in the descending list w2 with key' < key
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (sbuf[w2][mid] > key) lo = mid + 1; else hi = mid;
+      int lo = 0, hi2 = scnt[w2];                       // first position in list w2 with key' < key
+      while (lo < hi2) {
+        const int mid = (lo + hi2) >> 1;
+        if (sbuf[w2][mid] > key) lo = mid + 1; else hi2 = mid;
       }
       rank += lo;
     }
@@ -137,6 +165,15 @@ topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, i
     out_idx[(size_t)blockIdx.x * K + j] = -1;
     out_val[(size_t)blockIdx.x * K + j] = -INFINITY;
   }
+}
+
+inline cudaError_t topk_rows(const float* scores, int ld, int n, int n_items, int K, int* out_idx, float* out_val,
+                             cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  if (K <= 32) topk_rows_kernel<1><<<n, TK_THREADS, 0, st>>>(scores, ld, n_items, K, out_idx, out_val);
+  else if (K <= 64) topk_rows_kernel<2><<<n, TK_THREADS, 0, st>>>(scores, ld, n_items, K, out_idx, out_val);
+  else topk_rows_kernel<4><<<n, TK_THREADS, 0, st>>>(scores, ld, n_items, K, out_idx, out_val);
+  return cudaGetLastError();
 }
 
 // ----------------------------------------------------------------------------- metrics
@@ -311,13 +348,22 @@ __global__ void user_rmse_kernel(const float* __restrict__ scores, int ld, const
   for (int ci = 0; ci < n_cut; ++ci) vals[((size_t)r * n_cut + ci) * MC_NCOL + MC_RMSE] = v;
 }
 
-// sums[col] += vals[row][col] for rows in order (one thread per (cutoff, metric) column)
+// sums[col] += vals[row][col] for rows in order (one thread per (cutoff, metric) column).  The adds stay
+// strictly sequential (bit-exact vs the reference's running sum); loads are issued 16 at a time.
 __global__ void ordered_accumulate_kernel(const double* __restrict__ vals, int n_rows, int n_cols,
                                           double* __restrict__ sums) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= n_cols) return;
   double acc = sums[col];
-  for (int r = 0; r < n_rows; ++r) acc += vals[(size_t)r * n_cols + col];
+  int r = 0;
+  for (; r + 16 <= n_rows; r += 16) {
+    double v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = vals[(size_t)(r + j) * n_cols + col];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc += v[j];
+  }
+  for (; r < n_rows; ++r) acc += vals[(size_t)r * n_cols + col];
   sums[col] = acc;
 }
 

@@ -13,7 +13,7 @@
 // One CTA computes one 128 x BN output tile (optionally one K-split of it).
 //   warp 0      : TMA producer (one elected lane)
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2..5  : epilogue, one TMEM lane quarter each (warp_id % 4)
+//   warps 2..9  : epilogue, two warps per TMEM lane quarter (warp_id % 4), half the columns each
 // Stage = 32 fp32 of K (one 128-byte swizzle row), i.e. 4 UMMA (K=8) per stage.
 #pragma once
 #include <cuda.h>
@@ -28,7 +28,7 @@ namespace ganmf {
 constexpr int TC_BM = 128;         // output tile rows (UMMA M)
 constexpr int TC_BK = 32;          // fp32 elements of K per stage (128 bytes)
 constexpr int TC_UMMA_K = 8;       // tf32: 32 bytes of K per instruction
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;     // TMA warp, MMA warp, 8 epilogue warps
 
 enum Act { ACT_LINEAR = 0, ACT_TANH = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
 __device__ __forceinline__ float act_fwd(int act, float z) {
@@ -70,7 +70,9 @@ struct Epilogue {
 struct TcGemmArgs {
   int M, N, K;
   int a_mn, b_mn;          // 1 = MN-major operand
-  int kb_per_split;        // k-blocks (of TC_BK) per blockIdx.z
+  int kb_per_split;        // k-blocks (of TC_BK) per K split
+  int splits;
+  int dbg_epi;             // bring-up: 1 = no global stores, 2 = no TMEM loads either
   float* ws;               // split-K partials [splits][M][ws_ld] (splits > 1)
   int ws_ld;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;   // smem descriptor strides, bytes >> 4
@@ -112,10 +114,31 @@ struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;
   static constexpr int B_BYTES = BN * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + align slack
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES;          // 8 warps x 32 rows x 8 float4 (swizzled)
+  static constexpr int EPI_BYTES = 8 * 32 * 32 * 4;
+  static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;  // + align slack
 };
 
+// Work unit = (output tile, K split).  Units are numbered so that consecutive units (which run
+// concurrently on neighbouring SMs) share the operand tile of the dimension with FEWER tiles: the
+// small operand stays L2 resident and the large one streams from HBM once.
+struct TcUnit { int m0, n0, split; };
+__device__ __forceinline__ TcUnit tc_unit(int u, int tiles_m, int tiles_n, int m_fastest, int BN) {
+  const int tiles = tiles_m * tiles_n;
+  TcUnit r;
+  r.split = u / tiles;
+  const int t = u - r.split * tiles;
+  int tm, tn;
+  if (m_fastest) { tn = t / tiles_m; tm = t - tn * tiles_m; }
+  else           { tm = t / tiles_n; tn = t - tm * tiles_n; }
+  r.m0 = tm * TC_BM;
+  r.n0 = tn * BN;
+  return r;
+}
+
+// Persistent kernel: grid = min(#units, #SMs); each CTA walks units blockIdx.x, +gridDim.x, ...
+// Two TMEM accumulator stages let the epilogue of unit i overlap the MMAs of unit i+1.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -126,19 +149,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                              ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM;
-  const int n0 = blockIdx.x * BN;
-  const int split = blockIdx.z;
   const int total_kb = (args.K + TC_BK - 1) / TC_BK;
-  const int kb_begin = split * args.kb_per_split;
-  int kb_end = kb_begin + args.kb_per_split;
-  if (kb_end > total_kb) kb_end = total_kb;
-  const int nkb = kb_end - kb_begin;   // host guarantees >= 1 for every launched split
+  const int tiles_m = (args.M + TC_BM - 1) / TC_BM;
+  const int tiles_n = (args.N + BN - 1) / BN;
+  const int n_units = tiles_m * tiles_n * args.splits;
+  const int m_fastest = tiles_m <= tiles_n;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a);
@@ -147,11 +168,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 8);         // one arrival per epilogue warp
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, BN);
+    ptx::tmem_alloc(tmem_slot, 2 * BN);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -162,115 +186,206 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * S::STAGE_BYTES;
-        uint8_t* sb = sa + S::A_BYTES;
-        const int k0 = (kb_begin + i) * TC_BK;
-        ptx::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        if (!args.a_mn) {
-          ptx::tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);          // box {32 k, 128 m}
-        } else {
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN);
+        const int kb_begin = un.split * args.kb_per_split;
+        const int kb_end = min(kb_begin + args.kb_per_split, total_kb);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          const int k0 = kb * TC_BK;
+          ptx::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+          if (!args.a_mn) {
+            ptx::tma_load_2d(sa, &map_a, &full_bar[s], k0, un.m0);          // box {32 k, 128 m}
+          } else {
 #pragma unroll
-          for (int j = 0; j < TC_BM / 32; ++j)                         // box {32 m, 32 k}
-            ptx::tma_load_2d(sa + j * (TC_BK * 128), &map_a, &full_bar[s], m0 + 32 * j, k0);
-        }
-        if (!args.b_mn) {
-          ptx::tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);          // box {32 k, BN n}
-        } else {
+            for (int j = 0; j < TC_BM / 32; ++j)                            // box {32 m, 32 k}
+              ptx::tma_load_2d(sa + j * (TC_BK * 128), &map_a, &full_bar[s], un.m0 + 32 * j, k0);
+          }
+          if (!args.b_mn) {
+            ptx::tma_load_2d(sb, &map_b, &full_bar[s], k0, un.n0);          // box {32 k, BN n}
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j)
-            ptx::tma_load_2d(sb + j * (TC_BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0);
+            for (int j = 0; j < BN / 32; ++j)
+              ptx::tma_load_2d(sb + j * (TC_BK * 128), &map_b, &full_bar[s], un.n0 + 32 * j, k0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (ptx::elect_one()) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, ui = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+        const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN);
+        const int kb_begin = un.split * args.kb_per_split;
+        const int nkb = min(kb_begin + args.kb_per_split, total_kb) - kb_begin;
+        const uint32_t acc = ui & 1;
+        ptx::mbar_wait(&tmem_empty_bar[acc], ((ui >> 1) & 1) ^ 1);     // epilogue drained this stage
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + s * S::STAGE_BYTES);
-        const uint32_t sb = sa + S::A_BYTES;
-        const uint64_t da = make_smem_desc(sa, args.a_lbo, args.a_sbo, args.a_layout);
-        const uint64_t db = make_smem_desc(sb, args.b_lbo, args.b_sbo, args.b_layout);
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + s * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+          const uint64_t da = make_smem_desc(sa, args.a_lbo, args.a_sbo, args.a_layout);
+          const uint64_t db = make_smem_desc(sb, args.b_lbo, args.b_sbo, args.b_layout);
 #pragma unroll
-        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-          ptx::mma_tf32_ss(tmem_base, da + (uint64_t)(k * args.a_kstep),
-                           db + (uint64_t)(k * args.b_kstep), args.idesc, (i | k) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            ptx::mma_tf32_ss(tmem_d, da + (uint64_t)(k * args.a_kstep),
+                             db + (uint64_t)(k * args.b_kstep), args.idesc, (i | k) ? 1u : 0u);
+          }
+          ptx::mma_commit(&empty_bar[s]);          // frees the smem stage when those MMAs retire
         }
-        ptx::mma_commit(&empty_bar[s]);      // frees the smem stage when those MMAs retire
+        ptx::mma_commit(&tmem_full_bar[acc]);      // accumulator of this unit complete
       }
-      ptx::mma_commit(tmem_full_bar);        // accumulator complete
     }
   } else {
-    // ------------------------------------------------------------ epilogue
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < args.M;
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter, each draining half of the tile's columns: the epilogue is
+    // instruction-latency bound, so it needs several warps per scheduler to hide under the next
+    // tile's MMAs.  Per 32x32 chunk: tcgen05.ld (thread = row) -> XOR-swizzled smem slab ->
+    // read back with lanes spanning columns, so every global access is a full 128-byte row segment.
+    const int ew = warp - 2;
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                      // which half of the BN columns
+    float4* slab = reinterpret_cast<float4*>(smem + S::EPI_OFF) + ew * 256;     // 32 rows x 8 float4
     const Epilogue& ep = args.ep;
-    const bool partial = gridDim.z > 1;
-    float rs = 1.f;
-    if (!partial && ep.row_scale2 && row_ok) rs = __ldg(ep.row_scale2 + (m >= ep.row_split ? 1 : 0));
-    float sq = 0.f;
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-      ptx::tmem_ld_wait();
-      const int nb = n0 + c;
-      if (!row_ok || nb >= args.N) continue;
-      if (partial) {
-        float* dst = args.ws + ((size_t)split * args.M + m) * args.ws_ld + nb;
-        if (nb + 32 <= args.N) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + j) =
-                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    const bool partial = args.splits > 1;
+    const int sub_r = lane >> 3;                   // coalesced phase: 4 rows x 8 lanes x float4
+    const int sub_g = lane & 7;
+    float rs0 = 1.f, rs1 = 1.f;
+    if (!partial && ep.row_scale2) { rs0 = __ldg(ep.row_scale2); rs1 = __ldg(ep.row_scale2 + 1); }
+    auto al16 = [](const void* p, int ld) { return (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool vec_all = partial ? true
+                                 : (al16(ep.out, ep.ldo) && (!ep.c1 || al16(ep.c1, ep.ldc1)) &&
+                                    (!ep.c2 || al16(ep.c2, ep.ldc2)) && (!ep.bias || al16(ep.bias, 4)) &&
+                                    !ep.r1_row);
+    float sq0 = 0.f, sq1 = 0.f;
+    uint32_t ui = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+      const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN);
+      const uint32_t acc = ui & 1;
+      ptx::mbar_wait(&tmem_full_bar[acc], (ui >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      const int mw = un.m0 + q * 32;               // first row of this warp's 32-row slab
+      const bool interior = vec_all && (un.m0 + TC_BM <= args.M) && (un.n0 + BN <= args.N);
+      const int c_end = (half + 1) * (BN / 2);
+      for (int c = half * (BN / 2); c < c_end; c += 32) {
+        uint32_t r[32];
+        if (args.dbg_epi < 2) {
+          ptx::tmem_ld_32x32(taddr + (uint32_t)c, r);
+          ptx::tmem_ld_wait();
         } else {
-          for (int j = 0; j < 32 && nb + j < args.N; ++j) dst[j] = __uint_as_float(r[j]);
-        }
-      } else {
-        float* dst = ep.out + (size_t)m * ep.ldo + nb;
-        if (nb + 32 <= args.N && (ep.ldo & 3) == 0 &&
-            (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v;
-            v.x = apply_epilogue(ep, __uint_as_float(r[j]), m, nb + j, rs);
-            v.y = apply_epilogue(ep, __uint_as_float(r[j + 1]), m, nb + j + 1, rs);
-            v.z = apply_epilogue(ep, __uint_as_float(r[j + 2]), m, nb + j + 2, rs);
-            v.w = apply_epilogue(ep, __uint_as_float(r[j + 3]), m, nb + j + 3, rs);
-            sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-            *reinterpret_cast<float4*>(dst + j) = v;
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (c + 32 >= c_end) {                     // last TMEM read of this warp for this unit
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        const int nb = un.n0 + c;
+        if (nb >= args.N || mw >= args.M || args.dbg_epi >= 1) continue;          // warp-uniform
+        // thread = row: 8 float4 stores, column group g lands in slot g ^ (row & 7) (conflict free)
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          slab[lane * 8 + (g ^ (lane & 7))] =
+              make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                          __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+        __syncwarp();
+        const int n = nb + sub_g * 4;
+        if (interior) {
+          // ---- fast path: whole tile in range, everything 16-byte aligned
+          if (partial) {
+            float* dst = args.ws + ((size_t)un.split * args.M + mw + sub_r) * args.ws_ld + n;
+            const size_t step = (size_t)4 * args.ws_ld;
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+              const int row = itr * 4 + sub_r;
+              *reinterpret_cast<float4*>(dst) = slab[row * 8 + (sub_g ^ (row & 7))];
+              dst += step;
+            }
+          } else {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+            float* dst = ep.out + (size_t)(mw + sub_r) * ep.ldo + n;
+            const float* p1 = ep.c1 ? ep.c1 + (size_t)(mw + sub_r) * ep.ldc1 + n : nullptr;
+            const float* p2 = ep.c2 ? ep.c2 + (size_t)(mw + sub_r) * ep.ldc2 + n : nullptr;
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+              const int row = itr * 4 + sub_r;
+              const float4 a = slab[row * 8 + (sub_g ^ (row & 7))];
+              const bool lower = (mw + row) >= ep.row_split;
+              const float sc = ep.alpha * (lower ? rs1 : rs0);
+              float4 o = make_float4(fmaf(sc, a.x, b4.x), fmaf(sc, a.y, b4.y), fmaf(sc, a.z, b4.z),
+                                     fmaf(sc, a.w, b4.w));
+              if (p1) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p1 + (size_t)itr * 4 * ep.ldc1));
+                o.x = fmaf(ep.beta1, t.x, o.x); o.y = fmaf(ep.beta1, t.y, o.y);
+                o.z = fmaf(ep.beta1, t.z, o.z); o.w = fmaf(ep.beta1, t.w, o.w);
+              }
+              if (p2) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p2 + (size_t)itr * 4 * ep.ldc2));
+                o.x = fmaf(ep.beta2, t.x, o.x); o.y = fmaf(ep.beta2, t.y, o.y);
+                o.z = fmaf(ep.beta2, t.z, o.z); o.w = fmaf(ep.beta2, t.w, o.w);
+              }
+              if (ep.act != ACT_LINEAR) {
+                o.x = act_fwd(ep.act, o.x); o.y = act_fwd(ep.act, o.y);
+                o.z = act_fwd(ep.act, o.z); o.w = act_fwd(ep.act, o.w);
+              }
+              if (ep.round_out) {
+                o.x = ptx::round_tf32(o.x); o.y = ptx::round_tf32(o.y);
+                o.z = ptx::round_tf32(o.z); o.w = ptx::round_tf32(o.w);
+              }
+              *reinterpret_cast<float4*>(dst + (size_t)itr * 4 * ep.ldo) = o;
+              const float sq = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+              if (lower) sq1 += sq; else sq0 += sq;
+            }
           }
         } else {
-          for (int j = 0; j < 32 && nb + j < args.N; ++j) {
-            float v = apply_epilogue(ep, __uint_as_float(r[j]), m, nb + j, rs);
-            sq += v * v;
-            dst[j] = v;
+          // ---- generic path: boundary tiles / unaligned views / rank-1 term
+          for (int itr = 0; itr < 8; ++itr) {
+            const int row = itr * 4 + sub_r;
+            const int m = mw + row;
+            if (m >= args.M || n >= args.N) continue;
+            const float4 a4 = slab[row * 8 + (sub_g ^ (row & 7))];
+            const float v[4] = {a4.x, a4.y, a4.z, a4.w};
+            if (partial) {
+              float* dst = args.ws + ((size_t)un.split * args.M + m) * args.ws_ld + n;
+              for (int e = 0; e < 4 && n + e < args.N; ++e) dst[e] = v[e];
+              continue;
+            }
+            const float rs = m >= ep.row_split ? rs1 : rs0;
+            float sq = 0.f;
+            for (int e = 0; e < 4 && n + e < args.N; ++e) {
+              const float x = apply_epilogue(ep, v[e], m, n + e, rs);
+              ep.out[(size_t)m * ep.ldo + n + e] = x;
+              sq += x * x;
+            }
+            if (m >= ep.row_split) sq1 += sq; else sq0 += sq;
           }
         }
+        __syncwarp();                               // slab is reused by the next chunk
       }
     }
     if (!partial && ep.sumsq2) {
-      // rows of one warp may straddle row_split: reduce the two slots separately
-      float s0 = (row_ok && m < ep.row_split) ? sq : 0.f;
-      float s1 = (row_ok && m >= ep.row_split) ? sq : 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        sq0 += __shfl_xor_sync(0xffffffffu, sq0, o);
+        sq1 += __shfl_xor_sync(0xffffffffu, sq1, o);
       }
       if (lane == 0) {
-        if (s0 != 0.f) atomicAdd(ep.sumsq2, (double)s0);
-        if (s1 != 0.f) atomicAdd(ep.sumsq2 + 1, (double)s1);
+        if (sq0 != 0.f) atomicAdd(ep.sumsq2, (double)sq0);
+        if (sq1 != 0.f) atomicAdd(ep.sumsq2 + 1, (double)sq1);
       }
     }
   }
@@ -279,7 +394,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, BN);
+    ptx::tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -353,7 +468,7 @@ struct TcGemmCall {
   // (measured: FLOAT32 maps leave the bits alone and the MMA then truncates).
   int tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
   // bring-up overrides for the MN-major tile encoding (0 = use the defaults below)
-  int dbg_mn_layout = 0, dbg_mn_sbo = 0, dbg_mn_lbo = 0, dbg_mn_swizzle = 0;
+  int dbg_mn_layout = 0, dbg_mn_sbo = 0, dbg_mn_lbo = 0, dbg_mn_swizzle = 0, dbg_epi = 0;
 };
 
 inline uint32_t make_idesc_tf32(int bn, int a_mn, int b_mn) {
@@ -381,7 +496,15 @@ inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((c.N + BN - 1) / BN, (c.M + TC_BM - 1) / TC_BM, splits);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const int units = ((c.N + BN - 1) / BN) * ((c.M + TC_BM - 1) / TC_BM) * splits;
+  const int grid = units < num_sms ? units : num_sms;
   tc_gemm_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, args);
   return cudaGetLastError();
 }
@@ -413,6 +536,8 @@ inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   splits = (total_kb + kbps - 1) / kbps;          // no empty split is ever launched
   if (splits > 1 && !c.ws) return cudaErrorInvalidValue;
   args.kb_per_split = kbps;
+  args.splits = splits;
+  args.dbg_epi = c.dbg_epi;
   args.ws = c.ws;
   args.ws_ld = (c.N + 3) & ~3;
   // shared-memory matrix descriptors (bytes >> 4):

@@ -92,6 +92,7 @@ int main(int argc, char** argv) {
   if (getenv("TC_MN_SBO")) c.dbg_mn_sbo = atoi(getenv("TC_MN_SBO"));
   if (getenv("TC_MN_LBO")) c.dbg_mn_lbo = atoi(getenv("TC_MN_LBO"));
   if (getenv("TC_MN_SWZ")) c.dbg_mn_swizzle = atoi(getenv("TC_MN_SWZ"));
+  if (getenv("TC_DBG_EPI")) c.dbg_epi = atoi(getenv("TC_DBG_EPI"));
   c.ep.out = dO; c.ep.ldo = ldo;
   const int row_split = M / 3;
   if (epi) {
