@@ -42,4 +42,4 @@ class GANMF(GanRecommenderBase):
                               earlystopping_kwargs)
 
     def autoencoder_codes(self):                                       # GANMF.py:304-307: R . We + be for all rows
-        raise NotImplementedError("autoencoder_codes() (AblationStudy plots) is outside the hot path")
+        return self._engine.encode(np.arange(self.num_users))

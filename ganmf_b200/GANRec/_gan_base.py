@@ -169,8 +169,17 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
         self._apply_build_params(build_params)
         eng = self._build_engine(batch_size=getattr(self, '_load_batch', 32))
         name = self.RECOMMENDER_NAME + '_' + self.mode if file_name is None else file_name
-        z = np.load(os.path.join(folder_path, name + '.npz'))
-        eng.set_params({k: z[k] for k in z.files})
+        npz = os.path.join(folder_path, name + '.npz')
+        tf_data = os.path.join(folder_path, name + '.data-00000-of-00001')
+        if os.path.exists(npz):
+            z = np.load(npz)
+            eng.set_params({k: z[k] for k in z.files})
+        elif os.path.exists(tf_data):                                  # a model saved by the reference itself
+            from ..tf_bundle import read_tf_bundle
+            shapes = {n: ((c,) if n.endswith('bias') else (r, c)) for n, r, c, _ in eng.param_infos()}
+            eng.set_params(read_tf_bundle(tf_data, shapes))
+        else:
+            raise IOError("no saved model %s(.npz|.data-00000-of-00001) in %s" % (name, folder_path))
         if self.mode == 'item':
             self.URM_train = self._URM_users_items.T.tocsr()           # reference leaves it transposed (A.4)
 

@@ -57,11 +57,13 @@ SIGNATURES = {
     "ganmf_d_apply": (C.c_int, [_ctx, C.c_float, C.c_float, C.c_int]),
     "ganmf_g_forward_backward": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float]),
     "ganmf_g_apply": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]),
+    "ganmf_finalize_loss": (C.c_int, [_ctx, C.c_float, C.c_int]),
     "ganmf_train_epoch": (C.c_int, [_ctx, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                     C.c_float, C.c_float, C.c_float, C.c_float, _f32p, _f32p]),
     "ganmf_read_losses": (C.c_int, [_ctx, _f32p, C.c_int]),
     "ganmf_device_buffer": (C.c_int, [_ctx, C.c_char_p, C.POINTER(C.c_void_p), _i64p]),
     "ganmf_score": (C.c_int, [_ctx, _i32p, C.c_int, _f32p]),
+    "ganmf_encode": (C.c_int, [_ctx, _i32p, C.c_int, _f32p]),
     "ganmf_mask_topk": (C.c_int, [_ctx, _f32p, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _i32p, _f32p, C.c_int]),
     "ganmf_recommend": (C.c_int, [_ctx, _i32p, C.c_int, C.c_int, C.c_int, _i32p, _f32p, _f32p]),
     "ganmf_set_eval_tables": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, _f64p, _u8p, _f64p]),
@@ -76,6 +78,7 @@ SIGNATURES = {
     "ganmf_k_topk": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ganmf_profile": (C.c_int, [_ctx, C.c_int]),
     "ganmf_profile_read": (C.c_int, [_ctx, _f64p, _f64p, _i64p]),
+    "ganmf_profile_records": (C.c_int, [_ctx, _f64p, _i32p, C.c_int, _i32p]),
     "ganmf_launch_count": (C.c_int64, [_ctx]),
 }
 

@@ -106,6 +106,7 @@ struct ganmf_ctx {
   size_t ev_used = 0;
   double prof_flops = 0;
   long long prof_launches = 0;
+  std::vector<int> prof_shapes;
 };
 
 const char* ganmf_last_error(void) { return g_err; }
@@ -188,6 +189,7 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
     CU(cudaEventRecord(ev1, c->st));
     c->prof_flops += 2.0 * M * N * K;
     c->prof_launches += 1;
+    c->prof_shapes.insert(c->prof_shapes.end(), {M, N, K, splits});
   }
   return 0;
 }
@@ -344,7 +346,20 @@ int ganmf_profile(ganmf_ctx* c, int enable) {
   if (!c) return fail("null ctx");
   CU(cudaStreamSynchronize(c->st));
   c->profile = enable != 0;
-  c->ev_used = 0; c->prof_flops = 0; c->prof_launches = 0;
+  c->ev_used = 0; c->prof_flops = 0; c->prof_launches = 0; c->prof_shapes.clear();
+  return 0;
+}
+int ganmf_profile_records(ganmf_ctx* c, double* ms, int32_t* shape, int cap, int* n) {
+  if (!c || !n) return fail("null argument");
+  CU(cudaStreamSynchronize(c->st));
+  int k = 0;
+  for (size_t i = 0; i + 1 < c->ev_used && k < cap; i += 2, ++k) {
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, c->ev_pool[i], c->ev_pool[i + 1]));
+    if (ms) ms[k] = t;
+    if (shape) memcpy(shape + 4 * k, c->prof_shapes.data() + 4 * k, 16);
+  }
+  *n = k;
   return 0;
 }
 int ganmf_profile_read(ganmf_ctx* c, double* ms, double* flops, int64_t* launches) {
@@ -359,7 +374,7 @@ int ganmf_profile_read(ganmf_ctx* c, double* ms, double* flops, int64_t* launche
   if (ms) *ms = total;
   if (flops) *flops = c->prof_flops;
   if (launches) *launches = c->prof_launches;
-  c->ev_used = 0; c->prof_flops = 0; c->prof_launches = 0;
+  c->ev_used = 0; c->prof_flops = 0; c->prof_launches = 0; c->prof_shapes.clear();
   return 0;
 }
 
@@ -524,6 +539,7 @@ static int adam_group(ganmf_ctx* c, int first, int count, float alpha, float reg
   }
   a.alpha = alpha; a.reg = reg;
   a.l2_out = &c->sc->l2;
+  a.l2_shard_out = &c->sc->l2_shard;
   c->launches++;
   CU(fused_adam(a, c->st));
   return 0;
@@ -631,9 +647,12 @@ static int g_apply_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float
   RC(adam_group(c, c->n_d, 2, adam_alpha(c, 1, lr), reg, c->n_d));
   set_slots_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(c->slot, ids, B, 1);
   CU(cudaGetLastError());
-  finalize_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, reg, c->losses, loss_slot);
-  CU(cudaGetLastError());
-  c->launches += 4;
+  c->launches += 3;
+  if (n_global == B) {       // under data parallelism the caller sums l2_shard over ranks first
+    finalize_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, reg, c->losses, loss_slot);
+    CU(cudaGetLastError());
+    c->launches++;
+  }
   return 0;
 }
 
@@ -802,6 +821,14 @@ int ganmf_g_step(ganmf_ctx* c, int ids_offset, int B, int n_global, float lr, fl
   return g_apply_impl(c, ids_offset, B, n_global, lr, reg, alpha, loss_slot);
 }
 
+int ganmf_finalize_loss(ganmf_ctx* c, float reg, int loss_slot) {
+  if (!c || loss_slot < 0 || loss_slot >= c->losses_cap) return fail("bad argument");
+  finalize_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, reg, c->losses, loss_slot);
+  CU(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
 int ganmf_read_losses(ganmf_ctx* c, float* host, int n) {
   if (!c || n < 0 || n > c->losses_cap) return fail("bad loss count");
   CU(cudaMemcpyAsync(host, c->losses, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
@@ -840,7 +867,7 @@ int ganmf_device_buffer(ganmf_ctx* c, const char* name, void** ptr, int64_t* n) 
   if (!c || !name || !ptr || !n) return fail("null argument");
   if (!strcmp(name, "d_grads")) { *ptr = c->d_slab + 3 * c->d_elems; *n = (int64_t)c->d_elems; return 0; }
   if (!strcmp(name, "g_shared_grad")) { *ptr = c->v_slab + 3 * c->v_elems; *n = (int64_t)c->v_elems; return 0; }
-  if (!strcmp(name, "step_scalars")) { *ptr = c->sc; *n = 6; return 0; }
+  if (!strcmp(name, "step_scalars")) { *ptr = c->sc; *n = 7; return 0; }
   return fail("unknown buffer %s", name);
 }
 
@@ -931,6 +958,29 @@ int ganmf_score(ganmf_ctx* c, const int32_t* users, int n, float* scores_host) {
   CU(cudaMemcpy2DAsync(scores_host, (size_t)n_items * 4, c->scores, (size_t)ild * 4, (size_t)n_items * 4, n,
                        cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int ganmf_encode(ganmf_ctx* c, const int32_t* rows, int n, float* codes_host) {
+  if (!c || !rows || !codes_host || n <= 0) return fail("bad argument");
+  if (c->cfg.kind != GANMF_KIND_GANMF) return fail("encode: GANMF only");
+  const Csr& tr = c->csr[GANMF_CSR_TRAIN];
+  if (!tr.indptr) return fail("train CSR not set");
+  for (int i = 0; i < n; ++i)
+    if (rows[i] < 0 || rows[i] >= c->cfg.n_rows) return fail("row id %d out of range", rows[i]);
+  Param *We = &c->params[0], *be = &c->params[1];
+  for (int s = 0; s < n; s += c->B) {
+    const int b = std::min(c->B, n - s);
+    CU(cudaMemcpyAsync(c->ids, rows + s, (size_t)b * 4, cudaMemcpyHostToDevice, c->st));
+    CU(csr_gather_dense(tr.indptr, tr.indices, tr.data, c->ids, b, c->X2.p, c->X2.ld, 0, c->st));
+    c->launches++;
+    Epilogue e;
+    e.out = c->H2.p; e.ldo = c->H2.ld; e.bias = be->w.p;
+    RC(gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, b, c->E, c->W, e));
+    CU(cudaMemcpy2DAsync(codes_host + (size_t)s * c->E, (size_t)c->E * 4, c->H2.p, (size_t)c->H2.ld * 4,
+                         (size_t)c->E * 4, b, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+  }
   return 0;
 }
 

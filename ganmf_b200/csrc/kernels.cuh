@@ -128,6 +128,7 @@ struct AdamArgs {
   int nseg;
   float alpha, reg;
   double* l2_out;          // += sum theta_old^2 (nullable)
+  double* l2_shard_out;    // same, for segments that carry a slot map (row-sharded under DP)
 };
 constexpr int ADAM_THREADS = 256;
 constexpr int ADAM_VEC_PER_THREAD = 4;     // float4s per thread
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) fused_adam_kernel(const AdamArgs
     if (threadIdx.x < 32) {
       float x = threadIdx.x < ADAM_THREADS / 32 ? red[threadIdx.x] : 0.f;
       x = warp_sum(x);
-      if (threadIdx.x == 0) atomicAdd(a.l2_out, (double)x);
+      if (threadIdx.x == 0) atomicAdd((sg.slot && a.l2_shard_out) ? a.l2_shard_out : a.l2_out, (double)x);
     }
   }
 }
@@ -294,6 +295,7 @@ struct StepScalars {
   double fm;           // sum (Hr-Hf)^2 / sum (feat_r-feat_f)^2
   double l2;           // sum theta^2 over the optimiser's tensors (Adam kernel accumulates)
   double bce[2];       // DisGANMF: sum softplus(-out_r), sum softplus(out_f)
+  double l2_shard;     // sum theta^2 of row-sharded tensors (user factors): summed over ranks under DP
   float row_scale[2];  // GANMF D-step: cr' = (1+g*m)*2/N, cf' = -g*2/N
   float loss_main;     // loss without the l2 term
   float pad;
@@ -319,7 +321,7 @@ __global__ void gloss_kernel(StepScalars* s, float alpha, double n_elems, double
 
 // losses[slot] = loss_main + reg * l2 / 2     (l2 accumulated by the Adam kernel, pre-update)
 __global__ void finalize_loss_kernel(const StepScalars* s, float reg, float* losses, int slot) {
-  losses[slot] = s->loss_main + (float)(reg * 0.5 * s->l2);
+  losses[slot] = s->loss_main + (float)(reg * 0.5 * (s->l2 + s->l2_shard));
 }
 
 // ----------------------------------------------------------------------------- activations

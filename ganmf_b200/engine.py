@@ -57,6 +57,14 @@ class Engine(object):
     def profile(self, enable):
         L.check(self.lib.ganmf_profile(self.ctx, int(enable)))
 
+    def profile_records(self, cap=4096):
+        ms = np.zeros(cap, dtype=np.float64)
+        shp = np.zeros((cap, 4), dtype=np.int32)
+        n = C.c_int32()
+        L.check(self.lib.ganmf_profile_records(self.ctx, ms.ctypes.data_as(L._f64p), shp.ctypes.data_as(L._i32p),
+                                               cap, C.byref(n)))
+        return ms[:n.value], shp[:n.value]
+
     def profile_read(self):
         ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
         L.check(self.lib.ganmf_profile_read(self.ctx, C.byref(ms), C.byref(fl), C.byref(n)))
@@ -155,6 +163,9 @@ class Engine(object):
     def g_apply(self, B, n_rows_global, lr, reg, recon_coefficient, loss_slot):
         L.check(self.lib.ganmf_g_apply(self.ctx, B, n_rows_global, lr, reg, recon_coefficient, loss_slot))
 
+    def finalize_loss(self, reg, loss_slot):
+        L.check(self.lib.ganmf_finalize_loss(self.ctx, reg, loss_slot))
+
     def read_losses(self, n):
         out = np.empty(n, dtype=np.float32)
         L.check(self.lib.ganmf_read_losses(self.ctx, out.ctypes.data_as(L._f32p), n))
@@ -175,6 +186,12 @@ class Engine(object):
         a, p = L.i32(users)
         out = np.empty((a.size, self.n_items), dtype=np.float32)
         L.check(self.lib.ganmf_score(self.ctx, p, a.size, out.ctypes.data_as(L._f32p)))
+        return out
+
+    def encode(self, rows):
+        a, p = L.i32(rows)
+        out = np.empty((a.size, self.cfg.emb_dim), dtype=np.float32)
+        L.check(self.lib.ganmf_encode(self.ctx, p, a.size, out.ctypes.data_as(L._f32p)))
         return out
 
     def mask_topk(self, scores, K, users=None, remove_seen=False, write_back=False):

@@ -46,6 +46,9 @@ class DataParallelTrainer(object):
         self._sum(self.g_shared)
         self._sum(self.scalars)
         self.eng.g_apply(B, n_global, lr, reg, recon_coefficient, loss_slot)
+        if reg != 0.0:
+            self._sum(self.scalars[6:7])          # ||P||^2 lives in row shards
+        self.eng.finalize_loss(reg, loss_slot)
 
     def train_epoch(self, perm_local, batch_size, d_steps, g_steps, hp):
         """Reference schedule (GANMF.py:172-203) on this rank's shard; every rank must pass the same

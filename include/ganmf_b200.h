@@ -99,6 +99,9 @@ int ganmf_g_forward_backward(ganmf_ctx* ctx, int ids_offset, int B, int n_rows_g
                              float recon_coefficient);
 int ganmf_g_apply(ganmf_ctx* ctx, int B, int n_rows_global, float lr, float reg,
                   float recon_coefficient, int loss_slot);
+/* Data-parallel G step only (n_rows_global != B): after ganmf_g_apply, sum step_scalars[6] (the l2 of
+ * the row-sharded user factors) over ranks, then write loss_slot. */
+int ganmf_finalize_loss(ganmf_ctx* ctx, float reg, int loss_slot);
 /* One epoch of the reference schedule (GANMF.py:172-203): shuffled row ids in, d_steps full D
  * passes then g_steps full G passes over the same batches, per-batch losses out (host).
  * H2D: n_rows ids; D2H: the losses.  Synchronises once at the end. */
@@ -109,13 +112,17 @@ int ganmf_train_epoch(ganmf_ctx* ctx, const int32_t* perm_host, int n_ids, int b
 int ganmf_read_losses(ganmf_ctx* ctx, float* host, int n);        /* loss log [0, n) -> host    */
 /* Raw device buffers for the collectives (wrap with __cuda_array_interface__; fp32 unless noted):
  * "d_grads" (all discriminator gradients, contiguous), "g_shared_grad" (item-factor gradient),
- * "step_scalars" (6 float64: sumsq_real, sumsq_fake, feature-matching, l2, bce_real, bce_fake). */
+ * "step_scalars" (7 float64: sumsq_real, sumsq_fake, feature-matching, l2 of replicated tensors,
+ * bce_real, bce_fake, l2 of the row-sharded user factors). */
 int ganmf_device_buffer(ganmf_ctx* ctx, const char* name, void** dev_ptr, int64_t* n_elems);
 
 /* ---- scoring / recommendation / evaluation ---------------------------------------------- */
 /* ~ _compute_item_score (GANMF.py:285-292): scores_host[n][n_items], user ids in scoring
  * orientation.  H2D: ids; D2H: n * n_items floats. */
 int ganmf_score(ganmf_ctx* ctx, const int32_t* user_ids_host, int n, float* scores_host);
+/* ~ autoencoder_codes (GANMF.py:304-307): codes_host[n][emb_dim] = R[row_ids] . We + be for training rows
+ * (GANMF only). */
+int ganmf_encode(ganmf_ctx* ctx, const int32_t* row_ids_host, int n, float* codes_host);
 /* ~ BaseRecommender.recommend (:155-247) on a given fp32 score matrix: optional seen mask from
  * GANMF_CSR_SEEN, then top-K (descending score, ties -> lowest index).  idx = -1 where the score is
  * -inf.  scores_host is updated in place with the mask when write_back != 0. */
@@ -155,6 +162,9 @@ int ganmf_k_topk(ganmf_ctx* ctx, const float* scores, int ld, int n, int n_items
  * launch count of those GEMMs since the last read. */
 int ganmf_profile(ganmf_ctx* ctx, int enable);
 int ganmf_profile_read(ganmf_ctx* ctx, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+/* Per-launch records of the same window (call BEFORE ganmf_profile_read): ms[i] and the GEMM shape
+ * shape[4*i..] = {M, N, K, splits}; returns the number of records written (<= cap) in *n. */
+int ganmf_profile_records(ganmf_ctx* ctx, double* ms, int32_t* shape, int cap, int* n);
 /* number of kernels this library has launched since ganmf_create (bench.py's gpu_launches) */
 int64_t ganmf_launch_count(ganmf_ctx* ctx);
 

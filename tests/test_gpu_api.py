@@ -112,3 +112,43 @@ def test_disganmf_fit_and_scores():
         assert last == 6
         res, _ = EvaluatorHoldout(test, cutoff_list=[5], exclude_seen=True).evaluateRecommender(rec)
         assert np.isfinite(res[5]["NDCG"])
+
+
+def test_autoencoder_codes_and_factors():
+    from ganmf_b200.GANRec.GANMF import GANMF
+    train, _ = small_data(4)
+    rec = GANMF(train, mode="user", seed=2, is_experiment=True)
+    rec.fit(num_factors=8, emb_dim=24, epochs=1, batch_size=50)
+    w = rec.get_weights()
+    codes = rec.autoencoder_codes()                          # GANMF.py:304-307
+    want = train.toarray() @ w["autoencoder/encoding/kernel"] + w["autoencoder/encoding/bias"]
+    assert codes.shape == want.shape
+    assert np.max(np.abs(codes - want)) < 2e-3 * np.sqrt(np.maximum(train.getnnz(1).max(), 1))
+    assert np.array_equal(rec.user_factors(), w["generator/user_embeddings"])
+    assert np.array_equal(rec.item_factors(), w["generator/item_embeddings"])
+
+
+def test_load_reference_tf_bundle(tmp_path):
+    """A model saved by the reference (tf.train.Saver bundle: raw fp32, variables in name order) loads."""
+    import pickle
+    from ganmf_b200.GANRec.GANMF import GANMF
+    train, _ = small_data(5)
+    n_users, n_items = train.shape
+    k, E = 6, 10
+    rs = np.random.RandomState(0)
+    tensors = {"autoencoder/decoding/bias": rs.randn(n_items), "autoencoder/decoding/kernel": rs.randn(E, n_items),
+               "autoencoder/encoding/bias": rs.randn(E), "autoencoder/encoding/kernel": rs.randn(n_items, E),
+               "generator/item_embeddings": rs.randn(n_items, k), "generator/user_embeddings": rs.randn(n_users, k)}
+    with open(tmp_path / "GANMF_user.data-00000-of-00001", "wb") as f:
+        for name in sorted(tensors):
+            f.write(tensors[name].astype("<f4").tobytes())
+    with open(tmp_path / "build_params.pkl", "wb") as f:
+        pickle.dump({"num_factors": k, "emb_dim": E}, f)
+    rec = GANMF(train, mode="user", is_experiment=True)
+    rec.loadModel(str(tmp_path))
+    got = rec.get_weights()
+    for name in tensors:
+        assert np.array_equal(got[name], tensors[name].astype(np.float32))
+    s = rec._compute_item_score(np.arange(10))
+    want = tensors["generator/user_embeddings"][:10].astype(np.float32) @ tensors["generator/item_embeddings"].astype(np.float32).T
+    assert np.max(np.abs(s - want)) < 1e-4

@@ -21,7 +21,7 @@ class FakeEngine(object):
 
     def d_forward(self, off, B):
         self.log.append("d_forward")
-        self.b["step_scalars"][:] = torch.tensor([1.0 + self.rank, 10.0 * (1 + self.rank), 0, 0, 0, 0],
+        self.b["step_scalars"][:] = torch.tensor([1.0 + self.rank, 10.0 * (1 + self.rank), 0, 0, 0, 0, 0],
                                                  dtype=torch.float64)
 
     def d_backward(self, B, n_global, m):
@@ -39,6 +39,9 @@ class FakeEngine(object):
     def g_apply(self, B, n_global, lr, reg, a, slot):
         self.log.append(("g_apply", self.b["g_shared_grad"].tolist(), self.b["step_scalars"][0].item()))
 
+    def finalize_loss(self, reg, slot):
+        self.log.append("finalize")
+
     def evaluate(self, users, cutoffs, remove_seen=True):
         return np.full((len(cutoffs), 3), float(len(users))), np.full((len(cutoffs), 5), self.rank + 1, dtype=np.int64)
 
@@ -47,7 +50,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    bufs = {"d_grads": torch.zeros(4), "g_shared_grad": torch.zeros(3), "step_scalars": torch.zeros(6, dtype=torch.float64)}
+    bufs = {"d_grads": torch.zeros(4), "g_shared_grad": torch.zeros(3), "step_scalars": torch.zeros(7, dtype=torch.float64)}
     eng = FakeEngine(rank, bufs)
     tr = DataParallelTrainer(eng, world, buffers=bufs)
     tr.d_step(0, 8, 1e-3, 0.0, 1.0, 0)
@@ -76,7 +79,7 @@ def test_dp_step_collectives_gloo():
         assert log[1] == ("d_backward", 16, [3.0, 30.0])          # scalars summed BEFORE the backward
         assert log[2] == ("d_apply", [3.0] * 4)                    # gradients summed before Adam
         assert log[3] == ("g_fb", 16)
-        assert log[4] == ("g_apply", [30.0] * 3, 3.0)
+        assert log[4] == ("g_apply", [30.0] * 3, 3.0) and log[5] == "finalize"
         assert n == 7 and sums == [[7.0] * 3] * 2 and counts == [[3] * 5] * 2
 
 
