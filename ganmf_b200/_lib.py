@@ -54,6 +54,7 @@ SIGNATURES = {
     "ganmf_g_step": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]),
     "ganmf_d_forward": (C.c_int, [_ctx, C.c_int, C.c_int]),
     "ganmf_d_backward": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_float]),
+    "ganmf_d_backward_phase": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_float, C.c_int]),
     "ganmf_d_apply": (C.c_int, [_ctx, C.c_float, C.c_float, C.c_int]),
     "ganmf_g_forward_backward": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float]),
     "ganmf_g_apply": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]),

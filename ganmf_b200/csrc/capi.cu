@@ -153,20 +153,23 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   g.bn = N > 128 ? 256 : 128;
   const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + g.bn - 1) / g.bn);
   const int total_kb = (K + TC_BK - 1) / TC_BK;
-  // Split K when the output has too few tiles to fill the 148 SMs: pick the split count with the best
-  // wave efficiency units / (ceil(units / 148) * 148), at least 8 k-blocks per split.
+  // Split K when the output has too few tiles to fill the 148 SMs.  Cost model per candidate split
+  // count s: MMA rounds ceil(tiles*s/148) * (k-blocks per split) in units of one k-block of one tile,
+  // plus the partial-sum traffic (s copies of the M x N output written and read again) converted to the
+  // same unit (a 128 x BN x 32 tf32 k-block at ~600 TFLOP/s vs ~5 TB/s of workspace traffic).
   int splits = 1;
   if (tiles < 148 && total_kb >= 16) {
     const size_t per = (size_t)M * rup(N, 4);
-    int smax = std::min(std::min(total_kb / 8, 64), (int)std::min<size_t>(c->ws_floats / per, 64));
-    double best = (double)tiles / 148.0;
-    for (int sp = 2; sp <= smax; ++sp) {
+    const int smax = std::min(std::min(total_kb / 8, 64), (int)std::min<size_t>(c->ws_floats / per, 64));
+    const double kb_us = 2.0 * TC_BM * g.bn * TC_BK / (600e6 / 148.0);       // us per k-block per tile on one SM
+    double best = 1e30;
+    for (int sp = 1; sp <= smax; ++sp) {
       const int kbps = (total_kb + sp - 1) / sp;
-      const int real = (total_kb + kbps - 1) / kbps;
-      if (real != sp) continue;
-      const int units = tiles * sp;
-      const double eff = (double)units / (((units + 147) / 148) * 148.0);
-      if (eff > best + 0.02) { best = eff; splits = sp; }
+      if ((total_kb + kbps - 1) / kbps != sp) continue;
+      const int rounds = (tiles * sp + 147) / 148;
+      double cost = rounds * kbps * kb_us;
+      if (sp > 1) cost += 2.0 * sp * per * 4 / 5e6 + 3.0;                     // workspace traffic + reduce launch
+      if (cost < best) { best = cost; splits = sp; }
     }
   }
   g.splits = splits;
@@ -560,12 +563,17 @@ static int ganmf_d_forward_impl(ganmf_ctx* c, int ids_offset, int B) {
   return gemm(c, c->H2.p, c->H2.ld, 0, Wd->w.p, Wd->w.ld, 1, 2 * B, c->W, c->E, e3);
 }
 
-static int ganmf_d_backward_impl(ganmf_ctx* c, int B, int n_global, float m_hinge) {
+// phase 1: hinge gate, decoder gradients (dWd, dbd); phase 2: dH, encoder gradients (dWe, dbe);
+// phase 0: both.  The cut lets a data-parallel caller start summing the decoder gradients over ranks
+// while the encoder half is still being computed.
+static int ganmf_d_backward_impl(ganmf_ctx* c, int B, int n_global, float m_hinge, int phase) {
   Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
+  const float* rs = c->sc->row_scale;
+  if (phase == 2) goto second_half;
+  {
   const double n_elems = (double)n_global * c->W;
   hinge_gate_kernel<<<1, 1, 0, c->st>>>(c->sc, m_hinge, n_elems);
   CU(cudaGetLastError());
-  const float* rs = c->sc->row_scale;
   scale_rows_kernel<<<dim3(std::max(1, c->H2.ld / 4 / 128), 2 * B), 128, 0, c->st>>>(
       c->H2.p, c->H2s.p, c->H2.ld / 4, rs, B);
   CU(cudaGetLastError());
@@ -575,16 +583,21 @@ static int ganmf_d_backward_impl(ganmf_ctx* c, int B, int n_global, float m_hing
   colsum_kernel<<<(c->W + 31) / 32, dim3(32, 8), 0, c->st>>>(c->Res2.p, 2 * B, c->W, c->Res2.ld, rs, B,
                                                             nullptr, bd->g);   // dbd
   CU(cudaGetLastError());
+  // dbe = colsum(dH2) = dbd . Wd^T, evaluated in fp32 from the LOCAL fp32 column sums (no tensor-core
+  // rounding); it belongs to phase 1 because a data-parallel caller sums dbd in place right after it
+  rowdot_kernel<<<(c->E + 7) / 8, 256, 0, c->st>>>(Wd->w.p, c->E, c->W, Wd->w.ld, bd->g, be->g);
+  CU(cudaGetLastError());
+  c->launches += 4;
+  }
+  if (phase == 1) return 0;
+second_half:
   Epilogue e5;                                                                     // G5: dH2
   e5.out = c->dH2.p; e5.ldo = c->dH2.ld; e5.row_scale2 = rs; e5.row_split = B;
   RC(gemm(c, c->Res2.p, c->Res2.ld, 0, Wd->w.p, Wd->w.ld, 0, 2 * B, c->E, c->W, e5));
-  // dbe = colsum(dH2) = dbd . Wd^T, evaluated in fp32 from the fp32 column sums (no tensor-core rounding)
-  rowdot_kernel<<<(c->E + 7) / 8, 256, 0, c->st>>>(Wd->w.p, c->E, c->W, Wd->w.ld, bd->g, be->g);
-  CU(cudaGetLastError());
   Epilogue e6;                                                                     // G6: dWe
   e6.out = We->g; e6.ldo = We->w.ld;
   RC(gemm(c, c->X2.p, c->X2.ld, 1, c->dH2.p, c->dH2.ld, 1, c->W, c->E, 2 * B, e6));
-  c->launches += 4;
+  c->launches += 1;
   return 0;
 }
 
@@ -792,8 +805,14 @@ int ganmf_d_forward(ganmf_ctx* c, int ids_offset, int B) {
 }
 int ganmf_d_backward(ganmf_ctx* c, int B, int n_global, float m_hinge) {
   if (!c) return fail("null ctx");
-  return c->cfg.kind == GANMF_KIND_GANMF ? ganmf_d_backward_impl(c, B, n_global, m_hinge)
+  return c->cfg.kind == GANMF_KIND_GANMF ? ganmf_d_backward_impl(c, B, n_global, m_hinge, 0)
                                          : dis_d_backward_impl(c, B, n_global);
+}
+int ganmf_d_backward_phase(ganmf_ctx* c, int B, int n_global, float m_hinge, int phase) {
+  if (!c) return fail("null ctx");
+  if (c->cfg.kind != GANMF_KIND_GANMF) return fail("phased backward: GANMF only");
+  if (phase < 0 || phase > 2) return fail("phase must be 0, 1 or 2");
+  return ganmf_d_backward_impl(c, B, n_global, m_hinge, phase);
 }
 int ganmf_d_apply(ganmf_ctx* c, float lr, float reg, int loss_slot) {
   if (!c) return fail("null ctx");
@@ -866,6 +885,12 @@ int ganmf_train_epoch(ganmf_ctx* c, const int32_t* perm, int n_ids, int batch, i
 int ganmf_device_buffer(ganmf_ctx* c, const char* name, void** ptr, int64_t* n) {
   if (!c || !name || !ptr || !n) return fail("null argument");
   if (!strcmp(name, "d_grads")) { *ptr = c->d_slab + 3 * c->d_elems; *n = (int64_t)c->d_elems; return 0; }
+  if (!strcmp(name, "d_grads_enc")) {        // dWe | dbe
+    *ptr = c->params[0].g; *n = (int64_t)(c->params[0].w.elems() + c->params[1].w.elems()); return 0;
+  }
+  if (!strcmp(name, "d_grads_dec")) {        // dWd | dbd
+    *ptr = c->params[2].g; *n = (int64_t)(c->params[2].w.elems() + c->params[3].w.elems()); return 0;
+  }
   if (!strcmp(name, "g_shared_grad")) { *ptr = c->v_slab + 3 * c->v_elems; *n = (int64_t)c->v_elems; return 0; }
   if (!strcmp(name, "step_scalars")) { *ptr = c->sc; *n = 7; return 0; }
   return fail("unknown buffer %s", name);

@@ -63,8 +63,10 @@ __device__ __forceinline__ unsigned long long tk_kth(const unsigned long long (&
   return __shfl_sync(0xffffffffu, v, owner);
 }
 
-// One CTA per score row, 8 warps stream interleaved 512-byte tiles with 16-byte loads; the per-warp
-// winners are merged by rank.  Algorithmic bytes: 4*n_items read + 8*K written per row.
+// One CTA per score row; its 1..8 warps stream interleaved 512-byte tiles with 16-byte loads and the
+// per-warp winners are merged by rank.  Fewer warps per row mean fewer (latency-bound) insertions per
+// row, so the launcher uses as few as still give every SM ~32 warps.
+// Algorithmic bytes: 4*n_items read + 8*K written per row.
 template <int J>
 __global__ void __launch_bounds__(TK_THREADS)
 topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, int* __restrict__ out_idx,
@@ -72,6 +74,7 @@ topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, i
   __shared__ unsigned long long sbuf[TK_WARPS][32 * J];
   __shared__ int scnt[TK_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = blockDim.x >> 5;                       // warps working on this row
   const float* row = scores + (size_t)blockIdx.x * ld;
   unsigned long long lst[J];
 #pragma unroll
@@ -90,37 +93,51 @@ topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, i
     if (c + 2 < n_items) v.z = row[c + 2];
     return v;
   };
-  float4 nxt = load_tile(warp);
-  for (int t = warp; t < n_tiles; t += TK_WARPS) {
-    const float4 v = nxt;
-    nxt = load_tile(t + TK_WARPS);                      // prefetch the warp's next tile
-    const int c = t * 128 + lane * 4;
-    const float vs[4] = {v.x, v.y, v.z, v.w};
-    unsigned hi[4];
-    bool any = false;
+  // The warp walks its tiles (warp, warp+8, ...) in batches of TK_DEPTH with the next batch already in
+  // flight: 2*TK_DEPTH 16-byte loads per lane outstanding keep the row streaming at HBM speed.
+  constexpr int TK_DEPTH = 4;
+  float4 nxt[TK_DEPTH];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float f = vs[e];
-      unsigned u = f == 0.f ? 0u : __float_as_uint(f);
-      u = (f != f) ? 0u : (u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u));
-      hi[e] = u;
-      any |= (u >= thr_hi) && (c + e < n_items);
-    }
-    if (!__any_sync(0xffffffffu, any)) continue;        // fast path: nothing can beat the K-th best
+  for (int d = 0; d < TK_DEPTH; ++d) nxt[d] = load_tile(warp + d * nw);
+  for (int t0 = warp; t0 < n_tiles; t0 += nw * TK_DEPTH) {
+    float4 cur[TK_DEPTH];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const unsigned long long key =
-          ((unsigned long long)hi[e] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(c + e));
-      bool pass = (c + e < n_items) && key > thr;
-      unsigned bal;
-      while ((bal = __ballot_sync(0xffffffffu, pass)) != 0u) {
-        const int src = __ffs(bal) - 1;
-        const unsigned long long x = __shfl_sync(0xffffffffu, key, src);
-        tk_insert<J>(lst, x, lane);
-        thr = tk_kth<J>(lst, K);
-        thr_hi = (unsigned)(thr >> 32);
-        if (lane == src) pass = false;
-        pass = pass && key > thr;
+    for (int d = 0; d < TK_DEPTH; ++d) cur[d] = nxt[d];
+#pragma unroll
+    for (int d = 0; d < TK_DEPTH; ++d) nxt[d] = load_tile(t0 + (TK_DEPTH + d) * nw);
+#pragma unroll
+    for (int d = 0; d < TK_DEPTH; ++d) {
+      const int t = t0 + d * nw;
+      if (t >= n_tiles) break;                          // warp-uniform
+      const float4 v = cur[d];
+      const int c = t * 128 + lane * 4;
+      const float vs[4] = {v.x, v.y, v.z, v.w};
+      unsigned hi[4];
+      bool any = false;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float f = vs[e];
+        unsigned u = f == 0.f ? 0u : __float_as_uint(f);
+        u = (f != f) ? 0u : (u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u));
+        hi[e] = u;
+        any |= (u >= thr_hi) && (c + e < n_items);
+      }
+      if (!__any_sync(0xffffffffu, any)) continue;      // fast path: nothing can beat the K-th best
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned long long key =
+            ((unsigned long long)hi[e] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(c + e));
+        bool pass = (c + e < n_items) && key > thr;
+        unsigned bal;
+        while ((bal = __ballot_sync(0xffffffffu, pass)) != 0u) {
+          const int src = __ffs(bal) - 1;
+          const unsigned long long x = __shfl_sync(0xffffffffu, key, src);
+          tk_insert<J>(lst, x, lane);
+          thr = tk_kth<J>(lst, K);
+          thr_hi = (unsigned)(thr >> 32);
+          if (lane == src) pass = false;
+          pass = pass && key > thr;
+        }
       }
     }
   }
@@ -138,14 +155,13 @@ topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, i
   if (lane == 0) scnt[warp] = mine;
   __syncthreads();
   int total = 0;
-#pragma unroll
-  for (int w = 0; w < TK_WARPS; ++w) total += scnt[w];
-  for (int e = threadIdx.x; e < TK_WARPS * K; e += TK_THREADS) {
+  for (int w = 0; w < nw; ++w) total += scnt[w];
+  for (int e = threadIdx.x; e < nw * K; e += blockDim.x) {
     const int w = e / K, p = e - w * K;
     if (p >= scnt[w]) continue;
     const unsigned long long key = sbuf[w][p];
     int rank = p;
-    for (int w2 = 0; w2 < TK_WARPS; ++w2) {
+    for (int w2 = 0; w2 < nw; ++w2) {
       if (w2 == w) continue;
       int lo = 0, hi2 = scnt[w2];                       // first position in list w2 with key' < key
       while (lo < hi2) {
@@ -161,7 +177,7 @@ topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, i
       out_val[(size_t)blockIdx.x * K + rank] = sc;
     }
   }
-  for (int j = total + threadIdx.x; j < K; j += TK_THREADS) {
+  for (int j = total + threadIdx.x; j < K; j += blockDim.x) {
     out_idx[(size_t)blockIdx.x * K + j] = -1;
     out_val[(size_t)blockIdx.x * K + j] = -INFINITY;
   }
@@ -170,9 +186,13 @@ topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, i
 inline cudaError_t topk_rows(const float* scores, int ld, int n, int n_items, int K, int* out_idx, float* out_val,
                              cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  if (K <= 32) topk_rows_kernel<1><<<n, TK_THREADS, 0, st>>>(scores, ld, n_items, K, out_idx, out_val);
-  else if (K <= 64) topk_rows_kernel<2><<<n, TK_THREADS, 0, st>>>(scores, ld, n_items, K, out_idx, out_val);
-  else topk_rows_kernel<4><<<n, TK_THREADS, 0, st>>>(scores, ld, n_items, K, out_idx, out_val);
+  int wpr = 8;                                          // warps per row: keep >= ~32 warps per SM
+  while (wpr > 1 && (long long)n * (wpr / 2) >= 148LL * 32) wpr >>= 1;
+  while (wpr > 1 && (n_items + 127) / 128 < wpr * 4) wpr >>= 1;   // short rows: not worth splitting
+  const int threads = 32 * wpr;
+  if (K <= 32) topk_rows_kernel<1><<<n, threads, 0, st>>>(scores, ld, n_items, K, out_idx, out_val);
+  else if (K <= 64) topk_rows_kernel<2><<<n, threads, 0, st>>>(scores, ld, n_items, K, out_idx, out_val);
+  else topk_rows_kernel<4><<<n, threads, 0, st>>>(scores, ld, n_items, K, out_idx, out_val);
   return cudaGetLastError();
 }
 

@@ -318,8 +318,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ep.bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
             float* dst = ep.out + (size_t)(mw + sub_r) * ep.ldo + n;
-            const float* p1 = ep.c1 ? ep.c1 + (size_t)(mw + sub_r) * ep.ldc1 + n : nullptr;
-            const float* p2 = ep.c2 ? ep.c2 + (size_t)(mw + sub_r) * ep.ldc2 + n : nullptr;
+            // all addend loads of the chunk are issued before any store (the stores may alias them as far
+            // as the compiler knows), so their latency is paid once per chunk, not once per row group
+            float4 t1[8], t2[8];
+            if (ep.c1) {
+              const float* p1 = ep.c1 + (size_t)(mw + sub_r) * ep.ldc1 + n;
+#pragma unroll
+              for (int itr = 0; itr < 8; ++itr)
+                t1[itr] = __ldg(reinterpret_cast<const float4*>(p1 + (size_t)itr * 4 * ep.ldc1));
+            }
+            if (ep.c2) {
+              const float* p2 = ep.c2 + (size_t)(mw + sub_r) * ep.ldc2 + n;
+#pragma unroll
+              for (int itr = 0; itr < 8; ++itr)
+                t2[itr] = __ldg(reinterpret_cast<const float4*>(p2 + (size_t)itr * 4 * ep.ldc2));
+            }
 #pragma unroll
             for (int itr = 0; itr < 8; ++itr) {
               const int row = itr * 4 + sub_r;
@@ -328,15 +341,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const float sc = ep.alpha * (lower ? rs1 : rs0);
               float4 o = make_float4(fmaf(sc, a.x, b4.x), fmaf(sc, a.y, b4.y), fmaf(sc, a.z, b4.z),
                                      fmaf(sc, a.w, b4.w));
-              if (p1) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p1 + (size_t)itr * 4 * ep.ldc1));
-                o.x = fmaf(ep.beta1, t.x, o.x); o.y = fmaf(ep.beta1, t.y, o.y);
-                o.z = fmaf(ep.beta1, t.z, o.z); o.w = fmaf(ep.beta1, t.w, o.w);
+              if (ep.c1) {
+                o.x = fmaf(ep.beta1, t1[itr].x, o.x); o.y = fmaf(ep.beta1, t1[itr].y, o.y);
+                o.z = fmaf(ep.beta1, t1[itr].z, o.z); o.w = fmaf(ep.beta1, t1[itr].w, o.w);
               }
-              if (p2) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p2 + (size_t)itr * 4 * ep.ldc2));
-                o.x = fmaf(ep.beta2, t.x, o.x); o.y = fmaf(ep.beta2, t.y, o.y);
-                o.z = fmaf(ep.beta2, t.z, o.z); o.w = fmaf(ep.beta2, t.w, o.w);
+              if (ep.c2) {
+                o.x = fmaf(ep.beta2, t2[itr].x, o.x); o.y = fmaf(ep.beta2, t2[itr].y, o.y);
+                o.z = fmaf(ep.beta2, t2[itr].z, o.z); o.w = fmaf(ep.beta2, t2[itr].w, o.w);
               }
               if (ep.act != ACT_LINEAR) {
                 o.x = act_fwd(ep.act, o.x); o.y = act_fwd(ep.act, o.y);

@@ -154,6 +154,9 @@ class Engine(object):
     def d_backward(self, B, n_rows_global, m_hinge):
         L.check(self.lib.ganmf_d_backward(self.ctx, B, n_rows_global, m_hinge))
 
+    def d_backward_phase(self, B, n_rows_global, m_hinge, phase):
+        L.check(self.lib.ganmf_d_backward_phase(self.ctx, B, n_rows_global, m_hinge, phase))
+
     def d_apply(self, lr, reg, loss_slot):
         L.check(self.lib.ganmf_d_apply(self.ctx, lr, reg, loss_slot))
 

@@ -21,13 +21,18 @@ class DataParallelTrainer(object):
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.eng, self.world, self.group = engine, world_size, group
+        self.overlap = False
         if buffers is None:
             dev = torch.device("cuda", torch.cuda.current_device())
-            buffers = {n: torch.as_tensor(engine.device_buffer(n), device=dev)
-                       for n in ("d_grads", "g_shared_grad", "step_scalars")}
+            names = ["d_grads", "g_shared_grad", "step_scalars"]
+            if engine.cfg.kind == 0:                 # GANMF: decoder / encoder halves for the overlapped sum
+                names += ["d_grads_dec", "d_grads_enc"]
+                self.overlap = True
+            buffers = {n: torch.as_tensor(engine.device_buffer(n), device=dev) for n in names}
             engine.set_stream(torch.cuda.current_stream().cuda_stream)
         self.d_grads, self.g_shared, self.scalars = (buffers["d_grads"], buffers["g_shared_grad"],
                                                      buffers["step_scalars"])
+        self.d_dec, self.d_enc = buffers.get("d_grads_dec"), buffers.get("d_grads_enc")
 
     def _sum(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
@@ -36,8 +41,16 @@ class DataParallelTrainer(object):
         n_global = B * self.world
         self.eng.d_forward(ids_offset, B)
         self._sum(self.scalars)
-        self.eng.d_backward(B, n_global, m_hinge)
-        self._sum(self.d_grads)
+        if self.overlap:
+            # decoder gradients are summed on NCCL's stream while the encoder half is still computed
+            self.eng.d_backward_phase(B, n_global, m_hinge, 1)
+            w = self.dist.all_reduce(self.d_dec, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.eng.d_backward_phase(B, n_global, m_hinge, 2)
+            self._sum(self.d_enc)
+            w.wait()
+        else:
+            self.eng.d_backward(B, n_global, m_hinge)
+            self._sum(self.d_grads)
         self.eng.d_apply(lr, reg, loss_slot)
 
     def g_step(self, ids_offset, B, lr, reg, recon_coefficient, loss_slot):

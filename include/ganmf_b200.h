@@ -94,6 +94,9 @@ int ganmf_g_step(ganmf_ctx* ctx, int ids_offset, int B, int n_rows_global, float
  *   g_forward_backward -> allreduce(g shared grad + step scalars) -> g_apply */
 int ganmf_d_forward(ganmf_ctx* ctx, int ids_offset, int B);
 int ganmf_d_backward(ganmf_ctx* ctx, int B, int n_rows_global, float m_hinge);
+/* GANMF: the D backward in two halves so the sum of the decoder gradients ("d_grads_dec") can overlap the
+ * computation of the encoder half ("d_grads_enc"): phase 1 = gate + dWd,dbd; phase 2 = dH + dWe,dbe; 0 = both */
+int ganmf_d_backward_phase(ganmf_ctx* ctx, int B, int n_rows_global, float m_hinge, int phase);
 int ganmf_d_apply(ganmf_ctx* ctx, float lr, float reg, int loss_slot);
 int ganmf_g_forward_backward(ganmf_ctx* ctx, int ids_offset, int B, int n_rows_global,
                              float recon_coefficient);
