@@ -55,26 +55,52 @@ def peaks():
 
 
 class ClockSampler(object):
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (NVML every ~2 ms; nvidia-smi as a fallback)."""
+    SMI_Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
+        self.index, self.sm, self.bits, self.max_mhz, self.stop, self.src = index, [], 0, None, False, "nvml"
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(reasons(h))
+                time.sleep(0.002)
+            self.names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                          "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                          "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                          "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        except Exception:
+            self.src = "nvidia-smi"
+            self.smi_reasons = set()
+            while not self.stop:
+                try:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.SMI_Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                         timeout=5).stdout
+                    r = [x.strip() for x in out.strip().split(",")]
+                    self.sm.append(float(r[0]))
+                    self.max_mhz = float(r[1])
+                    for name, col in (("hw_slowdown", 2), ("hw_thermal_slowdown", 3), ("sw_thermal_slowdown", 4),
+                                      ("sw_power_cap", 5)):
+                        if r[col].lower().startswith("active"):
+                            self.smi_reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.05)
 
     def __enter__(self):
         self.t.start()
+        time.sleep(0.01)
         return self
 
     def __exit__(self, *a):
@@ -82,15 +108,22 @@ class ClockSampler(object):
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        reasons = []
-        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
-                          ("sw_power_cap", 6)):
-            if any(len(r) >= 7 and r[col].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.src == "nvml":
+            reasons = [n for n, bit in getattr(self, "names", {}).items() if self.bits & bit]
+        else:
+            reasons = sorted(getattr(self, "smi_reasons", ()))
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.sm), "source": self.src}
+
+
+def gemm_algorithmic_bytes(c):
+    """Operand + output bytes (each read/written once) of the 13 tensor-core GEMMs of one D+G step pair."""
+    B, I, k, E = c["B"], c["items"], c["k"], c["E"]
+    f = 4.0
+    g = lambda M, N, K, extra=0: f * (M * K + N * K + M * N * (1 + extra))
+    d = g(B, I, k) + g(2 * B, E, I) + g(2 * B, I, E, 1) + g(E, I, 2 * B) + g(2 * B, E, I) + g(I, E, 2 * B)
+    gs = g(B, I, k) + g(2 * B, E, I) + g(B, I, E, 1) + g(B, E, I, 2) + g(B, I, E, 1) + g(I, k, B) + g(B, k, I)
+    return d + gs
 
 
 def flops_per_row(c):
@@ -246,9 +279,15 @@ def main():
     gemm_ms, gemm_flops, gemm_launches = eng.profile_read()
     eng.profile(False)
     pk = peaks()
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_tc_gemm_dram_traffic.json")
+    if os.path.exists(tpath):                                 # from the committed `ncu --set full` capture
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["dram_bytes_per_launch_mean"], "profiles/r01_tc_gemm_dram_traffic.json: " + tj["note"]
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"kernel": "tc_gemm_kernel (tcgen05 kind::tf32, TMA, TMEM)", "bound": "tensor", "achieved": achieved,
-                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": None,
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch_mean": gemm_algorithmic_bytes(c) / 13.0,
                 "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json); kind::tf32 issues at half the "
                 "bf16 rate, so frac <= 0.5 by construction", "frac_of_tf32_rate": 2 * achieved / pk["tf_sust"],
                 "gemm_launches_per_step": gemm_launches / K, "gemm_share_of_step": gemm_ms / (ms if world == 1 else

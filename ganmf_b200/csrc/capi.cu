@@ -107,6 +107,7 @@ struct ganmf_ctx {
   double prof_flops = 0;
   long long prof_launches = 0;
   std::vector<int> prof_shapes;
+  TmapCache tmaps;
 };
 
 const char* ganmf_last_error(void) { return g_err; }
@@ -174,6 +175,7 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   }
   g.splits = splits;
   g.ws = c->ws;
+  g.cache = &c->tmaps;
   c->launches += splits > 1 ? 2 : 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (c->profile) {
@@ -951,10 +953,11 @@ static int prepare_item_factors(ganmf_ctx* c) {
   return 0;
 }
 // scores[n, items] for the users already in c->eval_users (device); prepare_item_factors() first
-static int score_block(ganmf_ctx* c, int n) {
+static int score_block(ganmf_ctx* c, int n, const int* users_dev = nullptr) {
+  if (!users_dev) users_dev = c->eval_users;
   const Param& rows_of = c->cfg.item_mode ? c->params[c->n_d + 1] : c->params[c->n_d];
   const int n_items = c->Ob.rows;
-  split3_rows_kernel<<<n, 64, 0, c->st>>>(rows_of.w.p, rows_of.w.ld, c->eval_users, c->Fb.p, c->Fb.ld, c->k, 0);
+  split3_rows_kernel<<<n, 64, 0, c->st>>>(rows_of.w.p, rows_of.w.ld, users_dev, c->Fb.p, c->Fb.ld, c->k, 0);
   CU(cudaGetLastError());
   c->launches++;
   Epilogue e;
@@ -1009,14 +1012,15 @@ int ganmf_encode(ganmf_ctx* c, const int32_t* rows, int n, float* codes_host) {
   return 0;
 }
 
-static int mask_and_topk(ganmf_ctx* c, int n, int n_items, int remove_seen, int K) {
+static int mask_and_topk(ganmf_ctx* c, int n, int n_items, int remove_seen, int K, const int* users_dev = nullptr) {
+  if (!users_dev) users_dev = c->eval_users;
   if (K < 1 || K > TK_MAXK) return fail("top-K supports 1 <= K <= %d (got %d)", TK_MAXK, K);
   const int ild = rup(n_items, 32);
   if (remove_seen) {
     const Csr& seen = c->csr[GANMF_CSR_SEEN];
     if (!seen.indptr) return fail("seen CSR not set");
     if (seen.n_cols != n_items) return fail("seen CSR has %d columns, scores have %d", seen.n_cols, n_items);
-    mask_seen_kernel<<<n, 128, 0, c->st>>>(c->scores, ild, c->eval_users, seen.indptr, seen.indices);
+    mask_seen_kernel<<<n, 128, 0, c->st>>>(c->scores, ild, users_dev, seen.indptr, seen.indices);
     CU(cudaGetLastError());
     c->launches++;
   }
@@ -1110,22 +1114,30 @@ int ganmf_set_eval_tables(ganmf_ctx* c, const float* gain, const float* gain_des
 }
 
 // metric stage for n rows whose lists are in c->topk_idx and users in c->eval_users
-static int metrics_block(ganmf_ctx* c, int n, int K, int n_cut, int n_items, bool with_rmse) {
+// per-user metric values for n rows whose lists are in c->topk_idx; `uvals` points at the first of those
+// rows inside the per-user value table.  The running sums are formed afterwards by accumulate_users().
+static int metrics_block(ganmf_ctx* c, int n, int K, int n_cut, int n_items, bool with_rmse,
+                         const int* users_dev, double* uvals) {
   const int total = n * n_cut;
-  user_metrics_kernel<<<(total + 127) / 128, 128, 0, c->st>>>(c->topk_idx, K, c->eval_users, n, c->cut_dev,
-                                                            n_cut, c->tb, c->uvals, c->icounts, n_items);
+  user_metrics_kernel<<<(total + 127) / 128, 128, 0, c->st>>>(c->topk_idx, K, users_dev, n, c->cut_dev, n_cut,
+                                                            c->tb, uvals, c->icounts, n_items);
   CU(cudaGetLastError());
+  c->launches++;
   if (with_rmse) {
     const Csr& te = c->csr[GANMF_CSR_TEST];
-    user_rmse_kernel<<<(n + 63) / 64, 64, 0, c->st>>>(c->scores, rup(n_items, 32), c->eval_users, n, n_cut,
-                                                    c->tb, te.data, c->rmse_scratch, c->uvals);
+    user_rmse_kernel<<<(n + 63) / 64, 64, 0, c->st>>>(c->scores, rup(n_items, 32), users_dev, n, n_cut, c->tb,
+                                                    te.data, c->rmse_scratch, uvals);
     CU(cudaGetLastError());
     c->launches++;
   }
+  return 0;
+}
+// sums[cutoff][metric] = sum over users IN ORDER (Evaluator.py:305-335 keeps one running sum)
+static int accumulate_users(ganmf_ctx* c, int n_users, int n_cut) {
   const int ncols = n_cut * MC_NCOL;
-  ordered_accumulate_kernel<<<(ncols + 63) / 64, 64, 0, c->st>>>(c->uvals, n, ncols, c->usums);
+  ordered_accumulate_kernel<<<(ncols + 63) / 64, 64, 0, c->st>>>(c->uvals, n_users, ncols, c->usums);
   CU(cudaGetLastError());
-  c->launches += 2;
+  c->launches++;
   return 0;
 }
 
@@ -1151,17 +1163,30 @@ int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_
   if (block <= 0) block = std::min(1000, std::max(1, (int)(1e8 / n_items)));   // Evaluator.py:238
   block = std::min(block, std::max(n_users, 1));
   RC(ensure_eval_buffers(c, block, K, n_cut));
+  if (c->eval_users_cap < n_users) {                       // all user ids go up once
+    cudaFree(c->eval_users);
+    RC(dalloc(&c->eval_users, (size_t)n_users));
+    c->eval_users_cap = n_users;
+  }
+  const size_t uv = (size_t)n_users * n_cut * MC_NCOL;     // per-user value table for the whole call
+  if (uv > c->uvals_cap) {
+    cudaFree(c->uvals);
+    RC(dalloc(&c->uvals, uv));
+    c->uvals_cap = uv;
+  }
+  CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n_users * 4, cudaMemcpyHostToDevice, c->st));
   CU(cudaMemcpyAsync(c->cut_dev, cutoffs, (size_t)n_cut * 4, cudaMemcpyHostToDevice, c->st));
   CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
   CU(cudaMemsetAsync(c->icounts, 0, (size_t)n_cut * n_items * 4, c->st));
   RC(prepare_item_factors(c));
   for (int s = 0; s < n_users; s += block) {
     const int n = std::min(block, n_users - s);
-    CU(cudaMemcpyAsync(c->eval_users, users + s, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
-    RC(score_block(c, n));
-    RC(mask_and_topk(c, n, n_items, remove_seen, K));
-    RC(metrics_block(c, n, K, n_cut, n_items, true));
+    const int* ud = c->eval_users + s;
+    RC(score_block(c, n, ud));
+    RC(mask_and_topk(c, n, n_items, remove_seen, K, ud));
+    RC(metrics_block(c, n, K, n_cut, n_items, true, ud, c->uvals + (size_t)s * n_cut * MC_NCOL));
   }
+  RC(accumulate_users(c, n_users, n_cut));
   CU(cudaMemcpyAsync(sums_host, c->usums, (size_t)n_cut * MC_NCOL * 8, cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));
   if (counts_host) {
@@ -1212,7 +1237,8 @@ int ganmf_metrics_from_topk(ganmf_ctx* c, const int32_t* topk, int K, const int3
   CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
   CU(cudaMemsetAsync(c->icounts, 0, ic * 4, c->st));
   CU(cudaMemsetAsync(c->uvals, 0, uv * 8, c->st));
-  RC(metrics_block(c, n, K, n_cut, n_items, false));
+  RC(metrics_block(c, n, K, n_cut, n_items, false, c->eval_users, c->uvals));
+  RC(accumulate_users(c, n, n_cut));
   CU(cudaMemcpyAsync(sums_host, c->usums, (size_t)n_cut * MC_NCOL * 8, cudaMemcpyDeviceToHost, c->st));
   if (per_user) CU(cudaMemcpyAsync(per_user, c->uvals, uv * 8, cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));

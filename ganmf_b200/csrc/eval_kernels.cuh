@@ -80,7 +80,7 @@ topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, i
 #pragma unroll
   for (int j = 0; j < J; ++j) lst[j] = 0ull;
   unsigned long long thr = 0ull;
-  unsigned thr_hi = 0u;
+  float thr_f = -INFINITY;                              // score of the current K-th best
   const int n_tiles = (n_items + 127) / 128;
   const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   auto load_tile = [&](int t) -> float4 {
@@ -110,23 +110,16 @@ topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, i
       const int t = t0 + d * nw;
       if (t >= n_tiles) break;                          // warp-uniform
       const float4 v = cur[d];
+      // fast path (8 instructions per 16 bytes): plain float compares against the score of the K-th
+      // best.  NaN never passes, out-of-range lanes hold -inf; while the list is not full thr_f = -inf
+      // sends everything to the exact path below.
+      const bool any = (v.x >= thr_f) | (v.y >= thr_f) | (v.z >= thr_f) | (v.w >= thr_f);
+      if (!__any_sync(0xffffffffu, any)) continue;
       const int c = t * 128 + lane * 4;
       const float vs[4] = {v.x, v.y, v.z, v.w};
-      unsigned hi[4];
-      bool any = false;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float f = vs[e];
-        unsigned u = f == 0.f ? 0u : __float_as_uint(f);
-        u = (f != f) ? 0u : (u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u));
-        hi[e] = u;
-        any |= (u >= thr_hi) && (c + e < n_items);
-      }
-      if (!__any_sync(0xffffffffu, any)) continue;      // fast path: nothing can beat the K-th best
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const unsigned long long key =
-            ((unsigned long long)hi[e] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(c + e));
+        const unsigned long long key = topk_key(vs[e], c + e);
         bool pass = (c + e < n_items) && key > thr;
         unsigned bal;
         while ((bal = __ballot_sync(0xffffffffu, pass)) != 0u) {
@@ -134,7 +127,7 @@ topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, i
           const unsigned long long x = __shfl_sync(0xffffffffu, key, src);
           tk_insert<J>(lst, x, lane);
           thr = tk_kth<J>(lst, K);
-          thr_hi = (unsigned)(thr >> 32);
+          thr_f = (thr >> 32) ? topk_key_score(thr) : -INFINITY;
           if (lane == src) pass = false;
           pass = pass && key > thr;
         }

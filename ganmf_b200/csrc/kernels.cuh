@@ -152,8 +152,10 @@ __global__ void __launch_bounds__(ADAM_THREADS) fused_adam_kernel(const AdamArgs
     if (i < sg.n4) {
       t[j] = th[i]; m[j] = mm[i]; v[j] = vv[i];
       if (sg.slot) {
-        const unsigned long long row = i / ld4;
-        const int sl = sg.slot[row];
+        // row of the factor matrix this float4 belongs to (32-bit division whenever the segment allows it)
+        const unsigned long long row = sg.n4 < 0xFFFFFFFFull ? (unsigned long long)((unsigned)i / (unsigned)ld4)
+                                                             : i / (unsigned long long)ld4;
+        const int sl = __ldg(sg.slot + row);
         g[j] = sl >= 0 ? gg[(unsigned long long)sl * ld4 + (i - row * ld4)] : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
         g[j] = gg[i];

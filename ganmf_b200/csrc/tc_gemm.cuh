@@ -450,11 +450,46 @@ inline PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// Tensor maps are pure functions of (pointer, extents, pitch, box, swizzle, dtype) and the operands of
+// the training step live in persistent buffers, so the encoded descriptors are memoised: small-batch
+// configurations are launch-bound and would otherwise re-encode ~26 maps per step on the host.
+struct TmapKey {
+  const void* ptr; int rows, cols, ld, box_cols, box_rows, dtype, swizzle;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols &&
+           box_rows == o.box_rows && dtype == o.dtype && swizzle == o.swizzle;
+  }
+};
+struct TmapCache {
+  static constexpr int N = 256;
+  TmapKey keys[N];
+  CUtensorMap maps[N];
+  bool used[N] = {};
+  static unsigned hash(const TmapKey& k) {
+    unsigned long long h = (unsigned long long)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+    h ^= (unsigned long long)k.rows * 0xBF58476D1CE4E5B9ull + (unsigned long long)k.cols * 0x94D049BB133111EBull +
+         (unsigned)k.box_rows * 31u + (unsigned)k.swizzle;
+    return (unsigned)(h >> 40);
+  }
+  const CUtensorMap* find(const TmapKey& k) const {
+    const unsigned i = hash(k) % N;
+    return used[i] && keys[i] == k ? &maps[i] : nullptr;
+  }
+  void put(const TmapKey& k, const CUtensorMap& m) {
+    const unsigned i = hash(k) % N;          // direct-mapped: a collision simply evicts
+    keys[i] = k; maps[i] = m; used[i] = true;
+  }
+};
+
 // fp32 row-major matrix [rows][cols] with leading dimension ld (elements);
 // box = {box_cols (contiguous), box_rows}; 128B swizzle; OOB reads give zeros.
 inline int make_tmap_2d(CUtensorMap* map, const float* ptr, int rows, int cols, int ld,
                         int box_cols, int box_rows, int tmap_dtype,
-                        int swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B) {
+                        int swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B, TmapCache* cache = nullptr) {
+  const TmapKey key{ptr, rows, cols, ld, box_cols, box_rows, tmap_dtype, swizzle};
+  if (cache) {
+    if (const CUtensorMap* hit = cache->find(key)) { *map = *hit; return 0; }
+  }
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return 1;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -464,6 +499,7 @@ inline int make_tmap_2d(CUtensorMap* map, const float* ptr, int rows, int cols, 
   CUresult r = enc(map, (CUtensorMapDataType)tmap_dtype, 2, const_cast<float*>(ptr), gdim, gstr,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS && cache) cache->put(key, *map);
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
@@ -480,6 +516,7 @@ struct TcGemmCall {
   int tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
   // bring-up overrides for the MN-major tile encoding (0 = use the defaults below)
   int dbg_mn_layout = 0, dbg_mn_sbo = 0, dbg_mn_lbo = 0, dbg_mn_swizzle = 0, dbg_epi = 0;
+  TmapCache* cache = nullptr;
 };
 
 inline uint32_t make_idesc_tf32(int bn, int a_mn, int b_mn) {
@@ -530,11 +567,12 @@ inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   CUtensorMap ma, mb;
   int rc;
   const int mn_swz = c.dbg_mn_swizzle ? c.dbg_mn_swizzle : (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  if (!c.a_mn) rc = make_tmap_2d(&ma, c.A, c.M, c.K, c.lda, TC_BK, TC_BM, c.tmap_dtype);
-  else         rc = make_tmap_2d(&ma, c.A, c.K, c.M, c.lda, 32, TC_BK, c.tmap_dtype, mn_swz);
+  const int k_swz = (int)CU_TENSOR_MAP_SWIZZLE_128B;
+  if (!c.a_mn) rc = make_tmap_2d(&ma, c.A, c.M, c.K, c.lda, TC_BK, TC_BM, c.tmap_dtype, k_swz, c.cache);
+  else         rc = make_tmap_2d(&ma, c.A, c.K, c.M, c.lda, 32, TC_BK, c.tmap_dtype, mn_swz, c.cache);
   if (rc) return cudaErrorUnknown;
-  if (!c.b_mn) rc = make_tmap_2d(&mb, c.B, c.N, c.K, c.ldb, TC_BK, bn, c.tmap_dtype);
-  else         rc = make_tmap_2d(&mb, c.B, c.K, c.N, c.ldb, 32, TC_BK, c.tmap_dtype, mn_swz);
+  if (!c.b_mn) rc = make_tmap_2d(&mb, c.B, c.N, c.K, c.ldb, TC_BK, bn, c.tmap_dtype, k_swz, c.cache);
+  else         rc = make_tmap_2d(&mb, c.B, c.K, c.N, c.ldb, 32, TC_BK, c.tmap_dtype, mn_swz, c.cache);
   if (rc) return cudaErrorUnknown;
 
   TcGemmArgs args;
