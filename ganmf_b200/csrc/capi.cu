@@ -587,7 +587,7 @@ static int ganmf_d_backward_impl(ganmf_ctx* c, int B, int n_global, float m_hing
   CU(cudaGetLastError());
   // dbe = colsum(dH2) = dbd . Wd^T, evaluated in fp32 from the LOCAL fp32 column sums (no tensor-core
   // rounding); it belongs to phase 1 because a data-parallel caller sums dbd in place right after it
-  rowdot_kernel<<<(c->E + 7) / 8, 256, 0, c->st>>>(Wd->w.p, c->E, c->W, Wd->w.ld, bd->g, be->g);
+  rowdot_kernel<<<c->E, 256, 0, c->st>>>(Wd->w.p, c->E, c->W, Wd->w.ld, bd->g, be->g);
   CU(cudaGetLastError());
   c->launches += 4;
   }
@@ -842,6 +842,37 @@ int ganmf_g_step(ganmf_ctx* c, int ids_offset, int B, int n_global, float lr, fl
   return g_apply_impl(c, ids_offset, B, n_global, lr, reg, alpha, loss_slot);
 }
 
+// Adam on arbitrary element ranges of the discriminator slab (theta, m, v and grad share offsets): under
+// data parallelism each rank updates only the chunk whose summed gradient it received from the
+// reduce-scatter, then the updated parameters are all-gathered.  sum(theta^2) of the ranges goes to
+// l2_shard (summed over ranks by the caller before ganmf_finalize_loss).
+int ganmf_d_apply_ranges(ganmf_ctx* c, float lr, float reg, const int64_t* offsets, const int64_t* counts,
+                         int n_ranges) {
+  if (!c || !offsets || !counts || n_ranges < 1 || n_ranges > ADAM_MAX_SEG) return fail("bad argument");
+  AdamArgs a;
+  memset(&a, 0, sizeof a);
+  a.nseg = n_ranges;
+  for (int i = 0; i < n_ranges; ++i) {
+    if (offsets[i] < 0 || counts[i] < 0 || (offsets[i] & 3) || (counts[i] & 3) ||
+        (size_t)(offsets[i] + counts[i]) > c->d_elems)
+      return fail("range %d outside the discriminator slab or not a multiple of 4", i);
+    AdamSeg& s = a.seg[i];
+    s.theta = c->d_slab + offsets[i];
+    s.m = c->d_slab + c->d_elems + offsets[i];
+    s.v = c->d_slab + 2 * c->d_elems + offsets[i];
+    s.g = c->d_slab + 3 * c->d_elems + offsets[i];
+    s.slot = nullptr; s.ld = 4;
+    s.n4 = (unsigned long long)counts[i] / 4;
+  }
+  a.alpha = adam_alpha(c, 0, lr);
+  a.reg = reg;
+  a.l2_out = &c->sc->l2_shard;
+  a.l2_shard_out = &c->sc->l2_shard;
+  c->launches++;
+  CU(fused_adam(a, c->st));
+  return 0;
+}
+
 int ganmf_finalize_loss(ganmf_ctx* c, float reg, int loss_slot) {
   if (!c || loss_slot < 0 || loss_slot >= c->losses_cap) return fail("bad argument");
   finalize_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, reg, c->losses, loss_slot);
@@ -892,6 +923,13 @@ int ganmf_device_buffer(ganmf_ctx* c, const char* name, void** ptr, int64_t* n) 
   }
   if (!strcmp(name, "d_grads_dec")) {        // dWd | dbd
     *ptr = c->params[2].g; *n = (int64_t)(c->params[2].w.elems() + c->params[3].w.elems()); return 0;
+  }
+  if (!strcmp(name, "d_params")) { *ptr = c->d_slab; *n = (int64_t)c->d_elems; return 0; }
+  if (!strcmp(name, "d_params_enc")) {
+    *ptr = c->params[0].w.p; *n = (int64_t)(c->params[0].w.elems() + c->params[1].w.elems()); return 0;
+  }
+  if (!strcmp(name, "d_params_dec")) {
+    *ptr = c->params[2].w.p; *n = (int64_t)(c->params[2].w.elems() + c->params[3].w.elems()); return 0;
   }
   if (!strcmp(name, "g_shared_grad")) { *ptr = c->v_slab + 3 * c->v_elems; *n = (int64_t)c->v_elems; return 0; }
   if (!strcmp(name, "step_scalars")) { *ptr = c->sc; *n = 7; return 0; }

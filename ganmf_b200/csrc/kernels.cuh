@@ -236,25 +236,33 @@ __global__ void colsum_kernel(const float* __restrict__ X, int M, int N, int ld,
   }
 }
 
-// out[e] = sum_i W[e, i] * x[i]   (fp32, one warp per row of W; ld multiple of 4).
+// out[e] = sum_i W[e, i] * x[i]   (fp32; ld multiple of 4).
 // Bias gradient of the encoder without tensor-core rounding: dbe = dbd . Wd^T, because
 // colsum(rs * Res2 . Wd^T) = (sum_m rs(m) Res2[m, :]) . Wd^T  and the bracket IS dbd (GANMF.py:64-68).
-__global__ void rowdot_kernel(const float* __restrict__ W, int rows, int cols, int ld,
-                              const float* __restrict__ x, float* __restrict__ out) {
-  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (e >= rows) return;
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const float* __restrict__ W, int rows, int cols, int ld, const float* __restrict__ x,
+              float* __restrict__ out) {
+  // one CTA per row of W: 8 warps stream the row with 16-byte loads, fixed-order block reduction
+  const int e = blockIdx.x;
   const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)e * ld);
   const float4* x4 = reinterpret_cast<const float4*>(x);
   float acc = 0.f;
   const int n4 = cols >> 2;
-  for (int i = lane; i < n4; i += 32) {
-    const float4 a = w4[i], b = x4[i];
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const float4 a = w4[i], b = __ldg(x4 + i);
     acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
   }
-  for (int i = (n4 << 2) + lane; i < cols; i += 32) acc = fmaf(W[(size_t)e * ld + i], x[i], acc);
+  for (int i = (n4 << 2) + threadIdx.x; i < cols; i += 256) acc = fmaf(W[(size_t)e * ld + i], x[i], acc);
+  __shared__ float red[8];
   acc = warp_sum(acc);
-  if (lane == 0) out[e] = acc;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j];
+    out[e] = t;
+  }
 }
 
 // Y[m, :] = X[m, :] * row_scale2[m >= row_split]

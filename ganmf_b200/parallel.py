@@ -22,17 +22,30 @@ class DataParallelTrainer(object):
         self.torch, self.dist = torch, dist
         self.eng, self.world, self.group = engine, world_size, group
         self.overlap = False
+        self.sharded_adam = False
         if buffers is None:
             dev = torch.device("cuda", torch.cuda.current_device())
             names = ["d_grads", "g_shared_grad", "step_scalars"]
             if engine.cfg.kind == 0:                 # GANMF: decoder / encoder halves for the overlapped sum
-                names += ["d_grads_dec", "d_grads_enc"]
+                names += ["d_grads_dec", "d_grads_enc", "d_params_dec", "d_params_enc"]
                 self.overlap = True
             buffers = {n: torch.as_tensor(engine.device_buffer(n), device=dev) for n in names}
             engine.set_stream(torch.cuda.current_stream().cuda_stream)
         self.d_grads, self.g_shared, self.scalars = (buffers["d_grads"], buffers["g_shared_grad"],
                                                      buffers["step_scalars"])
         self.d_dec, self.d_enc = buffers.get("d_grads_dec"), buffers.get("d_grads_enc")
+        self.p_dec, self.p_enc = buffers.get("d_params_dec"), buffers.get("d_params_enc")
+        if self.overlap and self.p_dec is not None:
+            # reduce-scatter -> Adam on this rank's 1/N of every half -> all-gather of the parameters:
+            # same bytes on the wire as an all-reduce, but the (HBM-bound) optimiser work is divided by N
+            ne, nd = self.d_enc.numel(), self.d_dec.numel()
+            self.sharded_adam = world_size > 1 and ne % (4 * world_size) == 0 and nd % (4 * world_size) == 0
+            if self.sharded_adam:
+                r = dist.get_rank(group)
+                ce, cd = ne // world_size, nd // world_size
+                self._enc_chunk, self._dec_chunk = slice(r * ce, (r + 1) * ce), slice(r * cd, (r + 1) * cd)
+                # slab layout: [We | be | Wd | bd]  (enc half first)
+                self._ranges = ([r * ce, ne + r * cd], [ce, cd])
 
     def _sum(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
@@ -41,6 +54,20 @@ class DataParallelTrainer(object):
         n_global = B * self.world
         self.eng.d_forward(ids_offset, B)
         self._sum(self.scalars)
+        if self.sharded_adam:
+            d = self.dist
+            self.eng.d_backward_phase(B, n_global, m_hinge, 1)
+            w = d.reduce_scatter_tensor(self.d_dec[self._dec_chunk], self.d_dec, op=d.ReduceOp.SUM, group=self.group,
+                                        async_op=True)                   # overlaps the encoder half
+            self.eng.d_backward_phase(B, n_global, m_hinge, 2)
+            d.reduce_scatter_tensor(self.d_enc[self._enc_chunk], self.d_enc, op=d.ReduceOp.SUM, group=self.group)
+            w.wait()
+            self.eng.d_apply_ranges(lr, reg, *self._ranges)
+            d.all_gather_into_tensor(self.p_dec, self.p_dec[self._dec_chunk], group=self.group)
+            d.all_gather_into_tensor(self.p_enc, self.p_enc[self._enc_chunk], group=self.group)
+            self._sum(self.scalars[6:7])
+            self.eng.finalize_loss(reg, loss_slot)
+            return
         if self.overlap:
             # decoder gradients are summed on NCCL's stream while the encoder half is still computed
             self.eng.d_backward_phase(B, n_global, m_hinge, 1)

@@ -102,6 +102,11 @@ int ganmf_g_forward_backward(ganmf_ctx* ctx, int ids_offset, int B, int n_rows_g
                              float recon_coefficient);
 int ganmf_g_apply(ganmf_ctx* ctx, int B, int n_rows_global, float lr, float reg,
                   float recon_coefficient, int loss_slot);
+/* Data-parallel D step with sharded optimiser work: after a reduce-scatter of the gradient slab, run
+ * Adam on [offsets[i], offsets[i]+counts[i]) (elements of the discriminator slab, multiples of 4) only;
+ * the caller all-gathers "d_params" afterwards, sums step_scalars[6] and calls ganmf_finalize_loss. */
+int ganmf_d_apply_ranges(ganmf_ctx* ctx, float lr, float reg, const int64_t* offsets, const int64_t* counts,
+                         int n_ranges);
 /* Data-parallel G step only (n_rows_global != B): after ganmf_g_apply, sum step_scalars[6] (the l2 of
  * the row-sharded user factors) over ranks, then write loss_slot. */
 int ganmf_finalize_loss(ganmf_ctx* ctx, float reg, int loss_slot);
@@ -114,7 +119,9 @@ int ganmf_train_epoch(ganmf_ctx* ctx, const int32_t* perm_host, int n_ids, int b
                       float* g_losses_host);
 int ganmf_read_losses(ganmf_ctx* ctx, float* host, int n);        /* loss log [0, n) -> host    */
 /* Raw device buffers for the collectives (wrap with __cuda_array_interface__; fp32 unless noted):
- * "d_grads" (all discriminator gradients, contiguous), "g_shared_grad" (item-factor gradient),
+ * "d_grads" (all discriminator gradients, contiguous; GANMF halves: "d_grads_enc" = dWe|dbe,
+ * "d_grads_dec" = dWd|dbd), "d_params" (+ "_enc"/"_dec": the matching parameter ranges),
+ * "g_shared_grad" (item-factor gradient),
  * "step_scalars" (7 float64: sumsq_real, sumsq_fake, feature-matching, l2 of replicated tensors,
  * bce_real, bce_fake, l2 of the row-sharded user factors). */
 int ganmf_device_buffer(ganmf_ctx* ctx, const char* name, void** dev_ptr, int64_t* n_elems);
