@@ -372,9 +372,9 @@ def hbm_kernel_rooflines(eng, torch, L, c, pk):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps * 1e-3
 
-    n, I = 4096, c["items"]
+    n, I = 8192, c["items"]
     ld = (I + 31) // 32 * 32
-    sc = torch.randn((n, ld), device="cuda", dtype=torch.float32)                      # 442 MB > L2
+    sc = torch.randn((n, ld), device="cuda", dtype=torch.float32)                      # 885 MB >> L2
     idx = torch.empty((n, 10), device="cuda", dtype=torch.int32)
     val = torch.empty((n, 10), device="cuda", dtype=torch.float32)
     t = timed(lambda: L.check(eng.lib.ganmf_k_topk(eng.ctx, sc.data_ptr(), ld, n, I, 10, idx.data_ptr(),

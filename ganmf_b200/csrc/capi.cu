@@ -1172,8 +1172,9 @@ static int metrics_block(ganmf_ctx* c, int n, int K, int n_cut, int n_items, boo
 }
 // sums[cutoff][metric] = sum over users IN ORDER (Evaluator.py:305-335 keeps one running sum)
 static int accumulate_users(ganmf_ctx* c, int n_users, int n_cut) {
-  const int ncols = n_cut * MC_NCOL;
-  ordered_accumulate_kernel<<<(ncols + 63) / 64, 64, 0, c->st>>>(c->uvals, n_users, ncols, c->usums);
+  const int ncols = n_cut * MC_NCOL;                     // <= 32 * 13 = 416 < OA_THREADS? no: handled below
+  if (ncols > OA_THREADS) return fail("too many (cutoff, metric) columns for the ordered accumulation");
+  ordered_accumulate_kernel<<<1, OA_THREADS, 0, c->st>>>(c->uvals, n_users, ncols, c->usums);
   CU(cudaGetLastError());
   c->launches++;
   return 0;
@@ -1181,7 +1182,7 @@ static int accumulate_users(ganmf_ctx* c, int n_users, int n_cut) {
 
 static int eval_prologue(ganmf_ctx* c, const int32_t* cutoffs, int n_cut, int* Kout) {
   if (!c->have_tables) return fail("call ganmf_set_eval_tables first");
-  if (n_cut < 1 || n_cut > 32) return fail("1..32 cutoffs supported");
+  if (n_cut < 1 || n_cut * MC_NCOL > OA_THREADS) return fail("1..%d cutoffs supported", OA_THREADS / MC_NCOL);
   int K = 0;
   for (int i = 0; i < n_cut; ++i) K = std::max(K, cutoffs[i]);
   if (K > TK_MAXK) return fail("cutoff %d > %d", K, TK_MAXK);
@@ -1198,7 +1199,10 @@ int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_
   const int n_items = n_items_of(c);
   if (c->csr[GANMF_CSR_TEST].n_cols != n_items) return fail("test CSR column count mismatch");
   if (!c->csr[GANMF_CSR_TEST].data) return fail("test CSR needs ratings (data) for RMSE");
-  if (block <= 0) block = std::min(1000, std::max(1, (int)(1e8 / n_items)));   // Evaluator.py:238
+  // The reference scores min(1000, 1e8/n_items) users at a time to bound HOST memory (Evaluator.py:238);
+  // the result does not depend on the block size, so on the device a block is as many users as a
+  // 1 GiB score buffer holds (at most 8192): fuller kernels, fewer launches.
+  if (block <= 0) block = (int)std::min<long long>(8192, std::max<long long>(1, (1LL << 28) / rup(n_items, 32)));
   block = std::min(block, std::max(n_users, 1));
   RC(ensure_eval_buffers(c, block, K, n_cut));
   if (c->eval_users_cap < n_users) {                       // all user ids go up once

@@ -179,8 +179,8 @@ topk_rows_kernel(const float* __restrict__ scores, int ld, int n_items, int K, i
 inline cudaError_t topk_rows(const float* scores, int ld, int n, int n_items, int K, int* out_idx, float* out_val,
                              cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  int wpr = 8;                                          // warps per row: keep >= ~32 warps per SM
-  while (wpr > 1 && (long long)n * (wpr / 2) >= 148LL * 32) wpr >>= 1;
+  int wpr = 8;                                          // warps per row: keep >= ~16 warps per SM
+  while (wpr > 1 && (long long)n * (wpr / 2) >= 148LL * 16) wpr >>= 1;
   while (wpr > 1 && (n_items + 127) / 128 < wpr * 4) wpr >>= 1;   // short rows: not worth splitting
   const int threads = 32 * wpr;
   if (K <= 32) topk_rows_kernel<1><<<n, threads, 0, st>>>(scores, ld, n_items, K, out_idx, out_val);
@@ -361,23 +361,55 @@ __global__ void user_rmse_kernel(const float* __restrict__ scores, int ld, const
   for (int ci = 0; ci < n_cut; ++ci) vals[((size_t)r * n_cut + ci) * MC_NCOL + MC_RMSE] = v;
 }
 
-// sums[col] += vals[row][col] for rows in order (one thread per (cutoff, metric) column).  The adds stay
-// strictly sequential (bit-exact vs the reference's running sum); loads are issued 16 at a time.
-__global__ void ordered_accumulate_kernel(const double* __restrict__ vals, int n_rows, int n_cols,
-                                          double* __restrict__ sums) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= n_cols) return;
-  double acc = sums[col];
-  int r = 0;
-  for (; r + 16 <= n_rows; r += 16) {
-    double v[16];
+// sums[col] += vals[row][col] for rows IN ORDER (bit-exact vs the reference's running sum, which is one
+// Python float per metric updated user after user).  Single CTA: the row-major value table is streamed
+// through shared memory in contiguous tiles (all threads load, coalesced, next tile in flight in
+// registers), and one thread per (cutoff, metric) column performs the strictly sequential adds.
+constexpr int OA_THREADS = 256;
+constexpr int OA_TILE = 2048;                 // doubles per tile (16 KB), two buffers
+__global__ void __launch_bounds__(OA_THREADS)
+ordered_accumulate_kernel(const double* __restrict__ vals, int n_rows, int n_cols, double* __restrict__ sums) {
+  __shared__ double buf[2][OA_TILE];
+  const int rows_per_tile = OA_TILE / n_cols;                 // host guarantees n_cols <= OA_TILE
+  const int n_tiles = (n_rows + rows_per_tile - 1) / rows_per_tile;
+  const size_t total = (size_t)n_rows * n_cols;
+  constexpr int PER = OA_TILE / OA_THREADS;
+  double pre[PER];
+  auto fetch = [&](int t) {
+    const size_t base = (size_t)t * rows_per_tile * n_cols;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = vals[(size_t)(r + j) * n_cols + col];
+    for (int j = 0; j < PER; ++j) {
+      const size_t i = base + threadIdx.x + (size_t)j * OA_THREADS;
+      pre[j] = (threadIdx.x + j * OA_THREADS < rows_per_tile * n_cols && i < total) ? vals[i] : 0.0;
+    }
+  };
+  auto stash = [&](int b) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc += v[j];
+    for (int j = 0; j < PER; ++j) buf[b][threadIdx.x + j * OA_THREADS] = pre[j];
+  };
+  double acc = threadIdx.x < n_cols ? sums[threadIdx.x] : 0.0;
+  if (n_tiles > 0) { fetch(0); stash(0); }
+  __syncthreads();
+  for (int t = 0; t < n_tiles; ++t) {
+    if (t + 1 < n_tiles) fetch(t + 1);                        // global loads in flight during the adds
+    if (threadIdx.x < n_cols) {
+      const int r0 = t * rows_per_tile;
+      const int nr = min(rows_per_tile, n_rows - r0);
+      const double* b = buf[t & 1] + threadIdx.x;
+      int r = 0;
+      for (; r + 8 <= nr; r += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = b[(r + j) * n_cols];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += v[j];
+      }
+      for (; r < nr; ++r) acc += b[r * n_cols];
+    }
+    if (t + 1 < n_tiles) stash((t + 1) & 1);
+    __syncthreads();
   }
-  for (; r < n_rows; ++r) acc += vals[(size_t)r * n_cols + col];
-  sums[col] = acc;
+  if (threadIdx.x < n_cols) sums[threadIdx.x] = acc;
 }
 
 }  // namespace ganmf
