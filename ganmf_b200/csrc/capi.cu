@@ -152,8 +152,15 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   g.M = M; g.N = N; g.K = K;
   g.ep = ep;
   g.bn = N > 128 ? 256 : 128;
-  const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + g.bn - 1) / g.bn);
+  int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + g.bn - 1) / g.bn);
   const int total_kb = (K + TC_BK - 1) / TC_BK;
+  // Small outputs with a long K (the split-K GEMMs) run 256-row CTA tiles: two accumulators share every
+  // B stage (1.5x flops per byte from L2; measured +9..11 % at 2048x1024x27000); no accumulator
+  // double-buffering is needed there because the epilogue is a small part of a long K loop.
+  if (tiles < 148 && g.bn == 256 && M >= 256 && N >= 512 && total_kb >= 256) {
+    g.mt = 2;
+    tiles = ((M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((N + g.bn - 1) / g.bn);
+  }
   // Split K when the output has too few tiles to fill the 148 SMs.  Cost model per candidate split
   // count s: MMA rounds ceil(tiles*s/148) * (k-blocks per split) in units of one k-block of one tile,
   // plus the partial-sum traffic (s copies of the M x N output written and read again) converted to the
@@ -162,7 +169,7 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   if (tiles < 148 && total_kb >= 16) {
     const size_t per = (size_t)M * rup(N, 4);
     const int smax = std::min(std::min(total_kb / 8, 64), (int)std::min<size_t>(c->ws_floats / per, 64));
-    const double kb_us = 2.0 * TC_BM * g.bn * TC_BK / (600e6 / 148.0);       // us per k-block per tile on one SM
+    const double kb_us = 2.0 * g.mt * TC_BM * g.bn * TC_BK / (600e6 / 148.0);   // us per k-block per tile on one SM
     double best = 1e30;
     for (int sp = 1; sp <= smax; ++sp) {
       const int kbps = (total_kb + sp - 1) / sp;
@@ -1203,8 +1210,10 @@ int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_
   // the result does not depend on the block size, so on the device a block is as many users as a
   // 1 GiB score buffer holds (at most 8192): fuller kernels, fewer launches.
   if (block <= 0) block = (int)std::min<long long>(8192, std::max<long long>(1, (1LL << 28) / rup(n_items, 32)));
-  block = std::min(block, std::max(n_users, 1));
+  // buffers are sized for the full block even when this call has fewer users, so later (larger) calls
+  // never re-allocate: cudaMalloc of a GiB-class buffer costs far more than the evaluation itself
   RC(ensure_eval_buffers(c, block, K, n_cut));
+  block = std::min(block, std::max(n_users, 1));
   if (c->eval_users_cap < n_users) {                       // all user ids go up once
     cudaFree(c->eval_users);
     RC(dalloc(&c->eval_users, (size_t)n_users));

@@ -78,6 +78,7 @@ struct TcGemmArgs {
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;   // smem descriptor strides, bytes >> 4
   uint32_t a_layout, b_layout;           // UMMA LayoutType of each operand's smem tile
   uint32_t a_kstep, b_kstep;             // start-address advance per UMMA_K, bytes >> 4
+  uint32_t a_mtstep;                     // start-address advance per 128-row sub-tile of A, bytes >> 4
   uint32_t idesc;
   Epilogue ep;
 };
@@ -109,9 +110,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
-template <int BN, int STAGES>
+// MT = number of 128-row MMA tiles stacked along M in one CTA tile (1 or 2).  MT = 2 (a 256 x BN CTA
+// tile, two accumulators sharing every B stage) raises the flops per byte fetched from L2 by 1.5x for
+// the long-K GEMMs that are L2-bandwidth bound; it fills the whole TMEM with BN = 256, so those tiles
+// do not double-buffer the accumulator (fine: their epilogue is a small fraction of a long K loop).
+template <int BN, int STAGES, int MT = 1>
 struct TcSmem {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 4;
+  static constexpr int A_BYTES = MT * TC_BM * TC_BK * 4;
   static constexpr int B_BYTES = BN * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;          // 8 warps x 32 rows x 8 float4 (swizzled)
@@ -124,7 +129,8 @@ struct TcSmem {
 // concurrently on neighbouring SMs) share the operand tile of the dimension with FEWER tiles: the
 // small operand stays L2 resident and the large one streams from HBM once.
 struct TcUnit { int m0, n0, split; };
-__device__ __forceinline__ TcUnit tc_unit(int u, int tiles_m, int tiles_n, int m_fastest, int BN) {
+__device__ __forceinline__ TcUnit tc_unit(int u, int tiles_m, int tiles_n, int m_fastest, int BN,
+                                          int BM = TC_BM) {
   const int tiles = tiles_m * tiles_n;
   TcUnit r;
   r.split = u / tiles;
@@ -132,18 +138,21 @@ __device__ __forceinline__ TcUnit tc_unit(int u, int tiles_m, int tiles_n, int m
   int tm, tn;
   if (m_fastest) { tn = t / tiles_m; tm = t - tn * tiles_m; }
   else           { tm = t / tiles_n; tn = t - tm * tiles_n; }
-  r.m0 = tm * TC_BM;
+  r.m0 = tm * BM;
   r.n0 = tn * BN;
   return r;
 }
 
 // Persistent kernel: grid = min(#units, #SMs); each CTA walks units blockIdx.x, +gridDim.x, ...
 // Two TMEM accumulator stages let the epilogue of unit i overlap the MMAs of unit i+1.
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcGemmArgs args) {
-  using S = TcSmem<BN, STAGES>;
+  using S = TcSmem<BN, STAGES, MT>;
+  constexpr int BM = MT * TC_BM;                       // CTA tile rows
+  constexpr int ACC = (2 * MT * BN <= 512) ? 2 : 1;    // accumulator stages that fit the 512 TMEM columns
+  constexpr int ACC_COLS = MT * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -156,7 +165,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_kb = (args.K + TC_BK - 1) / TC_BK;
-  const int tiles_m = (args.M + TC_BM - 1) / TC_BM;
+  const int tiles_m = (args.M + BM - 1) / BM;
   const int tiles_n = (args.N + BN - 1) / BN;
   const int n_units = tiles_m * tiles_n * args.splits;
   const int m_fastest = tiles_m <= tiles_n;
@@ -168,14 +177,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < ACC; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], 8);         // one arrival per epilogue warp
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 2 * BN);
+    ptx::tmem_alloc(tmem_slot, ACC * ACC_COLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -188,7 +197,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (ptx::elect_one()) {
       uint32_t it = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN);
+        const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN, BM);
         const int kb_begin = un.split * args.kb_per_split;
         const int kb_end = min(kb_begin + args.kb_per_split, total_kb);
         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
@@ -200,10 +209,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int k0 = kb * TC_BK;
           ptx::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
           if (!args.a_mn) {
-            ptx::tma_load_2d(sa, &map_a, &full_bar[s], k0, un.m0);          // box {32 k, 128 m}
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)                                 // box {32 k, 128 m}
+              ptx::tma_load_2d(sa + mt * (TC_BM * TC_BK * 4), &map_a, &full_bar[s], k0, un.m0 + mt * TC_BM);
           } else {
 #pragma unroll
-            for (int j = 0; j < TC_BM / 32; ++j)                            // box {32 m, 32 k}
+            for (int j = 0; j < BM / 32; ++j)                               // box {32 m, 32 k}
               ptx::tma_load_2d(sa + j * (TC_BK * 128), &map_a, &full_bar[s], un.m0 + 32 * j, k0);
           }
           if (!args.b_mn) {
@@ -221,13 +232,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (ptx::elect_one()) {
       uint32_t it = 0, ui = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-        const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN);
+        const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN, BM);
         const int kb_begin = un.split * args.kb_per_split;
         const int nkb = min(kb_begin + args.kb_per_split, total_kb) - kb_begin;
-        const uint32_t acc = ui & 1;
-        ptx::mbar_wait(&tmem_empty_bar[acc], ((ui >> 1) & 1) ^ 1);     // epilogue drained this stage
+        const uint32_t acc = ui % ACC;
+        ptx::mbar_wait(&tmem_empty_bar[acc], ((ui / ACC) & 1) ^ 1);    // epilogue drained this stage
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -239,8 +250,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint64_t db = make_smem_desc(sb, args.b_lbo, args.b_sbo, args.b_layout);
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-            ptx::mma_tf32_ss(tmem_d, da + (uint64_t)(k * args.a_kstep),
-                             db + (uint64_t)(k * args.b_kstep), args.idesc, (i | k) ? 1u : 0u);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)            // the 128-row sub-tiles share the B stage
+              ptx::mma_tf32_ss(tmem_d + mt * BN, da + (uint64_t)(mt * args.a_mtstep + k * args.a_kstep),
+                               db + (uint64_t)(k * args.b_kstep), args.idesc, (i | k) ? 1u : 0u);
           }
           ptx::mma_commit(&empty_bar[s]);          // frees the smem stage when those MMAs retire
         }
@@ -264,21 +277,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float rs0 = 1.f, rs1 = 1.f;
     if (!partial && ep.row_scale2) { rs0 = __ldg(ep.row_scale2); rs1 = __ldg(ep.row_scale2 + 1); }
     auto al16 = [](const void* p, int ld) { return (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    // fast path: 16-byte aligned everything, at most ONE addend matrix (the second addend and the rank-1
+    // term only occur in small / split-K GEMMs, which finish in the generic path or the reduce kernel)
     const bool vec_all = partial ? true
-                                 : (al16(ep.out, ep.ldo) && (!ep.c1 || al16(ep.c1, ep.ldc1)) &&
-                                    (!ep.c2 || al16(ep.c2, ep.ldc2)) && (!ep.bias || al16(ep.bias, 4)) &&
-                                    !ep.r1_row);
+                                 : (al16(ep.out, ep.ldo) && (!ep.c1 || al16(ep.c1, ep.ldc1)) && !ep.c2 &&
+                                    (!ep.bias || al16(ep.bias, 4)) && !ep.r1_row);
+    const bool use_c1 = !partial && ep.c1 != nullptr;
     float sq0 = 0.f, sq1 = 0.f;
     uint32_t ui = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-      const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN);
-      const uint32_t acc = ui & 1;
-      ptx::mbar_wait(&tmem_full_bar[acc], (ui >> 1) & 1);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      const int mw = un.m0 + q * 32;               // first row of this warp's 32-row slab
-      const bool interior = vec_all && (un.m0 + TC_BM <= args.M) && (un.n0 + BN <= args.N);
+      const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN, BM);
+      const uint32_t acc = ui % ACC;
+      const bool interior = vec_all && (un.m0 + BM <= args.M) && (un.n0 + BN <= args.N);
       const int c_end = (half + 1) * (BN / 2);
+      ptx::mbar_wait(&tmem_full_bar[acc], (ui / ACC) & 1);
+      ptx::tc_fence_after();
+      for (int mt = 0; mt < MT; ++mt) {
+      const uint32_t taddr = tmem_base + acc * ACC_COLS + mt * BN + ((uint32_t)(q * 32) << 16);
+      const int mw = un.m0 + mt * TC_BM + q * 32;   // first row of this warp's 32-row slab
       for (int c = half * (BN / 2); c < c_end; c += 32) {
         uint32_t r[32];
         if (args.dbg_epi < 2) {
@@ -288,7 +304,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
-        if (c + 32 >= c_end) {                     // last TMEM read of this warp for this unit
+        if (c + 32 >= c_end && mt == MT - 1) {     // last TMEM read of this warp for this unit
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -318,20 +334,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ep.bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
             float* dst = ep.out + (size_t)(mw + sub_r) * ep.ldo + n;
-            // all addend loads of the chunk are issued before any store (the stores may alias them as far
-            // as the compiler knows), so their latency is paid once per chunk, not once per row group
-            float4 t1[8], t2[8];
-            if (ep.c1) {
+            // the addend loads of the chunk are all issued before any store (the stores may alias them as
+            // far as the compiler knows), so their latency is paid once per chunk, not once per row group
+            float4 t1[8];
+            if (use_c1) {
               const float* p1 = ep.c1 + (size_t)(mw + sub_r) * ep.ldc1 + n;
 #pragma unroll
               for (int itr = 0; itr < 8; ++itr)
                 t1[itr] = __ldg(reinterpret_cast<const float4*>(p1 + (size_t)itr * 4 * ep.ldc1));
-            }
-            if (ep.c2) {
-              const float* p2 = ep.c2 + (size_t)(mw + sub_r) * ep.ldc2 + n;
-#pragma unroll
-              for (int itr = 0; itr < 8; ++itr)
-                t2[itr] = __ldg(reinterpret_cast<const float4*>(p2 + (size_t)itr * 4 * ep.ldc2));
             }
 #pragma unroll
             for (int itr = 0; itr < 8; ++itr) {
@@ -341,13 +351,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const float sc = ep.alpha * (lower ? rs1 : rs0);
               float4 o = make_float4(fmaf(sc, a.x, b4.x), fmaf(sc, a.y, b4.y), fmaf(sc, a.z, b4.z),
                                      fmaf(sc, a.w, b4.w));
-              if (ep.c1) {
+              if (use_c1) {
                 o.x = fmaf(ep.beta1, t1[itr].x, o.x); o.y = fmaf(ep.beta1, t1[itr].y, o.y);
                 o.z = fmaf(ep.beta1, t1[itr].z, o.z); o.w = fmaf(ep.beta1, t1[itr].w, o.w);
-              }
-              if (ep.c2) {
-                o.x = fmaf(ep.beta2, t2[itr].x, o.x); o.y = fmaf(ep.beta2, t2[itr].y, o.y);
-                o.z = fmaf(ep.beta2, t2[itr].z, o.z); o.w = fmaf(ep.beta2, t2[itr].w, o.w);
               }
               if (ep.act != ACT_LINEAR) {
                 o.x = act_fwd(ep.act, o.x); o.y = act_fwd(ep.act, o.y);
@@ -387,6 +393,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         __syncwarp();                               // slab is reused by the next chunk
       }
+      }
     }
     if (!partial && ep.sumsq2) {
 #pragma unroll
@@ -405,7 +412,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 2 * BN);
+    ptx::tmem_dealloc(tmem_base, ACC * ACC_COLS);
   }
 }
 
@@ -511,6 +518,7 @@ struct TcGemmCall {
   int splits = 1;          // > 1 needs ws
   float* ws = nullptr;     // >= splits * M * roundup(N,4) floats
   int bn = 128;            // 128 or 256
+  int mt = 1;              // 1: 128-row CTA tiles; 2: 256-row CTA tiles (needs bn == 256)
   // TFLOAT32 makes TMA round fp32 -> tf32 to nearest on the way into shared memory
   // (measured: FLOAT32 maps leave the bits alone and the MMA then truncates).
   int tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
@@ -533,13 +541,13 @@ inline uint32_t make_idesc_tf32(int bn, int a_mn, int b_mn) {
   return d;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT>
 inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const CUtensorMap& ma,
                                     const CUtensorMap& mb, int splits, cudaStream_t stream) {
-  using S = TcSmem<BN, STAGES>;
+  using S = TcSmem<BN, STAGES, MT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES>,
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, MT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -551,9 +559,9 @@ inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  const int units = ((c.N + BN - 1) / BN) * ((c.M + TC_BM - 1) / TC_BM) * splits;
+  const int units = ((c.N + BN - 1) / BN) * ((c.M + MT * TC_BM - 1) / (MT * TC_BM)) * splits;
   const int grid = units < num_sms ? units : num_sms;
-  tc_gemm_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, args);
+  tc_gemm_kernel<BN, STAGES, MT><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, args);
   return cudaGetLastError();
 }
 
@@ -603,14 +611,18 @@ inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   args.a_sbo = c.a_mn ? mn_sbo : 1024 >> 4;
   args.b_lbo = c.b_mn ? mn_lbo : 1;
   args.b_sbo = c.b_mn ? mn_sbo : 1024 >> 4;
+  // sub-tile mt of A starts TC_BM rows further: K-major rows are 128 B apart, MN-major 32-row chunks
+  // are one TMA box (TC_BK*128 B) apart
+  args.a_mtstep = c.a_mn ? ((TC_BM / 32) * TC_BK * 128) >> 4 : (TC_BM * TC_BK * 4) >> 4;
   args.a_kstep = c.a_mn ? (1024 >> 4) : (TC_UMMA_K * 4) >> 4;
   args.b_kstep = c.b_mn ? (1024 >> 4) : (TC_UMMA_K * 4) >> 4;
   args.idesc = make_idesc_tf32(bn, c.a_mn, c.b_mn);
   args.ep = c.ep;
 
   cudaError_t e;
-  if (bn == 256) e = tc_gemm_launch_t<256, 4>(c, args, ma, mb, splits, stream);
-  else           e = tc_gemm_launch_t<128, 6>(c, args, ma, mb, splits, stream);
+  if (bn == 256 && c.mt == 2) e = tc_gemm_launch_t<256, 3, 2>(c, args, ma, mb, splits, stream);
+  else if (bn == 256)         e = tc_gemm_launch_t<256, 4, 1>(c, args, ma, mb, splits, stream);
+  else                        e = tc_gemm_launch_t<128, 6, 1>(c, args, ma, mb, splits, stream);
   if (e != cudaSuccess) return e;
   if (splits > 1) {
     dim3 rb(256), rg((c.N + 255) / 256, c.M);

@@ -84,7 +84,7 @@ def main():
     test.sort_indices()
     eng.set_test(test, urm)
     users = np.flatnonzero(np.diff(test.indptr) > 0)[:a.eval_users].astype(np.int32)
-    eng.evaluate(users[:500], [10], remove_seen=True, want_counts=False)
+    eng.evaluate(users, [10], remove_seen=True, want_counts=False)      # warm-up sizes the device buffers
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     sums, _ = eng.evaluate(users, [10], remove_seen=True, want_counts=False)
