@@ -436,17 +436,20 @@ simt_gemm_kernel(const float* __restrict__ A, long long sam, long long sak, cons
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
-      const float v = apply_epilogue(ep, acc[i][j], m, n, rs);
-      ep.out[(size_t)m * ep.ldo + n] = v;
-      if (m < ep.row_split) sq0 += v * v; else sq1 += v * v;
+      const float v2 = finish_element(ep, apply_epilogue(ep, acc[i][j], m, n, rs), m, n);
+      if (ep.adam_m || m < ep.row_split) sq0 += v2; else sq1 += v2;
     }
   }
-  if (ep.sumsq2) {
+  if (ep.sumsq2 || (ep.adam_m && ep.adam_l2)) {
     sq0 = warp_sum(sq0);
     sq1 = warp_sum(sq1);
     if ((threadIdx.x & 31) == 0) {
-      if (sq0 != 0.f) atomicAdd(ep.sumsq2, (double)sq0);
-      if (sq1 != 0.f) atomicAdd(ep.sumsq2 + 1, (double)sq1);
+      if (ep.adam_m) {
+        if (sq0 != 0.f) atomicAdd(ep.adam_l2, (double)sq0);
+      } else {
+        if (sq0 != 0.f) atomicAdd(ep.sumsq2, (double)sq0);
+        if (sq1 != 0.f) atomicAdd(ep.sumsq2 + 1, (double)sq1);
+      }
     }
   }
 }

@@ -65,7 +65,24 @@ struct Epilogue {
   const float* r1_row = nullptr;
   const float* r1_col = nullptr;
   int act = ACT_LINEAR;
+  // Fused optimiser (single-GPU weight-gradient GEMMs): when adam_m != nullptr the epilogue value is the
+  // data gradient g of the parameter matrix `out` and, instead of being stored, drives TF's ApplyAdam in
+  // place:  g' = g + reg*theta; m += (g'-m)(1-b1); v += (g'^2-v)(1-b2); theta -= alpha*m/(sqrt(v)+eps);
+  // adam_l2 accumulates sum(theta_old^2) (l2 term of the reported loss).  m, v share out's layout.
+  float* adam_m = nullptr;
+  float* adam_v = nullptr;
+  float adam_alpha = 0.f;
+  float adam_reg = 0.f;
+  double* adam_l2 = nullptr;
 };
+
+constexpr float TC_ADAM_B1 = 0.9f, TC_ADAM_B2 = 0.999f, TC_ADAM_EPS = 1e-8f;
+__device__ __forceinline__ void adam_elem(float g, float& th, float& m, float& v, float alpha, float reg) {
+  const float ge = g + reg * th;
+  m = m + (ge - m) * (1.f - TC_ADAM_B1);
+  v = v + (ge * ge - v) * (1.f - TC_ADAM_B2);
+  th = th - (m * alpha) / (sqrtf(v) + TC_ADAM_EPS);
+}
 
 struct TcGemmArgs {
   int M, N, K;
@@ -93,6 +110,21 @@ __device__ __forceinline__ float apply_epilogue(const Epilogue& ep, float acc, i
   if (ep.act != ACT_LINEAR) v = act_fwd(ep.act, v);
   if (ep.round_out) v = ptx::round_tf32(v);
   return v;
+}
+
+// Generic (scalar) tail of the epilogue: store the value, or run the fused Adam update with it.
+// Returns the quantity that feeds the sum-of-squares accumulators (value^2, or theta_old^2 in Adam mode).
+__device__ __forceinline__ float finish_element(const Epilogue& ep, float x, int m, int n) {
+  const size_t o = (size_t)m * ep.ldo + n;
+  if (!ep.adam_m) {
+    ep.out[o] = x;
+    return x * x;
+  }
+  float th = ep.out[o], mm = ep.adam_m[o], vv = ep.adam_v[o];
+  const float th0 = th;
+  adam_elem(x, th, mm, vv, ep.adam_alpha, ep.adam_reg);
+  ep.out[o] = th; ep.adam_m[o] = mm; ep.adam_v[o] = vv;
+  return th0 * th0;
 }
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo,
@@ -281,7 +313,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // term only occur in small / split-K GEMMs, which finish in the generic path or the reduce kernel)
     const bool vec_all = partial ? true
                                  : (al16(ep.out, ep.ldo) && (!ep.c1 || al16(ep.c1, ep.ldc1)) && !ep.c2 &&
-                                    (!ep.bias || al16(ep.bias, 4)) && !ep.r1_row);
+                                    (!ep.bias || al16(ep.bias, 4)) && !ep.r1_row &&
+                                    (!ep.adam_m || (al16(ep.adam_m, 4) && al16(ep.adam_v, 4))));
     const bool use_c1 = !partial && ep.c1 != nullptr;
     float sq0 = 0.f, sq1 = 0.f;
     uint32_t ui = 0;
@@ -334,6 +367,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ep.bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
             float* dst = ep.out + (size_t)(mw + sub_r) * ep.ldo + n;
+            if (ep.adam_m) {
+              // fused Adam on the parameter tile: theta, m, v are read and written in place (24 B/param
+              // instead of 28 + the gradient round trip of a separate optimiser kernel)
+              const size_t off0 = (size_t)(mw + sub_r) * ep.ldo + n;
+              float l2 = 0.f;
+#pragma unroll
+              for (int hb = 0; hb < 2; ++hb) {
+                float4 th[4], mm[4], vv[4];
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  const size_t o = off0 + (size_t)(hb * 4 + i4) * 4 * ep.ldo;
+                  th[i4] = *reinterpret_cast<const float4*>(ep.out + o);
+                  mm[i4] = *reinterpret_cast<const float4*>(ep.adam_m + o);
+                  vv[i4] = *reinterpret_cast<const float4*>(ep.adam_v + o);
+                }
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  const int itr = hb * 4 + i4;
+                  const int row = itr * 4 + sub_r;
+                  const float4 a = slab[row * 8 + (sub_g ^ (row & 7))];
+                  const float sc = ep.alpha * ((mw + row) >= ep.row_split ? rs1 : rs0);
+                  l2 += th[i4].x * th[i4].x + th[i4].y * th[i4].y + th[i4].z * th[i4].z + th[i4].w * th[i4].w;
+                  adam_elem(sc * a.x, th[i4].x, mm[i4].x, vv[i4].x, ep.adam_alpha, ep.adam_reg);
+                  adam_elem(sc * a.y, th[i4].y, mm[i4].y, vv[i4].y, ep.adam_alpha, ep.adam_reg);
+                  adam_elem(sc * a.z, th[i4].z, mm[i4].z, vv[i4].z, ep.adam_alpha, ep.adam_reg);
+                  adam_elem(sc * a.w, th[i4].w, mm[i4].w, vv[i4].w, ep.adam_alpha, ep.adam_reg);
+                  const size_t o = off0 + (size_t)itr * 4 * ep.ldo;
+                  *reinterpret_cast<float4*>(ep.out + o) = th[i4];
+                  *reinterpret_cast<float4*>(ep.adam_m + o) = mm[i4];
+                  *reinterpret_cast<float4*>(ep.adam_v + o) = vv[i4];
+                }
+              }
+              sq0 += l2;
+              __syncwarp();
+              continue;
+            }
             // the addend loads of the chunk are all issued before any store (the stores may alias them as
             // far as the compiler knows), so their latency is paid once per chunk, not once per row group
             float4 t1[8];
@@ -383,27 +452,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             const float rs = m >= ep.row_split ? rs1 : rs0;
             float sq = 0.f;
-            for (int e = 0; e < 4 && n + e < args.N; ++e) {
-              const float x = apply_epilogue(ep, v[e], m, n + e, rs);
-              ep.out[(size_t)m * ep.ldo + n + e] = x;
-              sq += x * x;
-            }
-            if (m >= ep.row_split) sq1 += sq; else sq0 += sq;
+            for (int e = 0; e < 4 && n + e < args.N; ++e)
+              sq += finish_element(ep, apply_epilogue(ep, v[e], m, n + e, rs), m, n + e);
+            if (ep.adam_m || m < ep.row_split) sq0 += sq; else sq1 += sq;
           }
         }
         __syncwarp();                               // slab is reused by the next chunk
       }
       }
     }
-    if (!partial && ep.sumsq2) {
+    if (!partial && (ep.sumsq2 || ep.adam_l2)) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         sq0 += __shfl_xor_sync(0xffffffffu, sq0, o);
         sq1 += __shfl_xor_sync(0xffffffffu, sq1, o);
       }
       if (lane == 0) {
-        if (sq0 != 0.f) atomicAdd(ep.sumsq2, (double)sq0);
-        if (sq1 != 0.f) atomicAdd(ep.sumsq2 + 1, (double)sq1);
+        if (ep.adam_m) {
+          if (ep.adam_l2 && sq0 != 0.f) atomicAdd(ep.adam_l2, (double)sq0);
+        } else {
+          if (sq0 != 0.f) atomicAdd(ep.sumsq2, (double)sq0);
+          if (sq1 != 0.f) atomicAdd(ep.sumsq2 + 1, (double)sq1);
+        }
       }
     }
   }
@@ -427,15 +497,16 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += ws[((size_t)s * M + m) * ws_ld + n];
     float rs = ep.row_scale2 ? __ldg(ep.row_scale2 + (m >= ep.row_split ? 1 : 0)) : 1.f;
-    v = apply_epilogue(ep, acc, m, n, rs);
-    ep.out[(size_t)m * ep.ldo + n] = v;
+    v = finish_element(ep, apply_epilogue(ep, acc, m, n, rs), m, n);     // v = value^2 or theta_old^2
   }
-  if (ep.sumsq2) {
-    float sq = ok ? v * v : 0.f;
+  if (ep.sumsq2 || (ep.adam_m && ep.adam_l2)) {
+    float sq = ok ? v : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if ((threadIdx.x & 31) == 0 && sq != 0.f)
-      atomicAdd(ep.sumsq2 + (m >= ep.row_split ? 1 : 0), (double)sq);
+    if ((threadIdx.x & 31) == 0 && sq != 0.f) {
+      if (ep.adam_m) atomicAdd(ep.adam_l2, (double)sq);
+      else atomicAdd(ep.sumsq2 + (m >= ep.row_split ? 1 : 0), (double)sq);
+    }
   }
 }
 
