@@ -33,9 +33,10 @@ def main():
     from ganmf_b200.Base.Evaluation.Evaluator import EvaluatorHoldout
     from ganmf_b200.GANRec.DisGANMF import DisGANMF
     from ganmf_b200.GANRec.GANMF import GANMF
-    np.random.seed(1337)                                      # RunBestParameters.py:81
+    seed = int(sys.argv[sys.argv.index("--seed") + 1]) if "--seed" in sys.argv else 1337
+    np.random.seed(seed)                                      # RunBestParameters.py:81 (1337)
     cls = GANMF if algo == "GANMF" else DisGANMF
-    model = cls(split["train"], mode=mode, seed=1337, is_experiment=True)
+    model = cls(split["train"], mode=mode, seed=seed, is_experiment=True)
     t0 = time.time()
     model.fit(validation_set=None, sample_every=None, validation_evaluator=None, **bp)
     t_train = time.time() - t0
