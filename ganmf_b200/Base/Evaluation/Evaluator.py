@@ -78,6 +78,7 @@ class EvaluatorHoldout(Evaluator):
         super(EvaluatorHoldout, self).__init__(URM_test_list, cutoff_list, diversity_object=diversity_object,
                                                minRatingsPerUser=minRatingsPerUser, exclude_seen=exclude_seen,
                                                ignore_items=ignore_items, ignore_users=ignore_users)
+        self._scores_engine = None      # lazily created device context for recommenders without their own
 
     # ------------------------------------------------------------------------------------------
     def _device_sums(self, recommender_object, users):
@@ -87,8 +88,18 @@ class EvaluatorHoldout(Evaluator):
         eng = getattr(recommender_object, "_engine", None)
         URM_train = recommender_object.get_URM_train()
         if eng is None:
-            raise NotImplementedError("evaluating a recommender without a ganmf_b200 device engine is a 'next' row "
-                                      "(SURVEY.md section 8f); there is no CPU evaluation path")
+            # any recommender exposing _compute_item_score (e.g. the reference's own baselines): its host score
+            # rows are pushed, block by block as Evaluator.py:238 sizes them, through the device
+            # mask -> top-k -> metric stage.  There is no CPU evaluation path.
+            if self._scores_engine is None:
+                from ...engine import Engine
+                self._scores_engine = Engine(L.KIND_GANMF, self.n_users, self.n_items, 1, emb_dim=1, max_batch=1)
+            eng = self._scores_engine
+            eng.set_csr(L.CSR_SEEN, URM_train, with_data=False)
+            eng.set_test(self.URM_test, URM_train)
+            block = min(1000, max(1, int(1e8 / self.n_items)))
+            return eng.evaluate_scores(lambda u: recommender_object._compute_item_score(u), users, self.cutoff_list,
+                                       remove_seen=self.exclude_seen, block_size=block)
         eng.set_test(self.URM_test, URM_train)
         return eng.evaluate(users, self.cutoff_list, remove_seen=self.exclude_seen)
 

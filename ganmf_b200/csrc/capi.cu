@@ -100,6 +100,7 @@ struct ganmf_ctx {
   int* cut_dev = nullptr;
   int* eval_users = nullptr; int eval_users_cap = 0;
   long long launches = 0;
+  int ev_total = 0, ev_done = 0, ev_ncut = 0, ev_K = 0;     // streaming evaluation (ganmf_eval_begin..end)
   int last_ids_offset = 0;
   bool fuse_adam = true;      // ganmf_d_step / ganmf_g_step: optimiser inside the weight-gradient GEMMs
   // live GEMM timing (bench roofline)
@@ -1307,6 +1308,90 @@ int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_
     CU(cudaMemcpy(tmp.data(), c->icounts, tmp.size() * 4, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < tmp.size(); ++i) counts_host[i] = tmp[i];
   }
+  return 0;
+}
+
+int ganmf_eval_begin(ganmf_ctx* c, int n_users_total, const int32_t* cutoffs, int n_cut) {
+  if (!c || !cutoffs || n_users_total < 0) return fail("bad argument");
+  int K;
+  RC(eval_prologue(c, cutoffs, n_cut, &K));
+  const int n_items = c->csr[GANMF_CSR_TEST].n_cols;
+  if (!c->csr[GANMF_CSR_TEST].data) return fail("test CSR needs ratings (data) for RMSE");
+  if (c->eval_users_cap < n_users_total) {
+    cudaFree(c->eval_users);
+    RC(dalloc(&c->eval_users, (size_t)std::max(n_users_total, 1)));
+    c->eval_users_cap = std::max(n_users_total, 1);
+  }
+  const size_t uv = (size_t)std::max(n_users_total, 1) * n_cut * MC_NCOL;
+  if (uv > c->uvals_cap) {
+    cudaFree(c->uvals);
+    RC(dalloc(&c->uvals, uv));
+    c->uvals_cap = uv;
+  }
+  const size_t ic = (size_t)n_cut * n_items;
+  if (ic > c->icounts_cap) {
+    cudaFree(c->icounts); cudaFree(c->usums); cudaFree(c->cut_dev);
+    RC(dalloc(&c->icounts, ic));
+    RC(dalloc(&c->usums, (size_t)64 * MC_NCOL));
+    RC(dalloc(&c->cut_dev, (size_t)64));
+    c->icounts_cap = ic;
+  }
+  CU(cudaMemcpyAsync(c->cut_dev, cutoffs, (size_t)n_cut * 4, cudaMemcpyHostToDevice, c->st));
+  CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
+  CU(cudaMemsetAsync(c->icounts, 0, ic * 4, c->st));
+  c->ev_total = n_users_total; c->ev_done = 0; c->ev_ncut = n_cut; c->ev_K = K;
+  return 0;
+}
+
+int ganmf_eval_scores_block(ganmf_ctx* c, float* scores_host, const int32_t* users, int n, int remove_seen,
+                            int write_back) {
+  if (!c || !scores_host || !users || n <= 0) return fail("bad argument");
+  if (c->ev_ncut == 0) return fail("ganmf_eval_begin first");
+  if (c->ev_done + n > c->ev_total) return fail("more users than announced to ganmf_eval_begin");
+  const int n_items = c->csr[GANMF_CSR_TEST].n_cols, ild = rup(n_items, 32);
+  const int nu = c->csr[GANMF_CSR_TEST].n_rows;
+  for (int i = 0; i < n; ++i)
+    if (users[i] < 0 || users[i] >= nu) return fail("user id %d outside [0, %d)", users[i], nu);
+  const size_t need = (size_t)n * ild;
+  if (need > c->scores_elems) {
+    cudaFree(c->scores);
+    RC(dalloc(&c->scores, need));
+    c->scores_elems = need;
+  }
+  if ((size_t)n * c->ev_K > c->topk_cap) {
+    cudaFree(c->topk_idx); cudaFree(c->topk_val);
+    RC(dalloc(&c->topk_idx, (size_t)n * c->ev_K));
+    RC(dalloc(&c->topk_val, (size_t)n * c->ev_K));
+    c->topk_cap = (size_t)n * c->ev_K;
+  }
+  int* ud = c->eval_users + c->ev_done;
+  CU(cudaMemcpyAsync(ud, users, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+  CU(cudaMemcpy2DAsync(c->scores, (size_t)ild * 4, scores_host, (size_t)n_items * 4, (size_t)n_items * 4, n,
+                       cudaMemcpyHostToDevice, c->st));
+  RC(mask_and_topk(c, n, n_items, remove_seen, c->ev_K, ud));
+  RC(metrics_block(c, n, c->ev_K, c->ev_ncut, n_items, true, ud,
+                   c->uvals + (size_t)c->ev_done * c->ev_ncut * MC_NCOL));
+  if (write_back)
+    CU(cudaMemcpy2DAsync(scores_host, (size_t)n_items * 4, c->scores, (size_t)ild * 4, (size_t)n_items * 4, n,
+                         cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));          // the caller reuses / frees its score block next
+  c->ev_done += n;
+  return 0;
+}
+
+int ganmf_eval_end(ganmf_ctx* c, double* sums_host, int64_t* counts_host) {
+  if (!c || !sums_host) return fail("bad argument");
+  if (c->ev_ncut == 0) return fail("ganmf_eval_begin first");
+  const int n_items = c->csr[GANMF_CSR_TEST].n_cols;
+  if (c->ev_done > 0) RC(accumulate_users(c, c->ev_done, c->ev_ncut));
+  CU(cudaMemcpyAsync(sums_host, c->usums, (size_t)c->ev_ncut * MC_NCOL * 8, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (counts_host) {
+    std::vector<int> tmp((size_t)c->ev_ncut * n_items);
+    CU(cudaMemcpy(tmp.data(), c->icounts, tmp.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < tmp.size(); ++i) counts_host[i] = tmp[i];
+  }
+  c->ev_ncut = 0;
   return 0;
 }
 

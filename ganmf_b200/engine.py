@@ -269,6 +269,24 @@ class Engine(object):
                                         counts.ctypes.data_as(L._i64p) if counts is not None else None))
         return sums, counts
 
+    def evaluate_scores(self, score_fn, users, cutoffs, remove_seen=True, block_size=1000):
+        """Streaming evaluation of an arbitrary scorer: score_fn(user_ids) -> float32 [n, n_items] on the host;
+        mask, top-k and metric arithmetic run on the device."""
+        ua = np.ascontiguousarray(users, dtype=np.int32)
+        ca, cp = L.i32(cutoffs)
+        L.check(self.lib.ganmf_eval_begin(self.ctx, ua.size, cp, ca.size))
+        for s in range(0, ua.size, block_size):
+            blk = ua[s:s + block_size]
+            sc = np.ascontiguousarray(score_fn(blk), dtype=np.float32)
+            if sc.shape != (blk.size, self.n_items):
+                raise ValueError("scores have shape %r, expected %r" % (sc.shape, (blk.size, self.n_items)))
+            L.check(self.lib.ganmf_eval_scores_block(self.ctx, sc.ctypes.data_as(L._f32p),
+                                                     blk.ctypes.data_as(L._i32p), blk.size, int(remove_seen), 0))
+        sums = np.zeros((ca.size, L.MC_NCOL), dtype=np.float64)
+        counts = np.zeros((ca.size, self.n_items), dtype=np.int64)
+        L.check(self.lib.ganmf_eval_end(self.ctx, sums.ctypes.data_as(L._f64p), counts.ctypes.data_as(L._i64p)))
+        return sums, counts
+
     def metrics_from_topk(self, topk_idx, users, cutoffs, want_per_user=False):
         t = np.ascontiguousarray(topk_idx, dtype=np.int32)
         ua, up = L.i32(users)

@@ -152,6 +152,14 @@ int ganmf_set_eval_tables(ganmf_ctx* ctx, const float* test_gain_host, const flo
 int ganmf_evaluate(ganmf_ctx* ctx, const int32_t* user_ids_host, int n_users, const int32_t* cutoffs_host,
                    int n_cutoffs, int remove_seen, int block_size, double* sums_host,
                    int64_t* item_counts_host);
+/* The same evaluation for ANY recommender that can produce host score rows (the reference's
+ * recommender.recommend(...) call inside Evaluator.py:271-277): begin, then feed blocks of users IN ORDER
+ * with their fp32 score rows [n][n_items] (masked in place with -inf on seen items when remove_seen),
+ * then end.  Sums / counts as in ganmf_evaluate. */
+int ganmf_eval_begin(ganmf_ctx* ctx, int n_users_total, const int32_t* cutoffs_host, int n_cutoffs);
+int ganmf_eval_scores_block(ganmf_ctx* ctx, float* scores_host, const int32_t* user_ids_host, int n,
+                            int remove_seen, int write_back);
+int ganmf_eval_end(ganmf_ctx* ctx, double* sums_host, int64_t* item_counts_host);
 /* Same metric stage on caller-supplied top-K lists (bit-exact contract tests). */
 int ganmf_metrics_from_topk(ganmf_ctx* ctx, const int32_t* topk_idx_host, int K,
                             const int32_t* user_ids_host, int n_users, const int32_t* cutoffs_host,

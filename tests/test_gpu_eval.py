@@ -127,3 +127,38 @@ def test_large_scale_properties():
     idx2, _, _ = e.recommend(users, 50, remove_seen=True)                   # idempotent
     assert np.array_equal(idx, idx2)
     e.close()
+
+
+@pytest.mark.parametrize("name", ["eval_small_implicit", "eval_small_ratings", "eval_small_shortlists"])
+def test_evaluator_with_foreign_recommender_matches_reference_run(name):
+    """EvaluatorHoldout on a recommender that only exposes _compute_item_score / get_URM_train (as the
+    reference's baselines do): all 19 metrics equal the unmodified reference evaluator's output (golden),
+    up to the float32-vs-float64 running sums of numpy >= 2 (see oracle/eval_oracle.py), and are bit-exact
+    against the oracle in the reference's pinned-numpy arithmetic."""
+    from ganmf_b200.Base.Evaluation.Evaluator import EvaluatorHoldout
+    fx = load_eval_fixture(name)
+
+    class Fixed(object):
+        RECOMMENDER_NAME = "Fixed"
+
+        def get_URM_train(self):
+            return fx["train"].copy()
+
+        def _compute_item_score(self, user_id_array, items_to_compute=None):
+            return fx["scores"][user_id_array].copy()
+
+    ev = EvaluatorHoldout(fx["test"], cutoff_list=fx["cutoffs"], exclude_seen=True)
+    res, txt = ev.evaluateRecommender(Fixed())
+    ores, n_eval = eo.evaluate(lambda u: fx["scores"][u], fx["train"], fx["test"], fx["cutoffs"], promotion="legacy")
+    for ci, c in enumerate(fx["cutoffs"]):
+        for mi, m in enumerate(fx["metric_names"]):
+            want = fx["results"][ci, mi]
+            got = float(res[c][m])
+            if np.isnan(want):
+                assert np.isnan(got)
+                continue
+            assert got == pytest.approx(want, rel=2e-6, abs=1e-9), (c, m)
+            if m in ("ARHR", "RMSE"):          # BLAS ddot / float32 pairwise sum orders: equal to ~1 ulp
+                assert got == pytest.approx(float(ores[c][m]), rel=1e-12)
+            else:
+                assert got == float(ores[c][m]), (c, m, got, float(ores[c][m]))

@@ -140,3 +140,44 @@ def test_disganmf_steps_parity(act, layers, nodes):
     for n in orc.p:
         assert rel_err(got[n], orc.p[n]) <= REL, (n, rel_err(got[n], orc.p[n]))
     eng.close()
+
+
+def test_phased_and_ranged_updates_equal_the_fused_step():
+    """The data-parallel building blocks (phased backward, Adam on slab ranges) on one GPU reproduce the
+    single-call step: same losses, same weights (they are different kernels/fusions of the same math)."""
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    n_rows, width, k, E, B = 256, 390, 16, 40, 64
+    urm = make_urm(n_rows, width, 0.05, 11)
+    p0 = to.init_ganmf_params(n_rows, width, k, E, seed=2)
+    hp = dict(d_lr=1e-3, g_lr=1e-3, d_reg=1e-4, g_reg=1e-4, m=10.0, alpha=0.2)
+    ids = np.random.RandomState(0).permutation(n_rows)[:3 * B].astype(np.int32)
+    outs = []
+    for variant in ("fused", "phased", "ranges"):
+        eng = Engine(L.KIND_GANMF, n_rows, width, k, emb_dim=E, max_batch=B)
+        eng.set_csr(L.CSR_TRAIN, urm)
+        eng.set_params(p0)
+        eng.reset_optimizers()
+        eng.upload_ids(ids)
+        n_d = sum(r * ((c + 31) // 32 * 32) for _, r, c, g in eng.param_infos() if not g)
+        for s in range(3):
+            off = s * B
+            if variant == "fused":
+                eng.d_step(off, B, hp["d_lr"], hp["d_reg"], hp["m"], loss_slot=2 * s)
+            else:
+                eng.d_forward(off, B)
+                eng.d_backward_phase(B, B, hp["m"], 1)
+                eng.d_backward_phase(B, B, hp["m"], 2)
+                if variant == "phased":
+                    eng.d_apply(hp["d_lr"], hp["d_reg"], 2 * s)
+                else:
+                    half = (n_d // 2) // 4 * 4
+                    eng.d_apply_ranges(hp["d_lr"], hp["d_reg"], [0, half], [half, n_d - half])
+                    eng.finalize_loss(hp["d_reg"], 2 * s)
+            eng.g_step(off, B, hp["g_lr"], hp["g_reg"], hp["alpha"], loss_slot=2 * s + 1)
+        outs.append((eng.read_losses(6), eng.get_params()))
+        eng.close()
+    for losses, params in outs[1:]:
+        np.testing.assert_allclose(losses, outs[0][0], rtol=2e-5)
+        for n in params:
+            assert rel_err(params[n], outs[0][1][n]) < 2e-5, n
