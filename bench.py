@@ -126,6 +126,17 @@ def gemm_algorithmic_bytes(c):
     return d + gs
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms must use all host cores."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
 def flops_per_row(c):
     return c["items"] * (8 * c["k"] + 30 * c["E"])          # SURVEY.md section 8(d)
 
@@ -138,6 +149,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     from oracle import train_oracle as to
+    cores = use_all_host_threads()
     c = CFG4
     B = 256                                                   # bounded sample: 256-row minibatches
     n_users = 4096                                            # user-factor rows kept small: P is not the cost driver
@@ -158,7 +170,6 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     v = B * args.steps / dt
-    cores = os.cpu_count()
     sample = "NumPy restatement of the TF graph, %d steps of B=%d rows at 27000 items, k=250, E=1024 " \
              "(user-factor table cut to %d rows)" % (args.steps, B, n_users)
     line = {"impl": "reference", "metric": "GANMF-u train user-rows/s", "value": v, "unit": "rows/s", "n_gpus": 0,
@@ -413,6 +424,7 @@ def hbm_kernel_rooflines(eng, torch, L, c, pk):
 def cpu_baseline(c):
     """Oracle port of the reference graph on the host cores, bounded sample (about 10-30 s)."""
     from oracle import train_oracle as to
+    cores = use_all_host_threads()
     B, n_users = 256, 4096
     urm = synthetic_urm(n_users, c["items"], c["density"], 1337)
     orc = to.GanmfOracle(to.init_ganmf_params(n_users, c["items"], c["k"], c["E"], seed=1234), HP["d_lr"], HP["g_lr"],
@@ -431,7 +443,7 @@ def cpu_baseline(c):
         step()
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": B * n / dt, "unit": "rows/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": B * n / dt, "unit": "rows/s", "cores": cores, "kind": "port",
             "sample": "%d D+G steps of B=%d rows, 27000 items, k=250, E=1024 (NumPy/BLAS, all host threads; "
                       "user-factor table cut to %d rows)" % (n, B, n_users)}
 
