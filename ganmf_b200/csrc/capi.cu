@@ -102,6 +102,7 @@ struct ganmf_ctx {
   long long launches = 0;
   int ev_total = 0, ev_done = 0, ev_ncut = 0, ev_K = 0;     // streaming evaluation (ganmf_eval_begin..end)
   int last_ids_offset = 0;
+  float last_alpha_d = 0.f;
   bool fuse_adam = true;      // ganmf_d_step / ganmf_g_step: optimiser inside the weight-gradient GEMMs
   // live GEMM timing (bench roofline)
   bool profile = false;
@@ -562,8 +563,12 @@ static int adam_group(ganmf_ctx* c, int first, int count, float alpha, float reg
 }
 
 // ---- GANMF ---------------------------------------------------------------------------------
-static int ganmf_d_forward_impl(ganmf_ctx* c, int ids_offset, int B) {
-  RC(forward_generator(c, ids_offset, B));
+// phase 1: profiles + generator (independent of the discriminator weights); phase 2: discriminator
+// forward on [R ; F]; phase 0: both.  A data-parallel caller runs phase 1 of the NEXT step while the
+// all-gather of the freshly updated discriminator weights is still in flight.
+static int ganmf_d_forward_impl(ganmf_ctx* c, int ids_offset, int B, int phase = 0) {
+  if (phase != 2) RC(forward_generator(c, ids_offset, B));
+  if (phase == 1) return 0;
   Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
   CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
   Epilogue e2;                                                                     // G2
@@ -582,7 +587,7 @@ static int ganmf_d_forward_impl(ganmf_ctx* c, int ids_offset, int B) {
 static int ganmf_d_backward_impl(ganmf_ctx* c, int B, int n_global, float m_hinge, int phase) {
   Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
   const float* rs = c->sc->row_scale;
-  if (phase == 2) goto second_half;
+  if (phase >= 2) goto second_half;
   {
   const double n_elems = (double)n_global * c->W;
   hinge_gate_kernel<<<1, 1, 0, c->st>>>(c->sc, m_hinge, n_elems);
@@ -604,13 +609,16 @@ static int ganmf_d_backward_impl(ganmf_ctx* c, int B, int n_global, float m_hing
   }
   if (phase == 1) return 0;
 second_half:
-  Epilogue e5;                                                                     // G5: dH2
-  e5.out = c->dH2.p; e5.ldo = c->dH2.ld; e5.row_scale2 = rs; e5.row_split = B;
-  RC(gemm(c, c->Res2.p, c->Res2.ld, 0, Wd->w.p, Wd->w.ld, 0, 2 * B, c->E, c->W, e5));
-  Epilogue e6;                                                                     // G6: dWe
-  e6.out = We->g; e6.ldo = We->w.ld;
-  RC(gemm(c, c->X2.p, c->X2.ld, 1, c->dH2.p, c->dH2.ld, 1, c->W, c->E, 2 * B, e6));
-  c->launches += 1;
+  if (phase != 4) {
+    Epilogue e5;                                                                   // G5: dH2 (reads Wd)
+    e5.out = c->dH2.p; e5.ldo = c->dH2.ld; e5.row_scale2 = rs; e5.row_split = B;
+    RC(gemm(c, c->Res2.p, c->Res2.ld, 0, Wd->w.p, Wd->w.ld, 0, 2 * B, c->E, c->W, e5));
+  }
+  if (phase != 3) {
+    Epilogue e6;                                                                   // G6: dWe
+    e6.out = We->g; e6.ldo = We->w.ld;
+    RC(gemm(c, c->X2.p, c->X2.ld, 1, c->dH2.p, c->dH2.ld, 1, c->W, c->E, 2 * B, e6));
+  }
   return 0;
 }
 
@@ -871,6 +879,12 @@ int ganmf_d_forward(ganmf_ctx* c, int ids_offset, int B) {
   return c->cfg.kind == GANMF_KIND_GANMF ? ganmf_d_forward_impl(c, ids_offset, B)
                                          : dis_d_forward_impl(c, ids_offset, B);
 }
+int ganmf_d_forward_phase(ganmf_ctx* c, int ids_offset, int B, int phase) {
+  RC(check_batch(c, ids_offset, B));
+  if (c->cfg.kind != GANMF_KIND_GANMF) return fail("phased forward: GANMF only");
+  if (phase < 0 || phase > 2) return fail("phase must be 0, 1 or 2");
+  return ganmf_d_forward_impl(c, ids_offset, B, phase);
+}
 int ganmf_d_backward(ganmf_ctx* c, int B, int n_global, float m_hinge) {
   if (!c) return fail("null ctx");
   return c->cfg.kind == GANMF_KIND_GANMF ? ganmf_d_backward_impl(c, B, n_global, m_hinge, 0)
@@ -879,7 +893,7 @@ int ganmf_d_backward(ganmf_ctx* c, int B, int n_global, float m_hinge) {
 int ganmf_d_backward_phase(ganmf_ctx* c, int B, int n_global, float m_hinge, int phase) {
   if (!c) return fail("null ctx");
   if (c->cfg.kind != GANMF_KIND_GANMF) return fail("phased backward: GANMF only");
-  if (phase < 0 || phase > 2) return fail("phase must be 0, 1 or 2");
+  if (phase < 0 || phase > 4) return fail("phase must be 0..4");
   return ganmf_d_backward_impl(c, B, n_global, m_hinge, phase);
 }
 int ganmf_d_apply(ganmf_ctx* c, float lr, float reg, int loss_slot) {
@@ -917,7 +931,7 @@ int ganmf_g_step(ganmf_ctx* c, int ids_offset, int B, int n_global, float lr, fl
 // reduce-scatter, then the updated parameters are all-gathered.  sum(theta^2) of the ranges goes to
 // l2_shard (summed over ranks by the caller before ganmf_finalize_loss).
 int ganmf_d_apply_ranges(ganmf_ctx* c, float lr, float reg, const int64_t* offsets, const int64_t* counts,
-                         int n_ranges) {
+                         int n_ranges, int new_step) {
   if (!c || !offsets || !counts || n_ranges < 1 || n_ranges > ADAM_MAX_SEG) return fail("bad argument");
   AdamArgs a;
   memset(&a, 0, sizeof a);
@@ -934,7 +948,8 @@ int ganmf_d_apply_ranges(ganmf_ctx* c, float lr, float reg, const int64_t* offse
     s.slot = nullptr; s.ld = 4;
     s.n4 = (unsigned long long)counts[i] / 4;
   }
-  a.alpha = adam_alpha(c, 0, lr);
+  if (new_step) c->last_alpha_d = adam_alpha(c, 0, lr);     // one optimiser step may span several calls
+  a.alpha = c->last_alpha_d;
   a.reg = reg;
   a.l2_out = &c->sc->l2_shard;
   a.l2_shard_out = &c->sc->l2_shard;

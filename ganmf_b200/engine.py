@@ -166,11 +166,14 @@ class Engine(object):
     def g_apply(self, B, n_rows_global, lr, reg, recon_coefficient, loss_slot):
         L.check(self.lib.ganmf_g_apply(self.ctx, B, n_rows_global, lr, reg, recon_coefficient, loss_slot))
 
-    def d_apply_ranges(self, lr, reg, offsets, counts):
+    def d_apply_ranges(self, lr, reg, offsets, counts, new_step=True):
         o = np.ascontiguousarray(offsets, dtype=np.int64)
         n = np.ascontiguousarray(counts, dtype=np.int64)
         L.check(self.lib.ganmf_d_apply_ranges(self.ctx, lr, reg, o.ctypes.data_as(L._i64p), n.ctypes.data_as(L._i64p),
-                                              o.size))
+                                              o.size, int(new_step)))
+
+    def d_forward_phase(self, ids_offset, B, phase):
+        L.check(self.lib.ganmf_d_forward_phase(self.ctx, ids_offset, B, phase))
 
     def finalize_loss(self, reg, loss_slot):
         L.check(self.lib.ganmf_finalize_loss(self.ctx, reg, loss_slot))

@@ -23,6 +23,7 @@ class DataParallelTrainer(object):
         self.eng, self.world, self.group = engine, world_size, group
         self.overlap = False
         self.sharded_adam = False
+        self._pending = []
         if buffers is None:
             dev = torch.device("cuda", torch.cuda.current_device())
             names = ["d_grads", "g_shared_grad", "step_scalars"]
@@ -50,23 +51,42 @@ class DataParallelTrainer(object):
     def _sum(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
 
+    def _wait_pending(self):
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+
     def d_step(self, ids_offset, B, lr, reg, m_hinge, loss_slot):
         n_global = B * self.world
-        self.eng.d_forward(ids_offset, B)
+        if self._pending:
+            self.eng.d_forward_phase(ids_offset, B, 1)    # profiles + generator overlap the weight all-gather
+            self._wait_pending()
+            self.eng.d_forward_phase(ids_offset, B, 2)
+        else:
+            self.eng.d_forward(ids_offset, B)
         self._sum(self.scalars)
         if self.sharded_adam:
+            # Schedule (NCCL ops run on their own stream; -> = stream order, || = concurrent):
+            #   dWd,dbd -> RS(dec) || dH                      (RS of the decoder half hides behind dH)
+            #   Adam(dec chunk) -> AG(dec) || dWe             (decoder weights travel while dWe is computed)
+            #   RS(enc) -> Adam(enc chunk) -> AG(enc) || next step's profiles + generator
             d = self.dist
             self.eng.d_backward_phase(B, n_global, m_hinge, 1)
             w = d.reduce_scatter_tensor(self.d_dec[self._dec_chunk], self.d_dec, op=d.ReduceOp.SUM, group=self.group,
-                                        async_op=True)                   # overlaps the encoder half
-            self.eng.d_backward_phase(B, n_global, m_hinge, 2)
-            d.reduce_scatter_tensor(self.d_enc[self._enc_chunk], self.d_enc, op=d.ReduceOp.SUM, group=self.group)
+                                        async_op=True)
+            self.eng.d_backward_phase(B, n_global, m_hinge, 3)            # dH: last reader of the old Wd
             w.wait()
-            self.eng.d_apply_ranges(lr, reg, *self._ranges)
-            d.all_gather_into_tensor(self.p_dec, self.p_dec[self._dec_chunk], group=self.group)
-            d.all_gather_into_tensor(self.p_enc, self.p_enc[self._enc_chunk], group=self.group)
-            self._sum(self.scalars[6:7])
+            self.eng.d_apply_ranges(lr, reg, [self._ranges[0][1]], [self._ranges[1][1]], new_step=True)
+            ag_dec = d.all_gather_into_tensor(self.p_dec, self.p_dec[self._dec_chunk], group=self.group,
+                                              async_op=True)
+            self.eng.d_backward_phase(B, n_global, m_hinge, 4)            # dWe
+            d.reduce_scatter_tensor(self.d_enc[self._enc_chunk], self.d_enc, op=d.ReduceOp.SUM, group=self.group)
+            self.eng.d_apply_ranges(lr, reg, [self._ranges[0][0]], [self._ranges[1][0]], new_step=False)
+            self._sum(self.scalars[6:7])                                 # (before AG(enc): NCCL ops are serial)
             self.eng.finalize_loss(reg, loss_slot)
+            ag_enc = d.all_gather_into_tensor(self.p_enc, self.p_enc[self._enc_chunk], group=self.group,
+                                              async_op=True)
+            self._pending = [ag_dec, ag_enc]                             # awaited before the weights are read
             return
         if self.overlap:
             # decoder gradients are summed on NCCL's stream while the encoder half is still computed
@@ -82,6 +102,7 @@ class DataParallelTrainer(object):
 
     def g_step(self, ids_offset, B, lr, reg, recon_coefficient, loss_slot):
         n_global = B * self.world
+        self._wait_pending()
         self.eng.g_forward_backward(ids_offset, B, n_global, recon_coefficient)
         self._sum(self.g_shared)
         self._sum(self.scalars)
@@ -108,6 +129,7 @@ class DataParallelTrainer(object):
                 off = b * batch_size
                 self.g_step(off, min(batch_size, n - off), hp["g_lr"], hp["g_reg"], hp["alpha"], slot)
                 slot += 1
+        self._wait_pending()
         losses = self.eng.read_losses(slot)
         return losses[:nd], losses[nd:]
 

@@ -97,6 +97,10 @@ int ganmf_d_backward(ganmf_ctx* ctx, int B, int n_rows_global, float m_hinge);
 /* GANMF: the D backward in two halves so the sum of the decoder gradients ("d_grads_dec") can overlap the
  * computation of the encoder half ("d_grads_enc"): phase 1 = gate + dWd,dbd; phase 2 = dH + dWe,dbe; 0 = both */
 int ganmf_d_backward_phase(ganmf_ctx* ctx, int B, int n_rows_global, float m_hinge, int phase);
+/* ... phases 3 / 4 split phase 2 into dH (still reads the decoder weights) and dWe, so the decoder can be
+ * updated and all-gathered while dWe is computed.  Forward: phase 1 = profiles + generator (independent of
+ * the discriminator weights), phase 2 = discriminator forward, 0 = both. */
+int ganmf_d_forward_phase(ganmf_ctx* ctx, int ids_offset, int B, int phase);
 int ganmf_d_apply(ganmf_ctx* ctx, float lr, float reg, int loss_slot);
 int ganmf_g_forward_backward(ganmf_ctx* ctx, int ids_offset, int B, int n_rows_global,
                              float recon_coefficient);
@@ -106,7 +110,7 @@ int ganmf_g_apply(ganmf_ctx* ctx, int B, int n_rows_global, float lr, float reg,
  * Adam on [offsets[i], offsets[i]+counts[i]) (elements of the discriminator slab, multiples of 4) only;
  * the caller all-gathers "d_params" afterwards, sums step_scalars[6] and calls ganmf_finalize_loss. */
 int ganmf_d_apply_ranges(ganmf_ctx* ctx, float lr, float reg, const int64_t* offsets, const int64_t* counts,
-                         int n_ranges);
+                         int n_ranges, int new_step /* 1: first call of this optimiser step */);
 /* Data-parallel G step only (n_rows_global != B): after ganmf_g_apply, sum step_scalars[6] (the l2 of
  * the row-sharded user factors) over ranks, then write loss_slot. */
 int ganmf_finalize_loss(ganmf_ctx* ctx, float reg, int loss_slot);

@@ -165,14 +165,17 @@ def test_phased_and_ranged_updates_equal_the_fused_step():
             if variant == "fused":
                 eng.d_step(off, B, hp["d_lr"], hp["d_reg"], hp["m"], loss_slot=2 * s)
             else:
-                eng.d_forward(off, B)
+                eng.d_forward_phase(off, B, 1)
+                eng.d_forward_phase(off, B, 2)
                 eng.d_backward_phase(B, B, hp["m"], 1)
-                eng.d_backward_phase(B, B, hp["m"], 2)
+                eng.d_backward_phase(B, B, hp["m"], 3)
+                eng.d_backward_phase(B, B, hp["m"], 4)
                 if variant == "phased":
                     eng.d_apply(hp["d_lr"], hp["d_reg"], 2 * s)
                 else:
                     half = (n_d // 2) // 4 * 4
-                    eng.d_apply_ranges(hp["d_lr"], hp["d_reg"], [0, half], [half, n_d - half])
+                    eng.d_apply_ranges(hp["d_lr"], hp["d_reg"], [0], [half], new_step=True)
+                    eng.d_apply_ranges(hp["d_lr"], hp["d_reg"], [half], [n_d - half], new_step=False)
                     eng.finalize_loss(hp["d_reg"], 2 * s)
             eng.g_step(off, B, hp["g_lr"], hp["g_reg"], hp["alpha"], loss_slot=2 * s + 1)
         outs.append((eng.read_losses(6), eng.get_params()))

@@ -19,6 +19,10 @@ class FakeEngine(object):
     def __init__(self, rank, bufs):
         self.rank, self.b, self.log = rank, bufs, []
 
+    class _Cfg(object):
+        kind = 1
+    cfg = _Cfg()
+
     def d_forward(self, off, B):
         self.log.append("d_forward")
         self.b["step_scalars"][:] = torch.tensor([1.0 + self.rank, 10.0 * (1 + self.rank), 0, 0, 0, 0, 0],
