@@ -57,9 +57,11 @@ SIGNATURES = {
     "ganmf_d_backward_phase": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_float, C.c_int]),
     "ganmf_d_apply": (C.c_int, [_ctx, C.c_float, C.c_float, C.c_int]),
     "ganmf_g_forward_backward": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float]),
+    "ganmf_g_forward_backward_part": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]),
     "ganmf_g_apply": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]),
     "ganmf_d_apply_ranges": (C.c_int, [_ctx, C.c_float, C.c_float, _i64p, _i64p, C.c_int, C.c_int]),
     "ganmf_d_forward_phase": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int]),
+    "ganmf_set_gemm_sms": (C.c_int, [_ctx, C.c_int]),
     "ganmf_finalize_loss": (C.c_int, [_ctx, C.c_float, C.c_int]),
     "ganmf_train_epoch": (C.c_int, [_ctx, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                     C.c_float, C.c_float, C.c_float, C.c_float, _f32p, _f32p]),

@@ -103,7 +103,15 @@ struct ganmf_ctx {
   int ev_total = 0, ev_done = 0, ev_ncut = 0, ev_K = 0;     // streaming evaluation (ganmf_eval_begin..end)
   int last_ids_offset = 0;
   float last_alpha_d = 0.f;
+  int gemm_sm_cap = 0;        // > 0: persistent GEMM grids leave SMs free (ganmf_set_gemm_sms)
   bool fuse_adam = true;      // ganmf_d_step / ganmf_g_step: optimiser inside the weight-gradient GEMMs
+  // lazy user-factor optimiser (kernels.cuh K6b): p_last[row] = G step the row is current at, alpha_log[t -
+  // log_base] = step size of G step t+1, g_T = G steps taken, p_stale = some row may lag behind g_T
+  bool lazy_p = true;
+  bool p_stale = false;
+  int* p_last = nullptr;
+  float* alpha_log = nullptr;
+  int log_cap = 1 << 16, log_base = 0, g_T = 0;
   // live GEMM timing (bench roofline)
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -187,6 +195,7 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   g.splits = splits;
   g.ws = c->ws;
   g.cache = &c->tmaps;
+  g.max_ctas = c->gemm_sm_cap;
   c->launches += splits > 1 ? 2 : 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (c->profile) {
@@ -232,6 +241,8 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   ganmf_ctx* c = new ganmf_ctx();
   c->cfg = *cfg;
   if (const char* nf = getenv("GANMF_NO_FUSED_ADAM")) c->fuse_adam = !(nf[0] == '1');   // A/B switch
+  if (const char* nl = getenv("GANMF_NO_LAZY_ADAM")) c->lazy_p = !(nl[0] == '1');       // A/B switch
+  if (const char* lc = getenv("GANMF_LAZY_LOG_CAP")) c->log_cap = std::max(1, atoi(lc)); // tests: force log wrap
   c->B = cfg->max_batch; c->W = cfg->width; c->Wp = rup(cfg->width, 32);
   c->k = cfg->num_factors; c->kp = rup(c->k, 32);
   if (cfg->kind == GANMF_KIND_GANMF) {
@@ -317,6 +328,8 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   c->ids_cap = std::max(cfg->n_rows, 2 * B);
   RC(dalloc(&c->ids, (size_t)c->ids_cap));
   RC(dalloc(&c->slot, (size_t)cfg->n_rows));
+  RC(dalloc(&c->p_last, (size_t)cfg->n_rows));
+  RC(dalloc(&c->alpha_log, (size_t)c->log_cap));
   fill_int_kernel<<<(cfg->n_rows + 255) / 256, 256>>>(c->slot, -1, (size_t)cfg->n_rows);
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
@@ -334,6 +347,7 @@ void ganmf_destroy(ganmf_ctx* c) {
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
   cudaFree(c->d_slab); cudaFree(c->p_slab); cudaFree(c->v_slab);
+  cudaFree(c->p_last); cudaFree(c->alpha_log);
   for (Mat* m : {&c->X2, &c->H2, &c->H2s, &c->Res2, &c->dH2, &c->dF, &c->Pb, &c->dPb, &c->dhtmp, &c->Fb, &c->Ob})
     cudaFree(m->p);
   for (auto& m : c->hs) cudaFree(m.p);
@@ -352,6 +366,11 @@ void ganmf_destroy(ganmf_ctx* c) {
 int ganmf_set_stream(ganmf_ctx* c, void* s) {
   if (!c) return fail("null ctx");
   c->st = (cudaStream_t)s;
+  return 0;
+}
+int ganmf_set_gemm_sms(ganmf_ctx* c, int n_sms) {
+  if (!c || n_sms < 0) return fail("bad argument");
+  c->gemm_sm_cap = n_sms;
   return 0;
 }
 int ganmf_synchronize(ganmf_ctx* c) {
@@ -416,6 +435,27 @@ int ganmf_set_csr(ganmf_ctx* c, int which, int n_rows, int n_cols, const int32_t
   return 0;
 }
 
+// ------------------------------------------------------------------------------ lazy user factors
+// Replay the deferred zero-gradient Adam steps: for the rows in ids (device), or for every row.
+static int p_catchup(ganmf_ctx* c, const int* ids_dev, int n) {
+  if (!c->p_stale || n <= 0) return 0;
+  const Param& P = c->params[c->n_d];
+  const int grid = ids_dev ? n : std::min(n, 148 * 16);
+  p_catchup_kernel<<<grid, 64, 0, c->st>>>(P.w.p, P.m, P.v, P.w.ld, ids_dev, n, c->p_last, c->alpha_log, c->g_T,
+                                          c->log_base);
+  CU(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+// Every reader of the whole matrix (export, snapshot, scoring, a dense optimiser step) calls this first.
+static int p_flush(ganmf_ctx* c) {
+  if (!c->p_stale) return 0;
+  RC(p_catchup(c, nullptr, c->cfg.n_rows));
+  c->p_stale = false;
+  c->log_base = c->g_T;                  // nothing older than g_T is ever replayed again
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ parameters
 static Param* find_param(ganmf_ctx* c, const char* name) {
   for (auto& p : c->params)
@@ -436,6 +476,7 @@ int ganmf_set_param(ganmf_ctx* c, const char* name, const float* host, int64_t c
   Param* p = c ? find_param(c, name) : nullptr;
   if (!p) return fail("unknown parameter %s", name ? name : "(null)");
   if (count != (int64_t)p->w.rows * p->w.cols) return fail("%s: expected %d x %d", name, p->w.rows, p->w.cols);
+  RC(p_flush(c));
   CU(cudaStreamSynchronize(c->st));
   CU(cudaMemcpy2D(p->w.p, (size_t)p->w.ld * 4, host, (size_t)p->w.cols * 4, (size_t)p->w.cols * 4,
                   p->w.rows, cudaMemcpyHostToDevice));
@@ -445,6 +486,7 @@ int ganmf_get_param(ganmf_ctx* c, const char* name, float* host, int64_t count) 
   Param* p = c ? find_param(c, name) : nullptr;
   if (!p) return fail("unknown parameter %s", name ? name : "(null)");
   if (count != (int64_t)p->w.rows * p->w.cols) return fail("%s: expected %d x %d", name, p->w.rows, p->w.cols);
+  RC(p_flush(c));
   CU(cudaStreamSynchronize(c->st));
   CU(cudaMemcpy2D(host, (size_t)p->w.cols * 4, p->w.p, (size_t)p->w.ld * 4, (size_t)p->w.cols * 4,
                   p->w.rows, cudaMemcpyDeviceToHost));
@@ -481,6 +523,9 @@ int ganmf_init_params(ganmf_ctx* c, uint64_t seed) {
 }
 int ganmf_reset_optimizers(ganmf_ctx* c) {
   if (!c) return fail("null ctx");
+  c->p_stale = false;                     // the moments are zeroed: nothing deferred survives
+  c->g_T = 0; c->log_base = 0;
+  CU(cudaMemsetAsync(c->p_last, 0, (size_t)c->cfg.n_rows * 4, c->st));
   CU(cudaMemsetAsync(c->d_slab + c->d_elems, 0, 3 * c->d_elems * 4, c->st));   // m, v, grad
   CU(cudaMemsetAsync(c->p_slab + c->p_elems, 0, 2 * c->p_elems * 4, c->st));
   CU(cudaMemsetAsync(c->v_slab + c->v_elems, 0, 3 * c->v_elems * 4, c->st));
@@ -489,6 +534,7 @@ int ganmf_reset_optimizers(ganmf_ctx* c) {
   return 0;
 }
 int ganmf_snapshot(ganmf_ctx* c) {
+  RC(p_flush(c));
   CU(cudaMemcpyAsync(c->d_slab + 4 * c->d_elems, c->d_slab, c->d_elems * 4, cudaMemcpyDeviceToDevice, c->st));
   CU(cudaMemcpyAsync(c->p_slab + 3 * c->p_elems, c->p_slab, c->p_elems * 4, cudaMemcpyDeviceToDevice, c->st));
   CU(cudaMemcpyAsync(c->v_slab + 4 * c->v_elems, c->v_slab, c->v_elems * 4, cudaMemcpyDeviceToDevice, c->st));
@@ -499,6 +545,7 @@ int ganmf_restore(ganmf_ctx* c) {
   // the reference's shadow variables exist from graph construction with their own random init
   // (GANMF.py:123-128); restoring before any snapshot is therefore refused instead of guessed
   if (!c->have_best) return fail("load_model() before any save_current_model()");
+  RC(p_flush(c));                          // theta is replaced, the moments stay: bring them to the current step first
   CU(cudaMemcpyAsync(c->d_slab, c->d_slab + 4 * c->d_elems, c->d_elems * 4, cudaMemcpyDeviceToDevice, c->st));
   CU(cudaMemcpyAsync(c->p_slab, c->p_slab + 3 * c->p_elems, c->p_elems * 4, cudaMemcpyDeviceToDevice, c->st));
   CU(cudaMemcpyAsync(c->v_slab, c->v_slab + 4 * c->v_elems, c->v_elems * 4, cudaMemcpyDeviceToDevice, c->st));
@@ -535,6 +582,7 @@ static int forward_generator(ganmf_ctx* c, int ids_offset, int B) {
   CU(csr_gather_dense(tr.indptr, tr.indices, tr.data, ids, B, c->X2.p, c->X2.ld, 0, c->st));
   const Param& P = c->params[c->n_d];
   const Param& V = c->params[c->n_d + 1];
+  RC(p_catchup(c, ids, B));                // deferred optimiser steps of exactly these rows
   gather_rows_kernel<<<B, 64, 0, c->st>>>(P.w.p, ids, c->Pb.p, c->Pb.ld);
   CU(cudaGetLastError());
   c->launches += 2;
@@ -680,7 +728,13 @@ static int d_apply_impl(ganmf_ctx* c, float lr, float reg, int loss_slot) {
 }
 
 static int ganmf_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float alpha,
-                           bool fuse_adam = false, float adam_step = 0.f, float adam_reg = 0.f) {
+                           bool fuse_adam = false, float adam_step = 0.f, float adam_reg = 0.f, int part = 0) {
+  if (part == 2) {                                                                 // dPb only (after part 1)
+    Param& V2 = c->params[c->n_d + 1];
+    Epilogue e9;
+    e9.out = c->dPb.p; e9.ldo = c->dPb.ld;
+    return gemm(c, c->dF.p, c->dF.ld, 0, V2.w.p, V2.w.ld, 1, B, c->k, c->W, e9);
+  }
   RC(forward_generator(c, ids_offset, B));
   Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
   Param& V = c->params[c->n_d + 1];
@@ -706,9 +760,14 @@ static int ganmf_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, fl
   e7.out = c->dF.p; e7.ldo = c->dF.ld;
   e7.c1 = c->Res2.row(B); e7.ldc1 = c->Res2.ld; e7.beta1 = -c1;
   RC(gemm(c, c->dH2.row(B), c->dH2.ld, 0, We->w.p, We->w.ld, 0, B, c->W, c->E, e7));
-  Epilogue e9;                                                                     // G9: dPb (old V)
-  e9.out = c->dPb.p; e9.ldo = c->dPb.ld;
-  RC(gemm(c, c->dF.p, c->dF.ld, 0, V.w.p, V.w.ld, 1, B, c->k, c->W, e9));
+  // G9 (dPb, reads the old V) and G8 (dV): independent unless the optimiser is fused into G8's epilogue, which
+  // rewrites V.  part 1 ends with dV so a data-parallel caller can sum it over ranks while part 2 (dPb) runs.
+  auto g9 = [&]() -> int {
+    Epilogue e9;                                                                   // G9: dPb
+    e9.out = c->dPb.p; e9.ldo = c->dPb.ld;
+    return gemm(c, c->dF.p, c->dF.ld, 0, V.w.p, V.w.ld, 1, B, c->k, c->W, e9);
+  };
+  if (fuse_adam) RC(g9());
   Epilogue e8;                                                                     // G8: dV [-> Adam(V)]
   if (fuse_adam) {
     e8.out = V.w.p; e8.ldo = V.w.ld;
@@ -718,6 +777,7 @@ static int ganmf_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, fl
   }
   RC(gemm(c, c->dF.p, c->dF.ld, 1, c->Pb.p, c->Pb.ld, 1, c->W, c->k, B, e8));
   c->launches += 1;
+  if (!fuse_adam && part != 1) RC(g9());
   return 0;
 }
 
@@ -730,13 +790,33 @@ static int g_apply_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float
     dis_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, 1, alpha, (double)n_global, (double)n_global * c->E);
   CU(cudaGetLastError());
   const int* ids = c->ids + ids_offset;
-  set_slots_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(c->slot, ids, B, 0);
-  CU(cudaGetLastError());
-  if (v_done) RC(adam_group(c, c->n_d, 1, adam_step, reg, c->n_d));          // user factors only
-  else RC(adam_group(c, c->n_d, 2, adam_alpha(c, 1, lr), reg, c->n_d));
-  set_slots_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(c->slot, ids, B, 1);
-  CU(cudaGetLastError());
-  c->launches += 3;
+  if (c->lazy_p && reg == 0.f) {
+    // user factors: Adam on the minibatch rows only, every other row defers its zero-gradient step
+    // (kernels.cuh K6b); item factors: the usual dense update
+    const float a = v_done ? adam_step : adam_alpha(c, 1, lr);
+    if (c->g_T - c->log_base >= c->log_cap) RC(p_flush(c));
+    Param& P = c->params[c->n_d];
+    p_batch_adam_kernel<<<B, 64, 0, c->st>>>(P.w.p, P.m, P.v, P.w.ld, ids, c->dPb.p, c->dPb.ld, a, c->p_last,
+                                             c->alpha_log, c->g_T, c->log_base);
+    CU(cudaGetLastError());
+    c->launches++;
+    c->g_T++;
+    c->p_stale = true;
+    if (!v_done) RC(adam_group(c, c->n_d + 1, 1, a, reg, -1));
+  } else {
+    RC(p_flush(c));
+    set_slots_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(c->slot, ids, B, 0);
+    CU(cudaGetLastError());
+    if (v_done) RC(adam_group(c, c->n_d, 1, adam_step, reg, c->n_d));          // user factors only
+    else RC(adam_group(c, c->n_d, 2, adam_alpha(c, 1, lr), reg, c->n_d));
+    set_slots_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(c->slot, ids, B, 1);
+    CU(cudaGetLastError());
+    c->g_T++;
+    c->log_base = c->g_T;
+    fill_int_kernel<<<(c->cfg.n_rows + 255) / 256, 256, 0, c->st>>>(c->p_last, c->g_T, (size_t)c->cfg.n_rows);
+    CU(cudaGetLastError());
+    c->launches += 4;
+  }
   if (n_global == B) {       // under data parallelism the caller sums l2_shard over ranks first
     finalize_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, reg, c->losses, loss_slot);
     CU(cudaGetLastError());
@@ -900,11 +980,19 @@ int ganmf_d_apply(ganmf_ctx* c, float lr, float reg, int loss_slot) {
   if (!c) return fail("null ctx");
   return d_apply_impl(c, lr, reg, loss_slot);
 }
+
 int ganmf_g_forward_backward(ganmf_ctx* c, int ids_offset, int B, int n_global, float alpha) {
   RC(check_batch(c, ids_offset, B));
   c->last_ids_offset = ids_offset;
   return c->cfg.kind == GANMF_KIND_GANMF ? ganmf_g_fb_impl(c, ids_offset, B, n_global, alpha)
                                          : dis_g_fb_impl(c, ids_offset, B, n_global, alpha);
+}
+int ganmf_g_forward_backward_part(ganmf_ctx* c, int ids_offset, int B, int n_global, float alpha, int part) {
+  RC(check_batch(c, ids_offset, B));
+  if (c->cfg.kind != GANMF_KIND_GANMF) return fail("two-part G backward: GANMF only");
+  if (part < 1 || part > 2) return fail("part must be 1 or 2");
+  c->last_ids_offset = ids_offset;
+  return ganmf_g_fb_impl(c, ids_offset, B, n_global, alpha, false, 0.f, 0.f, part);
 }
 int ganmf_g_apply(ganmf_ctx* c, int B, int n_global, float lr, float reg, float alpha, int loss_slot) {
   if (!c) return fail("null ctx");
@@ -1069,6 +1157,7 @@ static int ensure_eval_buffers(ganmf_ctx* c, int block, int K, int n_cut) {
 // Ranking needs fp32-accurate scores (near-ties decide the order), so scoring runs the tensor cores
 // on split-TF32 operands: one GEMM over K' = 3k (see split3_rows_kernel).
 static int prepare_item_factors(ganmf_ctx* c) {
+  RC(p_flush(c));
   const Param& other = c->cfg.item_mode ? c->params[c->n_d] : c->params[c->n_d + 1];
   split3_rows_kernel<<<other.w.rows, 64, 0, c->st>>>(other.w.p, other.w.ld, nullptr, c->Ob.p, c->Ob.ld, c->k, 1);
   CU(cudaGetLastError());

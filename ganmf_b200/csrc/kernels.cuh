@@ -162,7 +162,6 @@ __global__ void __launch_bounds__(ADAM_THREADS) fused_adam_kernel(const AdamArgs
       }
     }
   }
-  const float c1 = 1.f - ADAM_B1, c2 = 1.f - ADAM_B2;
 #pragma unroll
   for (int j = 0; j < ADAM_VEC_PER_THREAD; ++j) {
     const unsigned long long i = base + j * ADAM_THREADS + threadIdx.x;
@@ -173,12 +172,8 @@ __global__ void __launch_bounds__(ADAM_THREADS) fused_adam_kernel(const AdamArgs
       const float* gp = reinterpret_cast<const float*>(&g[j]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float th0 = tp[e];
-        sq += th0 * th0;
-        const float ge = gp[e] + a.reg * th0;
-        mp[e] = mp[e] + (ge - mp[e]) * c1;
-        vp[e] = vp[e] + (ge * ge - vp[e]) * c2;
-        tp[e] = th0 - (mp[e] * a.alpha) / (sqrtf(vp[e]) + ADAM_EPS);
+        sq += tp[e] * tp[e];
+        adam_elem(gp[e], tp[e], mp[e], vp[e], a.alpha, a.reg);
       }
       th[i] = t[j]; mm[i] = m[j]; vv[i] = v[j];
     }
@@ -207,6 +202,73 @@ inline cudaError_t fused_adam(AdamArgs& a, cudaStream_t st) {
   if (blk == 0) return cudaSuccess;
   fused_adam_kernel<<<(unsigned)blk, ADAM_THREADS, 0, st>>>(a);
   return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------- K6b lazy user factors
+// TF's Adam is dense over the user-factor matrix P: with g_reg = 0 a row outside the minibatch still takes
+// the zero-gradient update  m *= b1-ish, v *= b2-ish, theta -= alpha_t * m / (sqrt(v) + eps)  every G
+// step (28 B/parameter of HBM traffic for rows whose values nobody reads until they are sampled again).
+// These updates depend only on the row's own (theta, m, v) and the step sizes alpha_t, so they are
+// DEFERRED: last[row] records the G step the row is current at, alpha_log keeps alpha_t, and a row replays
+// the steps it missed -- the same adam_elem() calls in the same order, in registers -- right before it is
+// read (minibatch gather, scoring, snapshot, export).  Bit-identical to the dense sweep by construction.
+__global__ void __launch_bounds__(64) p_catchup_kernel(float* __restrict__ theta, float* __restrict__ m,
+                                                       float* __restrict__ v, int ld, const int* __restrict__ ids,
+                                                       int n, int* __restrict__ last,
+                                                       const float* __restrict__ alpha_log, int T, int log_base) {
+  const int ld4 = ld >> 2;
+  for (int b = blockIdx.x; b < n; b += gridDim.x) {
+    const int row = ids ? ids[b] : b;
+    const int t0 = last[row];
+    __syncthreads();                                  // everyone has read last[row] before it is advanced
+    if (t0 >= T) continue;                            // block-uniform
+    float4* th4 = reinterpret_cast<float4*>(theta + (size_t)row * ld);
+    float4* m4 = reinterpret_cast<float4*>(m + (size_t)row * ld);
+    float4* v4 = reinterpret_cast<float4*>(v + (size_t)row * ld);
+    for (int c = threadIdx.x; c < ld4; c += blockDim.x) {
+      float4 mm = m4[c], vv = v4[c];
+      const bool idle = mm.x == 0.f && mm.y == 0.f && mm.z == 0.f && mm.w == 0.f && vv.x == 0.f && vv.y == 0.f &&
+                        vv.z == 0.f && vv.w == 0.f;
+      if (idle) continue;                             // never-sampled row: m = v = 0 is a fixed point
+      float4 tt = th4[c];
+      for (int t = t0; t < T; ++t) {
+        const float a = __ldg(alpha_log + (t - log_base));
+        adam_elem(0.f, tt.x, mm.x, vv.x, a, 0.f);
+        adam_elem(0.f, tt.y, mm.y, vv.y, a, 0.f);
+        adam_elem(0.f, tt.z, mm.z, vv.z, a, 0.f);
+        adam_elem(0.f, tt.w, mm.w, vv.w, a, 0.f);
+      }
+      th4[c] = tt; m4[c] = mm; v4[c] = vv;
+    }
+    if (threadIdx.x == 0) last[row] = T;
+  }
+}
+
+// G step T+1 on the (current) minibatch rows with their data gradient g[b, :]; logs alpha_{T+1}.
+__global__ void __launch_bounds__(64) p_batch_adam_kernel(float* __restrict__ theta, float* __restrict__ m,
+                                                          float* __restrict__ v, int ld, const int* __restrict__ ids,
+                                                          const float* __restrict__ g, int ldg, float alpha,
+                                                          int* __restrict__ last, float* __restrict__ alpha_log,
+                                                          int T, int log_base) {
+  const int row = ids[blockIdx.x];
+  const int ld4 = ld >> 2;
+  float4* th4 = reinterpret_cast<float4*>(theta + (size_t)row * ld);
+  float4* m4 = reinterpret_cast<float4*>(m + (size_t)row * ld);
+  float4* v4 = reinterpret_cast<float4*>(v + (size_t)row * ld);
+  const float4* g4 = reinterpret_cast<const float4*>(g + (size_t)blockIdx.x * ldg);
+  for (int c = threadIdx.x; c < ld4; c += blockDim.x) {
+    float4 tt = th4[c], mm = m4[c], vv = v4[c];
+    const float4 gg = g4[c];
+    adam_elem(gg.x, tt.x, mm.x, vv.x, alpha, 0.f);
+    adam_elem(gg.y, tt.y, mm.y, vv.y, alpha, 0.f);
+    adam_elem(gg.z, tt.z, mm.z, vv.z, alpha, 0.f);
+    adam_elem(gg.w, tt.w, mm.w, vv.w, alpha, 0.f);
+    th4[c] = tt; m4[c] = mm; v4[c] = vv;
+  }
+  if (threadIdx.x == 0) {
+    last[row] = T + 1;
+    if (blockIdx.x == 0) alpha_log[T - log_base] = alpha;
+  }
 }
 
 // ----------------------------------------------------------------------------- reductions

@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "ptx.cuh"
 
 namespace ganmf {
@@ -29,6 +30,8 @@ constexpr int TC_BM = 128;         // output tile rows (UMMA M)
 constexpr int TC_BK = 32;          // fp32 elements of K per stage (128 bytes)
 constexpr int TC_UMMA_K = 8;       // tf32: 32 bytes of K per instruction
 constexpr int TC_THREADS = 320;     // TMA warp, MMA warp, 8 epilogue warps
+constexpr int TC_SCHED = 8;         // depth of the work-unit ring between the producer and its consumers
+constexpr int TC_SCHED_SLOTS = 64;  // scheduler states cycled over launches (GEMMs in flight at once)
 
 enum Act { ACT_LINEAR = 0, ACT_TANH = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
 __device__ __forceinline__ float act_fwd(int act, float z) {
@@ -77,11 +80,14 @@ struct Epilogue {
 };
 
 constexpr float TC_ADAM_B1 = 0.9f, TC_ADAM_B2 = 0.999f, TC_ADAM_EPS = 1e-8f;
+// The ONE element update every optimiser path shares (fused_adam_kernel, the GEMM epilogue, the lazy
+// user-factor kernels).  Every operation is an explicit round-to-nearest intrinsic, so no path depends on
+// the compiler's contraction choices and a replayed update is bit-identical to the one it stands for.
 __device__ __forceinline__ void adam_elem(float g, float& th, float& m, float& v, float alpha, float reg) {
-  const float ge = g + reg * th;
-  m = m + (ge - m) * (1.f - TC_ADAM_B1);
-  v = v + (ge * ge - v) * (1.f - TC_ADAM_B2);
-  th = th - (m * alpha) / (sqrtf(v) + TC_ADAM_EPS);
+  const float ge = __fmaf_rn(reg, th, g);
+  m = __fmaf_rn(__fsub_rn(ge, m), 1.f - TC_ADAM_B1, m);
+  v = __fmaf_rn(__fmaf_rn(ge, ge, -v), 1.f - TC_ADAM_B2, v);
+  th = __fsub_rn(th, __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), TC_ADAM_EPS)));
 }
 
 struct TcGemmArgs {
@@ -97,6 +103,7 @@ struct TcGemmArgs {
   uint32_t a_kstep, b_kstep;             // start-address advance per UMMA_K, bytes >> 4
   uint32_t a_mtstep;                     // start-address advance per 128-row sub-tile of A, bytes >> 4
   uint32_t idesc;
+  unsigned int* sched;     // {next unit, CTAs done}: dynamic unit scheduler state (self-resetting)
   Epilogue ep;
 };
 
@@ -154,7 +161,8 @@ struct TcSmem {
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;          // 8 warps x 32 rows x 8 float4 (swizzled)
   static constexpr int EPI_BYTES = 8 * 32 * 32 * 4;
   static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;  // + align slack
+  static constexpr int SCHED_OFF = BAR_OFF + (2 * STAGES + 4) * 8 + 16;     // unit ring: full/empty barriers + ids
+  static constexpr int TOTAL = SCHED_OFF + TC_SCHED * (8 + 8 + 4) + 16 + 1024;  // + align slack
 };
 
 // Work unit = (output tile, K split).  Units are numbered so that consecutive units (which run
@@ -175,7 +183,13 @@ __device__ __forceinline__ TcUnit tc_unit(int u, int tiles_m, int tiles_n, int m
   return r;
 }
 
-// Persistent kernel: grid = min(#units, #SMs); each CTA walks units blockIdx.x, +gridDim.x, ...
+// Persistent kernel: grid = min(#units, #SMs).  Units are handed out DYNAMICALLY: the producer lane takes
+// the next unit from a global counter (one atomicAdd per unit, issued one unit ahead so its latency hides
+// under the loads) and publishes it to the MMA and epilogue warps through a small shared-memory ring.
+// A static blockIdx.x + i*gridDim.x walk needs every CTA resident from the start; when a collective
+// (NCCL over NVLink) holds some SMs, the CTAs that cannot be placed would run as a second wave and double
+// the GEMM's duration.  With the counter, late CTAs simply find less (or no) work.  The last CTA to leave
+// resets the counter pair, so launches need no memset.
 // Two TMEM accumulator stages let the epilogue of unit i overlap the MMAs of unit i+1.
 template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -193,6 +207,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* sched_full = reinterpret_cast<uint64_t*>(smem + S::SCHED_OFF);
+  uint64_t* sched_empty = sched_full + TC_SCHED;
+  volatile int* sched_unit = reinterpret_cast<volatile int*>(sched_empty + TC_SCHED);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -213,6 +230,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], 8);         // one arrival per epilogue warp
     }
+    for (int i = 0; i < TC_SCHED; ++i) {
+      ptx::mbar_init(&sched_full[i], 1);
+      ptx::mbar_init(&sched_empty[i], 9);            // MMA lane + one per epilogue warp
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -227,8 +248,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
-      uint32_t it = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      uint32_t it = 0, si = 0;
+      // first unit = blockIdx.x (no atomic in front of the first load; single-wave GEMMs behave exactly like
+      // a static grid), every later unit = gridDim.x + counter
+      const bool dyn = args.sched != nullptr;
+      const int g = (int)gridDim.x;
+      int u = (int)blockIdx.x;
+      while (true) {
+        const int sl = si % TC_SCHED;
+        ptx::mbar_wait(&sched_empty[sl], ((si / TC_SCHED) & 1) ^ 1);
+        sched_unit[sl] = u < n_units ? u : -1;
+        ptx::mbar_arrive(&sched_full[sl]);           // release: the id is visible to the waiters
+        ++si;
+        if (u >= n_units) break;
+        // in flight while this unit's loads are issued
+        const int u_next = dyn ? g + (int)atomicAdd(args.sched, 1u) : u + g;
         const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN, BM);
         const int kb_begin = un.split * args.kb_per_split;
         const int kb_end = min(kb_begin + args.kb_per_split, total_kb);
@@ -257,13 +291,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               ptx::tma_load_2d(sb + j * (TC_BK * 128), &map_b, &full_bar[s], un.n0 + 32 * j, k0);
           }
         }
+        u = u_next;
+      }
+      // every CTA makes its last counter increment before it reports done, so the CTA that sees all others
+      // done can hand a clean state to the next launch that uses this slot
+      if (dyn) {
+        __threadfence();
+        if (atomicAdd(args.sched + 1, 1u) == gridDim.x - 1) {
+          args.sched[0] = 0u;
+          args.sched[1] = 0u;
+          __threadfence();
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (ptx::elect_one()) {
       uint32_t it = 0, ui = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+      for (;; ++ui) {
+        const int sl = ui % TC_SCHED;
+        ptx::mbar_wait(&sched_full[sl], (ui / TC_SCHED) & 1);
+        const int u = sched_unit[sl];
+        ptx::mbar_arrive(&sched_empty[sl]);
+        if (u < 0) break;
         const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN, BM);
         const int kb_begin = un.split * args.kb_per_split;
         const int nkb = min(kb_begin + args.kb_per_split, total_kb) - kb_begin;
@@ -317,8 +367,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                     (!ep.adam_m || (al16(ep.adam_m, 4) && al16(ep.adam_v, 4))));
     const bool use_c1 = !partial && ep.c1 != nullptr;
     float sq0 = 0.f, sq1 = 0.f;
-    uint32_t ui = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+    for (uint32_t ui = 0;; ++ui) {
+      const int sl = ui % TC_SCHED;
+      ptx::mbar_wait(&sched_full[sl], (ui / TC_SCHED) & 1);
+      const int u = sched_unit[sl];
+      __syncwarp();                                   // every lane has read the id before the slot is released
+      if (lane == 0) ptx::mbar_arrive(&sched_empty[sl]);
+      if (u < 0) break;
       const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN, BM);
       const uint32_t acc = ui % ACC;
       const bool interior = vec_all && (un.m0 + BM <= args.M) && (un.n0 + BN <= args.N);
@@ -596,6 +651,7 @@ struct TcGemmCall {
   // bring-up overrides for the MN-major tile encoding (0 = use the defaults below)
   int dbg_mn_layout = 0, dbg_mn_sbo = 0, dbg_mn_lbo = 0, dbg_mn_swizzle = 0, dbg_epi = 0;
   TmapCache* cache = nullptr;
+  int max_ctas = 0;        // > 0: cap on the persistent grid (SMs left free for a concurrent collective)
 };
 
 inline uint32_t make_idesc_tf32(int bn, int a_mn, int b_mn) {
@@ -610,6 +666,25 @@ inline uint32_t make_idesc_tf32(int bn, int a_mn, int b_mn) {
   d |= (uint32_t)(bn >> 3) << 17;
   d |= (uint32_t)(TC_BM >> 4) << 24;
   return d;
+}
+
+// Scheduler state for the next launch: TC_SCHED_SLOTS {next, done} pairs per device, used round-robin so
+// GEMMs that overlap on different streams never share a pair; each pair is zero again when its kernel ends.
+inline cudaError_t tc_sched_slot(unsigned int** out) {
+  static unsigned int* base[64] = {};
+  static unsigned int seq = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!base[dev]) {
+    e = cudaMalloc((void**)&base[dev], TC_SCHED_SLOTS * 2 * sizeof(unsigned int));
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(base[dev], 0, TC_SCHED_SLOTS * 2 * sizeof(unsigned int));
+    if (e != cudaSuccess) return e;
+  }
+  *out = base[dev] + 2 * (seq++ % TC_SCHED_SLOTS);
+  return cudaSuccess;
 }
 
 template <int BN, int STAGES, int MT>
@@ -631,7 +706,18 @@ inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const
     if (num_sms <= 0) num_sms = 148;
   }
   const int units = ((c.N + BN - 1) / BN) * ((c.M + MT * TC_BM - 1) / (MT * TC_BM)) * splits;
-  const int grid = units < num_sms ? units : num_sms;
+  const int sms = (c.max_ctas > 0 && c.max_ctas < num_sms) ? c.max_ctas : num_sms;
+  const int grid = units < sms ? units : sms;
+  static int static_sched = -1;          // GANMF_STATIC_SCHED=1: A/B switch, units blockIdx.x + i*gridDim.x
+  if (static_sched < 0) {
+    const char* e = getenv("GANMF_STATIC_SCHED");
+    static_sched = (e && e[0] == '1') ? 1 : 0;
+  }
+  args.sched = nullptr;
+  if (!static_sched && units > grid) {
+    cudaError_t es = tc_sched_slot(&args.sched);
+    if (es != cudaSuccess) return es;
+  }
   tc_gemm_kernel<BN, STAGES, MT><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, args);
   return cudaGetLastError();
 }

@@ -48,6 +48,9 @@ class Engine(object):
     def set_stream(self, cuda_stream_ptr):
         L.check(self.lib.ganmf_set_stream(self.ctx, C.c_void_p(int(cuda_stream_ptr))))
 
+    def set_gemm_sms(self, n_sms):
+        L.check(self.lib.ganmf_set_gemm_sms(self.ctx, int(n_sms)))
+
     def synchronize(self):
         L.check(self.lib.ganmf_synchronize(self.ctx))
 
@@ -159,6 +162,10 @@ class Engine(object):
 
     def d_apply(self, lr, reg, loss_slot):
         L.check(self.lib.ganmf_d_apply(self.ctx, lr, reg, loss_slot))
+
+    def g_forward_backward_part(self, ids_offset, B, n_rows_global, recon_coefficient, part):
+        L.check(self.lib.ganmf_g_forward_backward_part(self.ctx, ids_offset, B, n_rows_global, recon_coefficient,
+                                                       part))
 
     def g_forward_backward(self, ids_offset, B, n_rows_global, recon_coefficient):
         L.check(self.lib.ganmf_g_forward_backward(self.ctx, ids_offset, B, n_rows_global, recon_coefficient))

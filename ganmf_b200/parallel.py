@@ -8,9 +8,33 @@ exchanged quantities are sums:
           discriminator gradients (one contiguous buffer);
   G step: the item-factor gradient and the loss scalars.  dP rows never leave their owner.
 Gradients are already normalised by the global element count, so the collective is a plain SUM."""
+import os
 import time
 
 import numpy as np
+
+
+# SMs set aside for NCCL while a collective overlaps the GEMMs, and the matching cap on NCCL's CTAs.  Measured
+# at N=2 on cfg4 (profiles/r01_dp_overlap_ab_n2.txt): no reservation 2.73 ms/step, 16: 2.99, 24: 2.79,
+# 32: 2.59, 40: 2.57 -- below 32 CTAs NCCL's own bandwidth drops (reduce-scatter of 105 MB: 0.155 -> 0.206 ms
+# at 16), without a reservation its kernels wait for the persistent GEMM to drain.
+NCCL_CTAS = 32
+
+
+def init_nccl(local_rank):
+    """One process per GPU over NCCL/NVLink.  GANMF_NCCL_MAX_CTAS caps the SMs NCCL may occupy: its kernels run
+    concurrently with the tcgen05 GEMMs (whose CTAs need a whole SM each), and over NVSwitch a collective does
+    not need many CTAs to saturate the links."""
+    import torch
+    import torch.distributed as dist
+    kw = {}
+    cap = int(os.environ.get("GANMF_NCCL_MAX_CTAS", str(NCCL_CTAS)))
+    if cap > 0:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = cap
+        opts.config.min_ctas = min(cap, max(1, int(os.environ.get("GANMF_NCCL_MIN_CTAS", "1"))))
+        kw["pg_options"] = opts
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), **kw)
 
 
 class DataParallelTrainer(object):
@@ -24,6 +48,7 @@ class DataParallelTrainer(object):
         self.overlap = False
         self.sharded_adam = False
         self._pending = []
+        self._pending_loss = None
         if buffers is None:
             dev = torch.device("cuda", torch.cuda.current_device())
             names = ["d_grads", "g_shared_grad", "step_scalars"]
@@ -47,6 +72,13 @@ class DataParallelTrainer(object):
                 self._enc_chunk, self._dec_chunk = slice(r * ce, (r + 1) * ce), slice(r * cd, (r + 1) * cd)
                 # slab layout: [We | be | Wd | bd]  (enc half first)
                 self._ranges = ([r * ce, ne + r * cd], [ce, cd])
+                self._rank = r
+                # SMs the GEMMs leave to NCCL while a collective is in flight (0 = no reservation)
+                self._reserve = int(os.environ.get("GANMF_DP_RESERVE_SMS", str(NCCL_CTAS)))
+
+    def _cap(self, on):
+        if getattr(self, "_reserve", 0) > 0:
+            self.eng.set_gemm_sms(148 - self._reserve if on else 0)
 
     def _sum(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
@@ -55,12 +87,16 @@ class DataParallelTrainer(object):
         for w in self._pending:
             w.wait()
         self._pending = []
+        if self._pending_loss is not None:
+            self.eng.finalize_loss(*self._pending_loss)
+            self._pending_loss = None
 
     def d_step(self, ids_offset, B, lr, reg, m_hinge, loss_slot):
         n_global = B * self.world
         if self._pending:
             self.eng.d_forward_phase(ids_offset, B, 1)    # profiles + generator overlap the weight all-gather
             self._wait_pending()
+            self._cap(False)
             self.eng.d_forward_phase(ids_offset, B, 2)
         else:
             self.eng.d_forward(ids_offset, B)
@@ -74,6 +110,7 @@ class DataParallelTrainer(object):
             self.eng.d_backward_phase(B, n_global, m_hinge, 1)
             w = d.reduce_scatter_tensor(self.d_dec[self._dec_chunk], self.d_dec, op=d.ReduceOp.SUM, group=self.group,
                                         async_op=True)
+            self._cap(True)                                               # until the last all-gather has landed
             self.eng.d_backward_phase(B, n_global, m_hinge, 3)            # dH: last reader of the old Wd
             w.wait()
             self.eng.d_apply_ranges(lr, reg, [self._ranges[0][1]], [self._ranges[1][1]], new_step=True)
@@ -82,11 +119,13 @@ class DataParallelTrainer(object):
             self.eng.d_backward_phase(B, n_global, m_hinge, 4)            # dWe
             d.reduce_scatter_tensor(self.d_enc[self._enc_chunk], self.d_enc, op=d.ReduceOp.SUM, group=self.group)
             self.eng.d_apply_ranges(lr, reg, [self._ranges[0][0]], [self._ranges[1][0]], new_step=False)
-            self._sum(self.scalars[6:7])                                 # (before AG(enc): NCCL ops are serial)
-            self.eng.finalize_loss(reg, loss_slot)
             ag_enc = d.all_gather_into_tensor(self.p_enc, self.p_enc[self._enc_chunk], group=self.group,
                                               async_op=True)
-            self._pending = [ag_dec, ag_enc]                             # awaited before the weights are read
+            # sum(theta^2) lives in rank shards; its sum and the loss bookkeeping trail the all-gather (NCCL ops
+            # are serial) and are settled when the weights are awaited, before the scalars are reused
+            w_l2 = d.all_reduce(self.scalars[6:7], op=d.ReduceOp.SUM, group=self.group, async_op=True)
+            self._pending = [ag_dec, ag_enc, w_l2]                       # awaited before the weights are read
+            self._pending_loss = (reg, loss_slot)
             return
         if self.overlap:
             # decoder gradients are summed on NCCL's stream while the encoder half is still computed
@@ -103,9 +142,22 @@ class DataParallelTrainer(object):
     def g_step(self, ids_offset, B, lr, reg, recon_coefficient, loss_slot):
         n_global = B * self.world
         self._wait_pending()
-        self.eng.g_forward_backward(ids_offset, B, n_global, recon_coefficient)
-        self._sum(self.g_shared)
-        self._sum(self.scalars)
+        self._cap(False)
+        if self.overlap:
+            # dV is complete after part 1: its sum over ranks (and the loss scalars) travel while dPb is computed
+            d = self.dist
+            self.eng.g_forward_backward_part(ids_offset, B, n_global, recon_coefficient, 1)
+            w1 = d.all_reduce(self.g_shared, op=d.ReduceOp.SUM, group=self.group, async_op=True)
+            w2 = d.all_reduce(self.scalars, op=d.ReduceOp.SUM, group=self.group, async_op=True)
+            self._cap(True)
+            self.eng.g_forward_backward_part(ids_offset, B, n_global, recon_coefficient, 2)
+            self._cap(False)
+            w1.wait()
+            w2.wait()
+        else:
+            self.eng.g_forward_backward(ids_offset, B, n_global, recon_coefficient)
+            self._sum(self.g_shared)
+            self._sum(self.scalars)
         self.eng.g_apply(B, n_global, lr, reg, recon_coefficient, loss_slot)
         if reg != 0.0:
             self._sum(self.scalars[6:7])          # ||P||^2 lives in row shards
@@ -130,6 +182,7 @@ class DataParallelTrainer(object):
                 self.g_step(off, min(batch_size, n - off), hp["g_lr"], hp["g_reg"], hp["alpha"], slot)
                 slot += 1
         self._wait_pending()
+        self._cap(False)
         losses = self.eng.read_losses(slot)
         return losses[:nd], losses[nd:]
 

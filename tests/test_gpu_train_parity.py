@@ -177,10 +177,73 @@ def test_phased_and_ranged_updates_equal_the_fused_step():
                     eng.d_apply_ranges(hp["d_lr"], hp["d_reg"], [0], [half], new_step=True)
                     eng.d_apply_ranges(hp["d_lr"], hp["d_reg"], [half], [n_d - half], new_step=False)
                     eng.finalize_loss(hp["d_reg"], 2 * s)
-            eng.g_step(off, B, hp["g_lr"], hp["g_reg"], hp["alpha"], loss_slot=2 * s + 1)
+            if variant == "fused":
+                eng.g_step(off, B, hp["g_lr"], hp["g_reg"], hp["alpha"], loss_slot=2 * s + 1)
+            else:                                       # the two-part G backward of the data-parallel trainer
+                eng.g_forward_backward_part(off, B, B, hp["alpha"], 1)
+                eng.g_forward_backward_part(off, B, B, hp["alpha"], 2)
+                eng.g_apply(B, B, hp["g_lr"], hp["g_reg"], hp["alpha"], 2 * s + 1)
         outs.append((eng.read_losses(6), eng.get_params()))
         eng.close()
     for losses, params in outs[1:]:
         np.testing.assert_allclose(losses, outs[0][0], rtol=2e-5)
         for n in params:
             assert rel_err(params[n], outs[0][1][n]) < 2e-5, n
+
+
+def _run_lazy_ab(monkeypatch, no_lazy, log_cap=None, kind="ganmf"):
+    """20 epochs of D+G steps with scoring, snapshot and restore in between; returns everything observable."""
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    monkeypatch.setenv("GANMF_NO_LAZY_ADAM", "1" if no_lazy else "0")
+    if log_cap is not None:
+        monkeypatch.setenv("GANMF_LAZY_LOG_CAP", str(log_cap))
+    else:
+        monkeypatch.delenv("GANMF_LAZY_LOG_CAP", raising=False)
+    n_rows, width, k, E, B = 300, 517, 24, 40, 64
+    urm = make_urm(n_rows, width, 0.05, 3)
+    if kind == "ganmf":
+        p0 = to.init_ganmf_params(n_rows, width, k, E, seed=4)
+        eng = Engine(L.KIND_GANMF, n_rows, width, k, emb_dim=E, max_batch=B, gemm_path=L.GEMM_TC)
+    else:
+        p0 = to.init_disganmf_params(n_rows, width, k, 2, 32, seed=4)
+        eng = Engine(L.KIND_DISGANMF, n_rows, width, k, d_layers=2, d_nodes=32, d_act="tanh", max_batch=B)
+    eng.set_csr(L.CSR_TRAIN, urm)
+    eng.set_params(p0)
+    eng.reset_optimizers()
+    out = []
+    users = np.arange(0, n_rows, 7, dtype=np.int32)
+    for ep, batches in to.epoch_index_stream(n_rows, B, 20, seed=1337):
+        perm = np.concatenate(batches)
+        if ep % 3 == 2:
+            perm = perm[:200]                       # some rows sit out whole epochs
+        dl, gl = eng.train_epoch(perm, B, 1, 1, HP["d_lr"], HP["g_lr"], HP["d_reg"], 0.0, HP["m"], HP["alpha"])
+        out += [np.asarray(dl), np.asarray(gl)]
+        if ep == 4:
+            out.append(eng.score(users))            # reads the user factors mid-training
+        if ep == 7:
+            eng.snapshot()
+        if ep == 12:
+            eng.restore()                           # theta replaced, moments kept
+        if ep == 15:                                # a step with g_reg != 0 takes the dense path
+            dl, gl = eng.train_epoch(perm[:64], B, 1, 1, HP["d_lr"], HP["g_lr"], HP["d_reg"], 1e-3, HP["m"],
+                                     HP["alpha"])
+            out += [np.asarray(dl), np.asarray(gl)]
+    got = eng.get_params()
+    out += [got[n] for n in sorted(got)]
+    eng.close()
+    return out
+
+
+@pytest.mark.parametrize("kind", ["ganmf", "disganmf"])
+@pytest.mark.parametrize("log_cap", [None, 3])
+def test_lazy_user_factor_adam_is_bit_identical_to_dense(monkeypatch, kind, log_cap):
+    """Deferring the zero-gradient Adam steps of unsampled user-factor rows (kernels.cuh K6b) must not change
+    a single bit of any loss, score or parameter relative to TF's dense sweep; log_cap=3 forces the
+    step-size log to wrap (flush) every third G step."""
+    dense = _run_lazy_ab(monkeypatch, True, None, kind)
+    lazy = _run_lazy_ab(monkeypatch, False, log_cap, kind)
+    assert len(dense) == len(lazy)
+    for a, b in zip(dense, lazy):
+        assert a.shape == b.shape
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))

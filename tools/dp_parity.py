@@ -20,18 +20,30 @@ sys.path.insert(0, ROOT)
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    from ganmf_b200.parallel import init_nccl
+    init_nccl(int(os.environ["LOCAL_RANK"]))
     from ganmf_b200 import _lib as L
     from ganmf_b200.engine import Engine
     from ganmf_b200.parallel import DataParallelTrainer, shard_rows
     from oracle import train_oracle as to
 
+    ok = True
+    for g_reg in (1e-3, 0.0):        # 0.0: the lazy user-factor optimiser (kernels.cuh K6b) under row sharding
+        ok = run_case(rank, world, L, Engine, DataParallelTrainer, shard_rows, to, g_reg) and ok
+    if rank == 0:
+        print("DP PARITY", "PASS" if ok else "FAIL")
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+def run_case(rank, world, L, Engine, DataParallelTrainer, shard_rows, to, g_reg):
     n_rows, width, k, E, B = 512, 700, 24, 48, 32            # B per rank
     rs = np.random.RandomState(0)
     urm = sps.random(n_rows, width, 0.05, format="csr", dtype=np.float32, random_state=rs)
     urm.data[:] = 1.0
     p0 = to.init_ganmf_params(n_rows, width, k, E, seed=3)
-    hp = dict(d_lr=1e-4, g_lr=2e-4, d_reg=1e-4, g_reg=1e-3, m=10.0, alpha=0.1)
+    hp = dict(d_lr=1e-4, g_lr=2e-4, d_reg=1e-4, g_reg=g_reg, m=10.0, alpha=0.1)
     lo, hi = shard_rows(n_rows, world, rank)
     eng = Engine(L.KIND_GANMF, hi - lo, width, k, emb_dim=E, max_batch=B, device=torch.cuda.current_device())
     eng.set_csr(L.CSR_TRAIN, urm[lo:hi])
@@ -71,17 +83,16 @@ def main():
         got["generator/user_embeddings"] = np.concatenate(shards, axis=0)
         dmax = float(np.max(np.abs(np.array(dl) / np.array(odl) - 1)))
         gmax = float(np.max(np.abs(np.array(gl) / np.array(ogl) - 1)))
-        print("world=%d steps=%d  max rel loss diff: D %.2e  G %.2e" % (world, len(dl), dmax, gmax))
+        print("world=%d g_reg=%g steps=%d  max rel loss diff: D %.2e  G %.2e" % (world, g_reg, len(dl), dmax, gmax))
         ok = dmax < 1e-3 and gmax < 1e-3
         for n in orc.p:
             err = np.linalg.norm(got[n] - orc.p[n]) / np.linalg.norm(orc.p[n])
             print("  %-34s rel err %.2e" % (n, err))
             ok = ok and err < 1e-3
-        print("DP PARITY", "PASS" if ok else "FAIL")
-    dist.barrier()
-    dist.destroy_process_group()
+    okt = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(okt, 0)
     eng.close()
-    return 0 if ok else 1
+    return bool(okt.item())
 
 
 if __name__ == "__main__":
