@@ -104,6 +104,7 @@ struct ganmf_ctx {
   int last_ids_offset = 0;
   float last_alpha_d = 0.f;
   int gemm_sm_cap = 0;        // > 0: persistent GEMM grids leave SMs free (ganmf_set_gemm_sms)
+  int pair_mode = 1;          // CTA-pair (cta_group::2) GEMM tiles: 0 = never, 1 = GEMMs with >= 148 tiles, 2 = whenever legal
   bool fuse_adam = true;      // ganmf_d_step / ganmf_g_step: optimiser inside the weight-gradient GEMMs
   // lazy user-factor optimiser (kernels.cuh K6b): p_last[row] = G step the row is current at, alpha_log[t -
   // log_base] = step size of G step t+1, g_T = G steps taken, p_stale = some row may lag behind g_T
@@ -192,6 +193,10 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
       if (cost < best) { best = cost; splits = sp; }
     }
   }
+  // Many-tile GEMMs are bound by the L2 -> SM fill rate: CTA pairs (256 x 256 tiles over two SMs, each CTA
+  // loading half of B) need 1.5x fewer bytes per flop and keep the accumulator double-buffered.
+  if (c->pair_mode && g.bn == 256 && g.mt == 1 && splits == 1 && M > TC_BM && (c->pair_mode == 2 || tiles >= 148))
+    g.cg = 2;
   g.splits = splits;
   g.ws = c->ws;
   g.cache = &c->tmaps;
@@ -241,6 +246,7 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   ganmf_ctx* c = new ganmf_ctx();
   c->cfg = *cfg;
   if (const char* nf = getenv("GANMF_NO_FUSED_ADAM")) c->fuse_adam = !(nf[0] == '1');   // A/B switch
+  if (const char* pm = getenv("GANMF_PAIR")) c->pair_mode = atoi(pm);                  // A/B switch / tests
   if (const char* nl = getenv("GANMF_NO_LAZY_ADAM")) c->lazy_p = !(nl[0] == '1');       // A/B switch
   if (const char* lc = getenv("GANMF_LAZY_LOG_CAP")) c->log_cap = std::max(1, atoi(lc)); // tests: force log wrap
   c->B = cfg->max_batch; c->W = cfg->width; c->Wp = rup(cfg->width, 32);

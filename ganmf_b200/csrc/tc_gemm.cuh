@@ -81,13 +81,21 @@ struct Epilogue {
 
 constexpr float TC_ADAM_B1 = 0.9f, TC_ADAM_B2 = 0.999f, TC_ADAM_EPS = 1e-8f;
 // The ONE element update every optimiser path shares (fused_adam_kernel, the GEMM epilogue, the lazy
-// user-factor kernels).  Every operation is an explicit round-to-nearest intrinsic, so no path depends on
-// the compiler's contraction choices and a replayed update is bit-identical to the one it stands for.
+// user-factor kernels).  Every operation is an explicit intrinsic, so no path depends on the compiler's
+// contraction choices and a replayed update is bit-identical to the one it stands for.  The square root and
+// the quotient are the hardware approximations (sqrt.approx / div.approx, <= 2 ulp, deterministic): inside the
+// weight-gradient GEMM epilogues the IEEE sequences (~20 extra instructions per parameter) made the optimiser
+// instruction-issue bound; the 2^-22 relative error sits four orders below the stated parity tolerance.
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void adam_elem(float g, float& th, float& m, float& v, float alpha, float reg) {
   const float ge = __fmaf_rn(reg, th, g);
   m = __fmaf_rn(__fsub_rn(ge, m), 1.f - TC_ADAM_B1, m);
   v = __fmaf_rn(__fmaf_rn(ge, ge, -v), 1.f - TC_ADAM_B2, v);
-  th = __fsub_rn(th, __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), TC_ADAM_EPS)));
+  th = __fsub_rn(th, __fdividef(__fmul_rn(m, alpha), __fadd_rn(sqrt_approx(v), TC_ADAM_EPS)));
 }
 
 struct TcGemmArgs {
@@ -153,10 +161,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // tile, two accumulators sharing every B stage) raises the flops per byte fetched from L2 by 1.5x for
 // the long-K GEMMs that are L2-bandwidth bound; it fills the whole TMEM with BN = 256, so those tiles
 // do not double-buffer the accumulator (fine: their epilogue is a small fraction of a long K loop).
-template <int BN, int STAGES, int MT = 1>
+// CG = 2 (a CTA pair = the two SMs of a TPC, tcgen05 cta_group::2): the pair computes ONE 256 x BN tile, each
+// CTA holding its 128 accumulator rows in its own TMEM and only HALF of every B stage in its shared memory
+// (the tensor cores read the peer's half directly).  Per CTA a stage is 16 KB of A + 16 KB of B for the same
+// 128 x 256 x 32 MMA volume that costs 48 KB on a single CTA: the GEMMs with many output tiles are bound by
+// the L2 -> SM fill rate (ncu: ~12 TB/s, the LTS cap), so 1.5x fewer bytes per flop is 1.5x more flops, and
+// unlike MT = 2 the accumulator still double-buffers (256 of the 512 TMEM columns per stage).
+template <int BN, int STAGES, int MT = 1, int CG = 1>
 struct TcSmem {
   static constexpr int A_BYTES = MT * TC_BM * TC_BK * 4;
-  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int B_BYTES = (BN / CG) * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;          // 8 warps x 32 rows x 8 float4 (swizzled)
   static constexpr int EPI_BYTES = 8 * 32 * 32 * 4;
@@ -191,12 +205,20 @@ __device__ __forceinline__ TcUnit tc_unit(int u, int tiles_m, int tiles_n, int m
 // the GEMM's duration.  With the counter, late CTAs simply find less (or no) work.  The last CTA to leave
 // resets the counter pair, so launches need no memset.
 // Two TMEM accumulator stages let the epilogue of unit i overlap the MMAs of unit i+1.
-template <int BN, int STAGES, int MT>
+// EPI = 1 ("lean"): the epilogue without the fused-optimiser, activation and tf32-rounding variants -- the
+// kernel the many-tile GEMMs of the step use; its epilogue is half the code (the full one overflows the
+// instruction cache: ncu attributes 10-17 % of the epilogue warps' stalls to instruction fetch).
+template <int BN, int STAGES, int MT, int CG, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcGemmArgs args) {
-  using S = TcSmem<BN, STAGES, MT>;
-  constexpr int BM = MT * TC_BM;                       // CTA tile rows
+  static_assert(CG == 1 || (CG == 2 && MT == 1), "a CTA pair holds one 128-row sub-tile per CTA");
+  using S = TcSmem<BN, STAGES, MT, CG>;
+  constexpr bool LEAN = EPI == 1;
+  constexpr int BM = MT * TC_BM * CG;                  // rows of a unit's tile (CTA pair: 256)
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // 0 = leader: issues the pair's MMAs
+  const int row_off = (int)rank * TC_BM;               // this CTA's rows inside the tile
+  const int col_off = (int)rank * (BN / CG);           // this CTA's share of the B tile
   constexpr int ACC = (2 * MT * BN <= 512) ? 2 : 1;    // accumulator stages that fit the 512 TMEM columns
   constexpr int ACC_COLS = MT * BN;
   extern __shared__ uint8_t smem_raw[];
@@ -228,7 +250,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int a = 0; a < ACC; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 8);         // one arrival per epilogue warp
+      ptx::mbar_init(&tmem_empty_bar[a], 8 * CG);    // one arrival per epilogue warp (of both CTAs of a pair)
     }
     for (int i = 0; i < TC_SCHED; ++i) {
       ptx::mbar_init(&sched_full[i], 1);
@@ -237,11 +259,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, ACC * ACC_COLS);
-    ptx::tmem_relinquish();
+    if (CG == 2) { ptx::tmem_alloc_pair(tmem_slot, ACC * ACC_COLS); ptx::tmem_relinquish_pair(); }
+    else         { ptx::tmem_alloc(tmem_slot, ACC * ACC_COLS); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync();                    // the peer's barriers are initialised before anyone signals them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -251,9 +274,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t it = 0, si = 0;
       // first unit = blockIdx.x (no atomic in front of the first load; single-wave GEMMs behave exactly like
       // a static grid), every later unit = gridDim.x + counter
+      // (a CTA pair walks units statically: both CTAs must take the same sequence)
       const bool dyn = args.sched != nullptr;
-      const int g = (int)gridDim.x;
-      int u = (int)blockIdx.x;
+      const int g = (int)gridDim.x / CG;
+      int u = (int)blockIdx.x / CG;
       while (true) {
         const int sl = si % TC_SCHED;
         ptx::mbar_wait(&sched_empty[sl], ((si / TC_SCHED) & 1) ^ 1);
@@ -273,22 +297,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* sa = smem + s * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
           const int k0 = kb * TC_BK;
-          ptx::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+          // pair: both CTAs' bytes are counted on the LEADER's full barrier (it alone consumes the stage)
+          const uint32_t fb = CG == 2 ? ptx::mapa(ptx::smem_u32(&full_bar[s]), 0u) : 0u;
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[s], CG * S::STAGE_BYTES);
+          auto ld = [&](uint8_t* dst, const CUtensorMap* map, int c0, int c1) {
+            if (CG == 2) ptx::tma_load_2d_pair(dst, map, fb, c0, c1);
+            else ptx::tma_load_2d(dst, map, &full_bar[s], c0, c1);
+          };
+          const int am = un.m0 + row_off, bn0 = un.n0 + col_off;
           if (!args.a_mn) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)                                 // box {32 k, 128 m}
-              ptx::tma_load_2d(sa + mt * (TC_BM * TC_BK * 4), &map_a, &full_bar[s], k0, un.m0 + mt * TC_BM);
+              ld(sa + mt * (TC_BM * TC_BK * 4), &map_a, k0, am + mt * TC_BM);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 32; ++j)                               // box {32 m, 32 k}
-              ptx::tma_load_2d(sa + j * (TC_BK * 128), &map_a, &full_bar[s], un.m0 + 32 * j, k0);
+            for (int j = 0; j < MT * TC_BM / 32; ++j)                       // box {32 m, 32 k}
+              ld(sa + j * (TC_BK * 128), &map_a, am + 32 * j, k0);
           }
           if (!args.b_mn) {
-            ptx::tma_load_2d(sb, &map_b, &full_bar[s], k0, un.n0);          // box {32 k, BN n}
+            ld(sb, &map_b, k0, bn0);                                        // box {32 k, BN / CG n}
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j)
-              ptx::tma_load_2d(sb + j * (TC_BK * 128), &map_b, &full_bar[s], un.n0 + 32 * j, k0);
+            for (int j = 0; j < BN / CG / 32; ++j)
+              ld(sb + j * (TC_BK * 128), &map_b, bn0 + 32 * j, k0);
           }
         }
         u = u_next;
@@ -314,6 +345,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int u = sched_unit[sl];
         ptx::mbar_arrive(&sched_empty[sl]);
         if (u < 0) break;
+        if (CG == 2 && rank != 0) continue;              // the leader issues the pair's MMAs
         const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN, BM);
         const int kb_begin = un.split * args.kb_per_split;
         const int nkb = min(kb_begin + args.kb_per_split, total_kb) - kb_begin;
@@ -333,13 +365,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)            // the 128-row sub-tiles share the B stage
-              ptx::mma_tf32_ss(tmem_d + mt * BN, da + (uint64_t)(mt * args.a_mtstep + k * args.a_kstep),
-                               db + (uint64_t)(k * args.b_kstep), args.idesc, (i | k) ? 1u : 0u);
+            for (int mt = 0; mt < MT; ++mt) {          // the 128-row sub-tiles share the B stage
+              const uint64_t dak = da + (uint64_t)(mt * args.a_mtstep + k * args.a_kstep);
+              const uint64_t dbk = db + (uint64_t)(k * args.b_kstep);
+              if (CG == 2) ptx::mma_tf32_ss_pair(tmem_d, dak, dbk, args.idesc, (i | k) ? 1u : 0u);
+              else ptx::mma_tf32_ss(tmem_d + mt * BN, dak, dbk, args.idesc, (i | k) ? 1u : 0u);
+            }
           }
-          ptx::mma_commit(&empty_bar[s]);          // frees the smem stage when those MMAs retire
+          // frees the smem stage (in both CTAs of a pair) when those MMAs retire
+          if (CG == 2) ptx::mma_commit_pair(&empty_bar[s], 3);
+          else ptx::mma_commit(&empty_bar[s]);
         }
-        ptx::mma_commit(&tmem_full_bar[acc]);      // accumulator of this unit complete
+        // accumulator of this unit complete (the peer's epilogue warps wait on their own copy of the barrier)
+        if (CG == 2) ptx::mma_commit_pair(&tmem_full_bar[acc], 3);
+        else ptx::mma_commit(&tmem_full_bar[acc]);
       }
     }
   } else {
@@ -376,26 +415,46 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (u < 0) break;
       const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN, BM);
       const uint32_t acc = ui % ACC;
-      const bool interior = vec_all && (un.m0 + BM <= args.M) && (un.n0 + BN <= args.N);
-      const int c_end = (half + 1) * (BN / 2);
+      const bool interior = vec_all && (un.m0 + row_off + MT * TC_BM <= args.M) && (un.n0 + BN <= args.N);
+      // this warp's chunks of the unit: 32 rows x 32 columns each, NCH = MT * BN / 64 of them
+      constexpr int CH = BN / 64, NCH = MT * CH;
+      auto chunk_mw = [&](int j) { return un.m0 + row_off + (j / CH) * TC_BM + q * 32; };
+      auto chunk_c = [&](int j) { return half * (BN / 2) + (j % CH) * 32; };
+      // Addend tile (residual / gradient GEMMs): its loads are issued one chunk AHEAD -- the first chunk's
+      // before the accumulator is even waited for, chunk j+1's row group right after chunk j's has been
+      // consumed -- so the HBM latency (ncu: 30 % of the epilogue warps' time when paid per chunk) hides
+      // under the TMEM read, the transpose and the stores of the chunk in between.
+      const bool pf = interior && use_c1 && !(ep.adam_m && !LEAN);
+      float4 t1[8];
+      auto load_c1 = [&](int j, int itr) {
+        const float* p1 = ep.c1 + (size_t)(chunk_mw(j) + sub_r + itr * 4) * ep.ldc1 + un.n0 + chunk_c(j) + sub_g * 4;
+        t1[itr] = __ldg(reinterpret_cast<const float4*>(p1));
+      };
+      if (pf) {
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) load_c1(0, itr);
+      }
       ptx::mbar_wait(&tmem_full_bar[acc], (ui / ACC) & 1);
       ptx::tc_fence_after();
-      for (int mt = 0; mt < MT; ++mt) {
-      const uint32_t taddr = tmem_base + acc * ACC_COLS + mt * BN + ((uint32_t)(q * 32) << 16);
-      const int mw = un.m0 + mt * TC_BM + q * 32;   // first row of this warp's 32-row slab
-      for (int c = half * (BN / 2); c < c_end; c += 32) {
+      for (int j = 0; j < NCH; ++j) {
+        const int mt = j / CH, c = chunk_c(j);
+        const uint32_t taddr = tmem_base + acc * ACC_COLS + mt * BN + ((uint32_t)(q * 32) << 16);
+        const int mw = chunk_mw(j);                   // first row of this warp's 32-row slab
         uint32_t r[32];
         if (args.dbg_epi < 2) {
           ptx::tmem_ld_32x32(taddr + (uint32_t)c, r);
           ptx::tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
+          for (int jj = 0; jj < 32; ++jj) r[jj] = 0u;
         }
-        if (c + 32 >= c_end && mt == MT - 1) {     // last TMEM read of this warp for this unit
+        if (j == NCH - 1) {                         // last TMEM read of this warp for this unit
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) {
+            if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty_bar[acc]), 0u));
+            else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          }
         }
         const int nb = un.n0 + c;
         if (nb >= args.N || mw >= args.M || args.dbg_epi >= 1) continue;          // warp-uniform
@@ -422,9 +481,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ep.bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
             float* dst = ep.out + (size_t)(mw + sub_r) * ep.ldo + n;
-            if (ep.adam_m) {
+            if (!LEAN && ep.adam_m) {
               // fused Adam on the parameter tile: theta, m, v are read and written in place (24 B/param
-              // instead of 28 + the gradient round trip of a separate optimiser kernel)
+              // instead of 28 + the gradient round trip of a separate optimiser kernel).  (Rotating these
+              // loads half a chunk ahead, as the addend loads are, measured 12 % SLOWER: the 12 loads of a
+              // half chunk issued back to back keep more of HBM busy than loads interleaved with stores.)
               const size_t off0 = (size_t)(mw + sub_r) * ep.ldo + n;
               float l2 = 0.f;
 #pragma unroll
@@ -458,15 +519,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               __syncwarp();
               continue;
             }
-            // the addend loads of the chunk are all issued before any store (the stores may alias them as
-            // far as the compiler knows), so their latency is paid once per chunk, not once per row group
-            float4 t1[8];
-            if (use_c1) {
-              const float* p1 = ep.c1 + (size_t)(mw + sub_r) * ep.ldc1 + n;
-#pragma unroll
-              for (int itr = 0; itr < 8; ++itr)
-                t1[itr] = __ldg(reinterpret_cast<const float4*>(p1 + (size_t)itr * 4 * ep.ldc1));
-            }
+            const bool more = j + 1 < NCH;
 #pragma unroll
             for (int itr = 0; itr < 8; ++itr) {
               const int row = itr * 4 + sub_r;
@@ -479,15 +532,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 o.x = fmaf(ep.beta1, t1[itr].x, o.x); o.y = fmaf(ep.beta1, t1[itr].y, o.y);
                 o.z = fmaf(ep.beta1, t1[itr].z, o.z); o.w = fmaf(ep.beta1, t1[itr].w, o.w);
               }
-              if (ep.act != ACT_LINEAR) {
+              if (!LEAN && ep.act != ACT_LINEAR) {
                 o.x = act_fwd(ep.act, o.x); o.y = act_fwd(ep.act, o.y);
                 o.z = act_fwd(ep.act, o.z); o.w = act_fwd(ep.act, o.w);
               }
-              if (ep.round_out) {
+              if (!LEAN && ep.round_out) {
                 o.x = ptx::round_tf32(o.x); o.y = ptx::round_tf32(o.y);
                 o.z = ptx::round_tf32(o.z); o.w = ptx::round_tf32(o.w);
               }
               *reinterpret_cast<float4*>(dst + (size_t)itr * 4 * ep.ldo) = o;
+              if (use_c1 && more) load_c1(j + 1, itr);         // next chunk's row group, a whole chunk ahead
               const float sq = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
               if (lower) sq1 += sq; else sq0 += sq;
             }
@@ -514,7 +568,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         __syncwarp();                               // slab is reused by the next chunk
       }
-      }
     }
     if (!partial && (ep.sumsq2 || ep.adam_l2)) {
 #pragma unroll
@@ -534,10 +587,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync();                    // the leader's MMAs read the peer's shared memory until the end
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, ACC * ACC_COLS);
+    if (CG == 2) ptx::tmem_dealloc_pair(tmem_base, ACC * ACC_COLS);
+    else ptx::tmem_dealloc(tmem_base, ACC * ACC_COLS);
   }
 }
 
@@ -645,6 +700,7 @@ struct TcGemmCall {
   float* ws = nullptr;     // >= splits * M * roundup(N,4) floats
   int bn = 128;            // 128 or 256
   int mt = 1;              // 1: 128-row CTA tiles; 2: 256-row CTA tiles (needs bn == 256)
+  int cg = 1;              // 2: CTA pairs (cta_group::2) on 256 x 256 tiles (needs bn == 256, mt == 1)
   // TFLOAT32 makes TMA round fp32 -> tf32 to nearest on the way into shared memory
   // (measured: FLOAT32 maps leave the bits alone and the MMA then truncates).
   int tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
@@ -654,7 +710,7 @@ struct TcGemmCall {
   int max_ctas = 0;        // > 0: cap on the persistent grid (SMs left free for a concurrent collective)
 };
 
-inline uint32_t make_idesc_tf32(int bn, int a_mn, int b_mn) {
+inline uint32_t make_idesc_tf32(int bn, int a_mn, int b_mn, int m = TC_BM) {
   // cute::UMMA::InstrDescriptor: c_format[4,6)=1 (F32) a_format[7,10)=2 (TF32)
   // b_format[10,13)=2 a_major bit15 b_major bit16 n_dim[17,23)=N>>3 m_dim[24,29)=M>>4
   uint32_t d = 0;
@@ -664,7 +720,7 @@ inline uint32_t make_idesc_tf32(int bn, int a_mn, int b_mn) {
   d |= (uint32_t)(a_mn ? 1 : 0) << 15;
   d |= (uint32_t)(b_mn ? 1 : 0) << 16;
   d |= (uint32_t)(bn >> 3) << 17;
-  d |= (uint32_t)(TC_BM >> 4) << 24;
+  d |= (uint32_t)(m >> 4) << 24;
   return d;
 }
 
@@ -687,13 +743,13 @@ inline cudaError_t tc_sched_slot(unsigned int** out) {
   return cudaSuccess;
 }
 
-template <int BN, int STAGES, int MT>
+template <int BN, int STAGES, int MT, int CG, int EPI>
 inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const CUtensorMap& ma,
                                     const CUtensorMap& mb, int splits, cudaStream_t stream) {
-  using S = TcSmem<BN, STAGES, MT>;
+  using S = TcSmem<BN, STAGES, MT, CG>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, MT>,
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, MT, CG, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -705,8 +761,24 @@ inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  const int units = ((c.N + BN - 1) / BN) * ((c.M + MT * TC_BM - 1) / (MT * TC_BM)) * splits;
+  const int units = ((c.N + BN - 1) / BN) * ((c.M + CG * MT * TC_BM - 1) / (CG * MT * TC_BM)) * splits;
   const int sms = (c.max_ctas > 0 && c.max_ctas < num_sms) ? c.max_ctas : num_sms;
+  if (CG == 2) {
+    // one cluster of two CTAs per unit in flight; units are walked statically (cluster id + i * #clusters)
+    const int pairs = units < sms / 2 ? units : sms / 2;
+    args.sched = nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, STAGES, MT, CG, EPI>, ma, mb, args);
+  }
   const int grid = units < sms ? units : sms;
   static int static_sched = -1;          // GANMF_STATIC_SCHED=1: A/B switch, units blockIdx.x + i*gridDim.x
   if (static_sched < 0) {
@@ -718,7 +790,7 @@ inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const
     cudaError_t es = tc_sched_slot(&args.sched);
     if (es != cudaSuccess) return es;
   }
-  tc_gemm_kernel<BN, STAGES, MT><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, args);
+  tc_gemm_kernel<BN, STAGES, MT, CG, EPI><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, args);
   return cudaGetLastError();
 }
 
@@ -729,6 +801,7 @@ inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(c.A) & 15) || (reinterpret_cast<uintptr_t>(c.B) & 15))
     return cudaErrorInvalidValue;
   const int bn = c.bn == 256 ? 256 : 128;
+  const int cg = (c.cg == 2 && bn == 256 && c.mt == 1) ? 2 : 1;
   CUtensorMap ma, mb;
   int rc;
   const int mn_swz = c.dbg_mn_swizzle ? c.dbg_mn_swizzle : (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
@@ -736,7 +809,7 @@ inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   if (!c.a_mn) rc = make_tmap_2d(&ma, c.A, c.M, c.K, c.lda, TC_BK, TC_BM, c.tmap_dtype, k_swz, c.cache);
   else         rc = make_tmap_2d(&ma, c.A, c.K, c.M, c.lda, 32, TC_BK, c.tmap_dtype, mn_swz, c.cache);
   if (rc) return cudaErrorUnknown;
-  if (!c.b_mn) rc = make_tmap_2d(&mb, c.B, c.N, c.K, c.ldb, TC_BK, bn, c.tmap_dtype, k_swz, c.cache);
+  if (!c.b_mn) rc = make_tmap_2d(&mb, c.B, c.N, c.K, c.ldb, TC_BK, bn / cg, c.tmap_dtype, k_swz, c.cache);
   else         rc = make_tmap_2d(&mb, c.B, c.K, c.N, c.ldb, 32, TC_BK, c.tmap_dtype, mn_swz, c.cache);
   if (rc) return cudaErrorUnknown;
 
@@ -773,13 +846,19 @@ inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   args.a_mtstep = c.a_mn ? ((TC_BM / 32) * TC_BK * 128) >> 4 : (TC_BM * TC_BK * 4) >> 4;
   args.a_kstep = c.a_mn ? (1024 >> 4) : (TC_UMMA_K * 4) >> 4;
   args.b_kstep = c.b_mn ? (1024 >> 4) : (TC_UMMA_K * 4) >> 4;
-  args.idesc = make_idesc_tf32(bn, c.a_mn, c.b_mn);
+  args.idesc = make_idesc_tf32(bn, c.a_mn, c.b_mn, cg * TC_BM);
   args.ep = c.ep;
 
   cudaError_t e;
-  if (bn == 256 && c.mt == 2) e = tc_gemm_launch_t<256, 3, 2>(c, args, ma, mb, splits, stream);
-  else if (bn == 256)         e = tc_gemm_launch_t<256, 4, 1>(c, args, ma, mb, splits, stream);
-  else                        e = tc_gemm_launch_t<128, 6, 1>(c, args, ma, mb, splits, stream);
+  const bool lean = !c.ep.adam_m && c.ep.act == ACT_LINEAR && !c.ep.round_out;
+#define TC_LAUNCH(BN_, ST_, MT_, CG_)                                                            \
+  (lean ? tc_gemm_launch_t<BN_, ST_, MT_, CG_, 1>(c, args, ma, mb, splits, stream)               \
+        : tc_gemm_launch_t<BN_, ST_, MT_, CG_, 0>(c, args, ma, mb, splits, stream))
+  if (cg == 2)                     e = TC_LAUNCH(256, 6, 1, 2);
+  else if (bn == 256 && c.mt == 2) e = TC_LAUNCH(256, 3, 2, 1);
+  else if (bn == 256)              e = TC_LAUNCH(256, 4, 1, 1);
+  else                             e = TC_LAUNCH(128, 6, 1, 1);
+#undef TC_LAUNCH
   if (e != cudaSuccess) return e;
   if (splits > 1) {
     dim3 rb(256), rg((c.N + 255) / 256, c.M);

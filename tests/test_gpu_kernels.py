@@ -18,6 +18,25 @@ def eng():
     e.close()
 
 
+@pytest.fixture(scope="module")
+def eng_pair():
+    """GANMF_PAIR=2: every tcgen05 GEMM that legally can runs on CTA pairs (cta_group::2, 256 x 256 tiles)."""
+    import os
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    old = os.environ.get("GANMF_PAIR")
+    os.environ["GANMF_PAIR"] = "2"
+    try:
+        e = Engine(L.KIND_GANMF, 64, 96, 8, emb_dim=8, max_batch=16)
+    finally:
+        if old is None:
+            del os.environ["GANMF_PAIR"]
+        else:
+            os.environ["GANMF_PAIR"] = old
+    yield e
+    e.close()
+
+
 def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
@@ -53,6 +72,36 @@ def test_gemm_paths_match_fp64(eng, a_mn, b_mn, shape):
         scale = np.sqrt(K)          # |A||B| row norms ~ sqrt(K)
         assert np.max(np.abs(got - want)) / scale < tol, (path, np.max(np.abs(got - want)) / scale)
         assert np.all(out.cpu().numpy()[:, N:] == 0)      # padding columns untouched
+
+
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (300, 700, 260), (1000, 520, 100), (129, 300, 40), (2048, 3000, 96)])
+def test_gemm_cta_pairs_match_fp64(eng_pair, a_mn, b_mn, shape):
+    """The cta_group::2 tiles (two SMs per 256 x 256 tile, B split between them): ragged M / N / K tails, tiles
+    whose second CTA is entirely out of range, several tiles per pair, all operand major-ness combinations."""
+    from ganmf_b200 import _lib as L
+    M, N, K = shape
+    rs = np.random.RandomState(M + N + K + a_mn * 2 + b_mn)
+    A = rs.standard_normal((M, K)).astype(np.float32)
+    B = rs.standard_normal((N, K)).astype(np.float32)
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+
+    def padded(x):
+        out = np.full((x.shape[0], rup(x.shape[1])), 1e30, dtype=np.float32)
+        out[:, :x.shape[1]] = x
+        return out
+    As = padded(A.T if a_mn else A)
+    Bs = padded(B.T if b_mn else B)
+    dA, dB = dev(As), dev(Bs)
+    ldo = rup(N)
+    out = torch.zeros((M, ldo), dtype=torch.float32, device="cuda")
+    for _ in range(2):                                     # twice: barrier phases / TMEM hand-back between launches
+        L.check(eng_pair.lib.ganmf_k_gemm(eng_pair.ctx, dA.data_ptr(), As.shape[1], a_mn, dB.data_ptr(), Bs.shape[1],
+                                          b_mn, M, N, K, out.data_ptr(), ldo, L.GEMM_TC))
+    got = out.cpu().numpy()[:, :N].astype(np.float64)
+    assert np.max(np.abs(got - want)) / np.sqrt(K) < 2e-3
+    assert np.all(out.cpu().numpy()[:, N:] == 0)
 
 
 def test_csr_gather_dense_matches_scipy():
