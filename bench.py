@@ -116,12 +116,15 @@ class ClockSampler(object):
                 "reasons": reasons, "samples": len(self.sm), "source": self.src}
 
 
-def gemm_algorithmic_bytes(c):
-    """Operand + output bytes (each read/written once) of the 13 tensor-core GEMMs of one D+G step pair."""
+def gemm_algorithmic_bytes(c, fused_adam=False):
+    """Operand + output bytes (each read/written once) of the 13 tensor-core GEMMs of one D+G step pair.
+    fused_adam (single GPU): the dWd / dWe epilogues do not write the gradient but read and write theta, m, v
+    in place (24 B per parameter instead of 4)."""
     B, I, k, E = c["B"], c["items"], c["k"], c["E"]
     f = 4.0
     g = lambda M, N, K, extra=0: f * (M * K + N * K + M * N * (1 + extra))
-    d = g(B, I, k) + g(2 * B, E, I) + g(2 * B, I, E, 1) + g(E, I, 2 * B) + g(2 * B, E, I) + g(I, E, 2 * B)
+    wg = 5 if fused_adam else 0                   # 6 tensors moved instead of 1
+    d = g(B, I, k) + g(2 * B, E, I) + g(2 * B, I, E, 1) + g(E, I, 2 * B, wg) + g(2 * B, E, I) + g(I, E, 2 * B, wg)
     gs = g(B, I, k) + g(2 * B, E, I) + g(B, I, E, 1) + g(B, E, I, 2) + g(B, I, E, 1) + g(I, k, B) + g(B, k, I)
     return d + gs
 
@@ -268,12 +271,17 @@ def main():
     barrier()
     launches0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_range = os.environ.get("GANMF_BENCH_PROFILER_RANGE") == "1"     # ncu --profile-from-start off: timed steps only
     with ClockSampler(local_rank) as clk:
         barrier()
+        if prof_range:
+            torch.cuda.profiler.start()
         e0.record()
         run_steps(W, K)
         e1.record()
         barrier()
+        if prof_range:
+            torch.cuda.profiler.stop()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count() - launches0
     value = world * B * K / (ms * 1e-3)
@@ -312,9 +320,9 @@ def main():
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["dram_bytes_per_launch_mean"], "profiles/r01_tc_gemm_dram_traffic.json: " + tj["note"]
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"kernel": "tc_gemm_kernel (tcgen05 kind::tf32, TMA, TMEM)", "bound": "tensor", "achieved": achieved,
+    roofline = {"kernel": "tc_gemm_kernel (tcgen05 kind::tf32, TMA, TMEM; CTA pairs cta_group::2 on the many-tile GEMMs)", "bound": "tensor", "achieved": achieved,
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch_mean": gemm_algorithmic_bytes(c) / 13.0,
+                "algorithmic_bytes_per_launch_mean": gemm_algorithmic_bytes(c, fused_adam=(world == 1)) / 13.0,
                 "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json); kind::tf32 issues at half the "
                 "bf16 rate, so frac <= 0.5 by construction", "frac_of_tf32_rate": 2 * achieved / pk["tf_sust"],
                 "achieved_excl_fused_adam_gemms": pure_flops / (pure_ms * 1e-3) / 1e12 if pure_ms > 0 else None,

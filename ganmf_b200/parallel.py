@@ -17,7 +17,9 @@ import numpy as np
 # SMs set aside for NCCL while a collective overlaps the GEMMs, and the matching cap on NCCL's CTAs.  Measured
 # at N=2 on cfg4 (profiles/r01_dp_overlap_ab_n2.txt): no reservation 2.73 ms/step, 16: 2.99, 24: 2.79,
 # 32: 2.59, 40: 2.57 -- below 32 CTAs NCCL's own bandwidth drops (reduce-scatter of 105 MB: 0.155 -> 0.206 ms
-# at 16), without a reservation its kernels wait for the persistent GEMM to drain.
+# at 16), without a reservation its kernels wait for the persistent GEMM to drain.  At N=8 the collectives run
+# through the switch (NVLS) and do not compete for SMs: 2.722 ms with the reservation, 2.701 without, so it is
+# applied to two-rank groups only (GANMF_DP_RESERVE_SMS overrides).
 NCCL_CTAS = 32
 
 
@@ -74,7 +76,7 @@ class DataParallelTrainer(object):
                 self._ranges = ([r * ce, ne + r * cd], [ce, cd])
                 self._rank = r
                 # SMs the GEMMs leave to NCCL while a collective is in flight (0 = no reservation)
-                self._reserve = int(os.environ.get("GANMF_DP_RESERVE_SMS", str(NCCL_CTAS)))
+                self._reserve = int(os.environ.get("GANMF_DP_RESERVE_SMS", str(NCCL_CTAS if world_size == 2 else 0)))
 
     def _cap(self, on):
         if getattr(self, "_reserve", 0) > 0:
