@@ -392,7 +392,7 @@ def main():
             "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": c["name"], "state": "after one full untimed epoch (all 138000 rows hold Adam moments)",
                        "l2": "per-step working set (weights 221 MB + activations) exceeds the "
-                       "126 MB L2", "parallelism": "dp%d over users; D and item factors replicated, NCCL allreduce" %
+                       "126 MB L2", "parallelism": "dp%d over users; D and item factors replicated, NCCL reduce-scatter / sharded Adam / all-gather" %
                        world if world > 1 else "single GPU"},
             "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e, "roofline": roofline,
             "eval": eval_info, "hbm_kernels": hbm_kernels,

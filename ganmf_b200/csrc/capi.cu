@@ -139,10 +139,6 @@ static int mat_alloc(Mat* m, int rows, int cols) {
   m->rows = rows; m->cols = cols; m->ld = rup(cols, 32);
   return dalloc(&m->p, m->elems());
 }
-static Mat mat_view(float* p, int rows, int cols) {
-  Mat m; m.p = p; m.rows = rows; m.cols = cols; m.ld = rup(cols, 32);
-  return m;
-}
 
 // ------------------------------------------------------------------------------ GEMM dispatch
 // out[M,N] = epilogue(A . B^T), A logical [M,K], B logical [N,K]; *_mn = stored transposed.

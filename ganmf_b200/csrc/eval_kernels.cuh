@@ -268,16 +268,14 @@ __global__ void user_metrics_kernel(const int* __restrict__ topk_idx, int K, con
   o[MC_COVERED] = L > 0 ? 1.0 : 0.0;
   // MAP: is_rel * cumsum(f32) / (1 + arange) -> float64 terms, np.sum, / min(T, L)
   if (L) {
-    int cum = 0;
-    // np_sum evaluates term(i) with i increasing exactly once each, so a running count is safe
-    // only if we precompute it: use popcount of the mask prefix instead.
+    // np_sum does not evaluate term(i) in increasing i, so the cumulative hit count comes from a popcount of
+    // the mask prefix, not from a running counter
     auto cum_at = [&](int j) -> int {
       int s = 0;
       for (int w = 0; w < (j >> 5); ++w) s += __popc(hm[w]);
       s += __popc(hm[j >> 5] & (0xFFFFFFFFu >> (31 - (j & 31))));
       return s;
     };
-    (void)cum;
     const double ap = np_sum<double>(L, [&](int j) -> double {
       return hit(j) ? (double)(float)cum_at(j) / (double)(j + 1) : 0.0;
     });

@@ -70,6 +70,22 @@ def test_ganmf_100_steps_parity(path_name, hp):
         assert rel_err(got[n], want[n]) <= REL, (n, rel_err(got[n], want[n]))
 
 
+@pytest.mark.parametrize("hp", [HP, dict(HP, m=0.05, alpha=0.3)])                  # gate open / closed
+def test_ganmf_steps_parity_on_cta_pairs(monkeypatch, hp):
+    """GANMF_PAIR=2 forces every legal tcgen05 GEMM onto CTA pairs (cta_group::2), which the benchmark shapes
+    use for all many-tile GEMMs: residual epilogue with prefetched addend + bias + energy sums (2B=320 rows: the
+    second CTA of the last pair tile is partly out of range; 517 columns: ragged last tile), the fused-Adam
+    epilogues of dWd / dWe, the plain generator GEMMs.  Same tolerance as the single-CTA paths."""
+    from ganmf_b200 import _lib as L
+    monkeypatch.setenv("GANMF_PAIR", "2")
+    dl, gl, odl, ogl, got, want = run_ganmf(600, 517, 24, 300, 160, 8, hp, L.GEMM_TC)
+    assert len(dl) == 32 and len(gl) == 32
+    np.testing.assert_allclose(dl, odl, rtol=REL)
+    np.testing.assert_allclose(gl, ogl, rtol=REL)
+    for n in want:
+        assert rel_err(got[n], want[n]) <= REL, (n, rel_err(got[n], want[n]))
+
+
 def test_ganmf_ml1m_shape_steps_parity():
     """cfg1 shape (GANMF-u ML-1M: I=3706, k=250, E=992, B=64) on the committed split, best params."""
     from ganmf_b200 import _lib as L
@@ -108,6 +124,38 @@ def test_ganmf_ml1m_shape_steps_parity():
     for n in orc.p:
         assert rel_err(got[n], orc.p[n]) <= REL, (n, rel_err(got[n], orc.p[n]))
     eng.close()
+
+
+@pytest.mark.parametrize("act", ["tanh", "relu"])
+def test_disganmf_cta_pairs_equal_single_ctas(monkeypatch, act):
+    """Wide DisGANMF layers (300 nodes, 2B = 192 rows) with every legal GEMM forced onto CTA pairs (activation
+    epilogue, rank-1 id term, weight gradients under cta_group::2) against the same run on single-CTA tiles:
+    the two tilings accumulate each output element over the same K blocks in the same order, so losses and
+    weights must agree to fp32 round-off (this wide net at d_lr = 1e-3 drifts ~1 % from the fp32 oracle under
+    TF32 on EITHER tiling, so the oracle comparison lives in the narrower configurations below)."""
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    n_rows, width, k, B, layers, nodes = 400, 310, 12, 96, 2, 300
+    urm = make_urm(n_rows, width, 0.06, 3)
+    p0 = to.init_disganmf_params(n_rows, width, k, layers, nodes, seed=9)
+    hp = dict(d_lr=1e-3, g_lr=2e-4, d_reg=1e-5, g_reg=1e-4, alpha=0.3)
+    outs = []
+    for pair in ("2", "0"):
+        monkeypatch.setenv("GANMF_PAIR", pair)
+        eng = Engine(L.KIND_DISGANMF, n_rows, width, k, d_layers=layers, d_nodes=nodes, d_act=act, max_batch=B)
+        eng.set_csr(L.CSR_TRAIN, urm)
+        eng.set_params(p0)
+        eng.reset_optimizers()
+        losses = []
+        for _, batches in to.epoch_index_stream(n_rows, B, 3, seed=1337):
+            dl, gl = eng.train_epoch(np.concatenate(batches), B, 1, 1, hp["d_lr"], hp["g_lr"], hp["d_reg"], hp["g_reg"],
+                                     1.0, hp["alpha"])
+            losses += list(dl) + list(gl)
+        outs.append((np.array(losses), eng.get_params()))
+        eng.close()
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=2e-5)
+    for n in outs[0][1]:
+        assert rel_err(outs[0][1][n], outs[1][1][n]) < 2e-5, n
 
 
 @pytest.mark.parametrize("act,layers,nodes", [("linear", 1, 4), ("tanh", 2, 48), ("relu", 3, 33), ("sigmoid", 2, 130)])
