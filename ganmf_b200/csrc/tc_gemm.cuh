@@ -485,7 +485,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               // fused Adam on the parameter tile: theta, m, v are read and written in place (24 B/param
               // instead of 28 + the gradient round trip of a separate optimiser kernel).  (Rotating these
               // loads half a chunk ahead, as the addend loads are, measured 12 % SLOWER: the 12 loads of a
-              // half chunk issued back to back keep more of HBM busy than loads interleaved with stores.)
+              // half chunk issued back to back keep more of HBM busy than loads interleaved with stores.
+              // Pulling the next chunk's lines into L2 with prefetch.global.L2 made no measurable difference.)
               const size_t off0 = (size_t)(mw + sub_r) * ep.ldo + n;
               float l2 = 0.f;
 #pragma unroll
