@@ -102,6 +102,7 @@ struct ganmf_ctx {
   long long launches = 0;
   int ev_total = 0, ev_done = 0, ev_ncut = 0, ev_K = 0;     // streaming evaluation (ganmf_eval_begin..end)
   int last_ids_offset = 0;
+  int last_n_global = 0;      // DisGANMF: rows of the global minibatch of the pending D update
   float last_alpha_d = 0.f;
   int gemm_sm_cap = 0;        // > 0: persistent GEMM grids leave SMs free (ganmf_set_gemm_sms)
   int pair_mode = 1;          // CTA-pair (cta_group::2) GEMM tiles: 0 = never, 1 = GEMMs with >= 148 tiles, 2 = whenever legal
@@ -722,6 +723,11 @@ static int ganmf_d_backward_apply_fused(ganmf_ctx* c, int B, int n_global, float
 
 static int d_apply_impl(ganmf_ctx* c, float lr, float reg, int loss_slot) {
   if (loss_slot < 0 || loss_slot >= c->losses_cap) return fail("loss slot out of range");
+  if (c->cfg.kind == GANMF_KIND_DISGANMF) {
+    dis_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, 0, 0.f, (double)c->last_n_global, 1.0);
+    CU(cudaGetLastError());
+    c->launches++;
+  }
   RC(adam_group(c, 0, c->n_d, adam_alpha(c, 0, lr), reg, -1));
   finalize_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, reg, c->losses, loss_slot);
   CU(cudaGetLastError());
@@ -832,10 +838,9 @@ static int g_apply_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float
 static int dis_forward(ganmf_ctx* c, int ids_offset, int B) {
   const int L = c->cfg.d_layers, H = c->cfg.d_nodes, act = c->cfg.d_act;
   const int* ids = c->ids + ids_offset;
-  ids_to_float_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(ids, c->idf, B);
-  ids_to_float_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(ids, c->idf + B, B);
+  ids_to_float_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(ids, c->idf, B, c->cfg.row_id_offset);
+  ids_to_float_kernel<<<(B + 127) / 128, 128, 0, c->st>>>(ids, c->idf + B, B, c->cfg.row_id_offset);
   CU(cudaGetLastError());
-  if (c->cfg.row_id_offset != 0) return fail("row_id_offset for DisGANMF shards is not wired yet");
   c->launches += 2;
   for (int l = 0; l < L; ++l) {
     Param& Wl = c->params[2 * l];
@@ -921,21 +926,23 @@ static int dis_d_forward_impl(ganmf_ctx* c, int ids_offset, int B) {
   CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
   return dis_forward(c, ids_offset, B);
 }
+// (the BCE sums are formed here; the reported loss is assembled in d_apply_impl, after a data-parallel caller
+//  has summed the step scalars over ranks -- no gradient depends on them)
 static int dis_d_backward_impl(ganmf_ctx* c, int B, int n_global) {
-  if (n_global != B) return fail("DisGANMF data-parallel normalisation is not wired yet");
-  bce_kernel<<<std::max(1, std::min(64, (2 * B + 255) / 256)), 256, 0, c->st>>>(c->out2, c->dout2, B, 0, c->sc);
-  dis_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, 0, 0.f, (double)n_global, 1.0);
+  bce_kernel<<<std::max(1, std::min(64, (2 * B + 255) / 256)), 256, 0, c->st>>>(c->out2, c->dout2, B, 0, c->sc,
+                                                                              (float)n_global);
   CU(cudaGetLastError());
-  c->launches += 2;
+  c->last_n_global = n_global;
+  c->launches += 1;
   return dis_backward(c, B, true, false, false);
 }
 static int dis_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float alpha) {
-  if (n_global != B) return fail("DisGANMF data-parallel normalisation is not wired yet");
   const int L = c->cfg.d_layers, H = c->cfg.d_nodes;
   RC(forward_generator(c, ids_offset, B));
   CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
   RC(dis_forward(c, ids_offset, B));
-  bce_kernel<<<std::max(1, std::min(64, (2 * B + 255) / 256)), 256, 0, c->st>>>(c->out2, c->dout2, B, 1, c->sc);
+  bce_kernel<<<std::max(1, std::min(64, (2 * B + 255) / 256)), 256, 0, c->st>>>(c->out2, c->dout2, B, 1, c->sc,
+                                                                              (float)n_global);
   const Mat& ft = c->hs[L - 1];
   sqdiff_kernel<<<std::min(B, 296), 256, 0, c->st>>>(ft.p, ft.row(B), B, H, ft.ld, &c->sc->fm);
   CU(cudaGetLastError());

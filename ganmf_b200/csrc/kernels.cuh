@@ -92,9 +92,10 @@ __global__ void split3_rows_kernel(const float* __restrict__ src, int ld_src, co
 }
 
 // first column of the DisGANMF discriminator input: float(row id)  (DisGANMF.py:110-111)
-__global__ void ids_to_float_kernel(const int* __restrict__ ids, float* __restrict__ out, int B) {
+// (ids are LOCAL rows of this GPU's shard; id_offset = global id of local row 0)
+__global__ void ids_to_float_kernel(const int* __restrict__ ids, float* __restrict__ out, int B, int id_offset) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B) out[i] = (float)ids[i];
+  if (i < B) out[i] = (float)(ids[i] + id_offset);
 }
 
 __global__ void set_slots_kernel(int* __restrict__ slot, const int* __restrict__ ids, int B, int reset) {
@@ -423,20 +424,21 @@ __global__ void axpby_kernel(const float* X, const float* Y, float* Z, int M, in
 }
 
 // DisGANMF output losses and their gradients (DisGANMF.py:114-117).
-//   out2 = [out_r (B) ; out_f (B)] logits.  mode 0 (D step): d_r = -sigmoid(-o)/B, d_f = sigmoid(o)/B
-//   mode 1 (G step): only the fake half gets d_f = sigmoid(o)/B (real half set to 0).
+//   out2 = [out_r (B) ; out_f (B)] logits.  mode 0 (D step): d_r = -sigmoid(-o)/Bg, d_f = sigmoid(o)/Bg
+//   mode 1 (G step): only the fake half gets d_f = sigmoid(o)/Bg (real half set to 0).
+//   Bg = rows of the whole (all-GPU) minibatch: the losses are means over it.
 __device__ __forceinline__ float softplusf(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
 __global__ void bce_kernel(const float* __restrict__ out2, float* __restrict__ dout2, int B, int mode,
-                           StepScalars* s) {
+                           StepScalars* s, float Bg) {
   float lr = 0.f, lf = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * B; i += gridDim.x * blockDim.x) {
     const float o = out2[i];
     if (i < B) {
       lr += softplusf(-o);
-      dout2[i] = mode == 0 ? -(1.f / (1.f + expf(o))) / (float)B : 0.f;
+      dout2[i] = mode == 0 ? -(1.f / (1.f + expf(o))) / Bg : 0.f;
     } else {
       lf += softplusf(o);
-      dout2[i] = (1.f / (1.f + expf(-o))) / (float)B;
+      dout2[i] = (1.f / (1.f + expf(-o))) / Bg;
     }
   }
   lr = warp_sum(lr);

@@ -139,6 +139,8 @@ class DataParallelTrainer(object):
         else:
             self.eng.d_backward(B, n_global, m_hinge)
             self._sum(self.d_grads)
+            if self.eng.cfg.kind != 0:
+                self._sum(self.scalars)       # DisGANMF forms its loss sums in the backward (no gradient needs them)
         self.eng.d_apply(lr, reg, loss_slot)
 
     def g_step(self, ids_offset, B, lr, reg, recon_coefficient, loss_slot):
