@@ -140,6 +140,25 @@ def use_all_host_threads():
     return n
 
 
+def cpu_eval_baseline(c, n_users=768):
+    """The reference's evaluation path on the host: NumPy P[u].V^T scorer + the oracle port of
+    BaseRecommender.recommend / EvaluatorHoldout (per-user Python loop, as in the reference), top-10."""
+    from oracle import eval_oracle as eo
+    rs = np.random.RandomState(7)
+    train = synthetic_urm(n_users, c["items"], c["density"], 99)
+    test = synthetic_urm(n_users, c["items"], c["density"] / 4, 100)
+    test = sps.csr_matrix(test - test.multiply(train))
+    test.eliminate_zeros()
+    lim = np.sqrt(6.0 / (c["items"] + c["k"]))
+    P = rs.uniform(-lim, lim, (n_users, c["k"])).astype(np.float32)
+    V = rs.uniform(-lim, lim, (c["items"], c["k"])).astype(np.float32)
+    t0 = time.perf_counter()
+    _, n_eval = eo.evaluate(lambda u: P[u] @ V.T, train, test, [10], promotion="legacy")
+    dt = time.perf_counter() - t0
+    return {"value": n_eval / dt, "unit": "users/s", "sample": "%d users x %d items, cutoff 10 (NumPy scorer + oracle "
+            "port of recommend()/EvaluatorHoldout: single-threaded per-user loop as in the reference)" % (n_eval, c["items"])}
+
+
 def flops_per_row(c):
     return c["items"] * (8 * c["k"] + 30 * c["E"])          # SURVEY.md section 8(d)
 
@@ -180,7 +199,8 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": c["name"]},
             "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "eval": dict(cpu_eval_baseline(c), metric="top-10 eval users/s (score -> seen mask -> top-10 -> metric sums)")}
     print(json.dumps(line))
     return 0
 
@@ -474,7 +494,8 @@ def cpu_baseline(c):
     dt = time.perf_counter() - t0
     return {"value": B * n / dt, "unit": "rows/s", "cores": cores, "kind": "port",
             "sample": "%d D+G steps of B=%d rows, 27000 items, k=250, E=1024 (NumPy/BLAS, all host threads; "
-                      "user-factor table cut to %d rows)" % (n, B, n_users)}
+                      "user-factor table cut to %d rows)" % (n, B, n_users),
+            "eval": cpu_eval_baseline(c)}
 
 
 if __name__ == "__main__":
