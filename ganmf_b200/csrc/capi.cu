@@ -510,6 +510,7 @@ __global__ void glorot_kernel(float* w, int rows, int cols, int ld, float lim, u
 }
 int ganmf_init_params(ganmf_ctx* c, uint64_t seed) {
   if (!c) return fail("null ctx");
+  c->p_stale = false;                     // every tensor and moment is replaced: nothing deferred survives
   int i = 0;
   for (auto& p : c->params) {
     CU(cudaMemsetAsync(p.w.p, 0, p.w.elems() * 4, c->st));
@@ -526,7 +527,7 @@ int ganmf_init_params(ganmf_ctx* c, uint64_t seed) {
 }
 int ganmf_reset_optimizers(ganmf_ctx* c) {
   if (!c) return fail("null ctx");
-  c->p_stale = false;                     // the moments are zeroed: nothing deferred survives
+  RC(p_flush(c));                         // deferred steps still use the OLD moments: apply them before zeroing
   c->g_T = 0; c->log_base = 0;
   CU(cudaMemsetAsync(c->p_last, 0, (size_t)c->cfg.n_rows * 4, c->st));
   CU(cudaMemsetAsync(c->d_slab + c->d_elems, 0, 3 * c->d_elems * 4, c->st));   // m, v, grad

@@ -271,6 +271,8 @@ def _run_lazy_ab(monkeypatch, no_lazy, log_cap=None, kind="ganmf"):
             out.append(eng.score(users))            # reads the user factors mid-training
         if ep == 7:
             eng.snapshot()
+        if ep == 10:
+            eng.reset_optimizers()                  # moments zeroed: steps still deferred must land first
         if ep == 12:
             eng.restore()                           # theta replaced, moments kept
         if ep == 15:                                # a step with g_reg != 0 takes the dense path
