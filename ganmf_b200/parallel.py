@@ -63,6 +63,8 @@ class DataParallelTrainer(object):
                                                      buffers["step_scalars"])
         self.d_dec, self.d_enc = buffers.get("d_grads_dec"), buffers.get("d_grads_enc")
         self.p_dec, self.p_enc = buffers.get("d_params_dec"), buffers.get("d_params_enc")
+        if engine.cfg.kind == 0 and None not in (self.d_dec, self.d_enc, self.p_dec, self.p_enc):
+            self.overlap = True                      # (also for a stand-in engine that hands in all four halves)
         if self.overlap and self.p_dec is not None:
             # reduce-scatter -> Adam on this rank's 1/N of every half -> all-gather of the parameters:
             # same bytes on the wire as an all-reduce, but the (HBM-bound) optimiser work is divided by N
