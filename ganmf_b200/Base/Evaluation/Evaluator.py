@@ -83,10 +83,21 @@ class EvaluatorHoldout(Evaluator):
     # ------------------------------------------------------------------------------------------
     def _device_sums(self, recommender_object, users):
         """(sums[n_cut, MC_NCOL], counts[n_cut, n_items]) over `users` in ascending order."""
-        if self.ignore_items_flag:
-            raise NotImplementedError("ignore_items is outside the GANMF hot path (Evaluator.py:369-370)")
         eng = getattr(recommender_object, "_engine", None)
         URM_train = recommender_object.get_URM_train()
+        block = min(1000, max(1, int(1e8 / self.n_items)))             # Evaluator.py:238
+        score_fn = lambda u: recommender_object._compute_item_score(u)
+        if self.ignore_items_flag:
+            # Evaluator.py:369-370 / BaseRecommender.py:103-106,210-211: the custom items get -inf before the
+            # ranking.  Rare API-edge path: the score rows make a round trip through the host, where the columns
+            # are masked, and re-enter the device mask -> top-k -> metric stage block by block.
+            ignore = np.asarray(self.ignore_items_ID, dtype=np.int64)
+            base_fn = score_fn
+
+            def score_fn(u):
+                sc = np.array(base_fn(u), dtype=np.float32, copy=True)
+                sc[:, ignore] = -np.inf
+                return sc
         if eng is None:
             # any recommender exposing _compute_item_score (e.g. the reference's own baselines): its host score
             # rows are pushed, block by block as Evaluator.py:238 sizes them, through the device
@@ -97,10 +108,12 @@ class EvaluatorHoldout(Evaluator):
             eng = self._scores_engine
             eng.set_csr(L.CSR_SEEN, URM_train, with_data=False)
             eng.set_test(self.URM_test, URM_train)
-            block = min(1000, max(1, int(1e8 / self.n_items)))
-            return eng.evaluate_scores(lambda u: recommender_object._compute_item_score(u), users, self.cutoff_list,
-                                       remove_seen=self.exclude_seen, block_size=block)
+            return eng.evaluate_scores(score_fn, users, self.cutoff_list, remove_seen=self.exclude_seen,
+                                       block_size=block)
         eng.set_test(self.URM_test, URM_train)
+        if self.ignore_items_flag:
+            return eng.evaluate_scores(score_fn, users, self.cutoff_list, remove_seen=self.exclude_seen,
+                                       block_size=block)
         return eng.evaluate(users, self.cutoff_list, remove_seen=self.exclude_seen)
 
     def evaluateRecommender(self, recommender_object):
@@ -108,13 +121,18 @@ class EvaluatorHoldout(Evaluator):
         n_eval = len(users)
         results_dict = {}
         if n_eval > 0:
+            if self.ignore_items_flag and hasattr(recommender_object, "set_items_to_ignore"):
+                recommender_object.set_items_to_ignore(self.ignore_items_ID)          # Evaluator.py:369-370
             sums, counts = self._device_sums(recommender_object, users)
+            if self.ignore_items_flag and hasattr(recommender_object, "reset_items_to_ignore"):
+                recommender_object.reset_items_to_ignore()                            # Evaluator.py:410-411
             for ci, cutoff in enumerate(self.cutoff_list):
                 s = dict(zip(L.MC_NAMES, sums[ci]))
                 res = {k: s[k] / n_eval for k in ("ROC_AUC", "PRECISION", "PRECISION_RECALL_MIN_DEN", "RECALL", "MAP",
                                                   "MRR", "NDCG", "HIT_RATE", "ARHR", "RMSE", "NOVELTY",
                                                   "AVERAGE_POPULARITY")}
-                res.update(finalize_count_metrics(counts[ci], n_eval, cutoff, self.n_items))
+                res.update(finalize_count_metrics(counts[ci], n_eval, cutoff, self.n_items,
+                                                  len(self.ignore_items_ID) if self.ignore_items_flag else 0))
                 res["COVERAGE_USER"] = s["COVERED"] / self.n_users     # metrics.py:57-80
                 p_, r_ = res["PRECISION"], res["RECALL"]
                 res["F1"] = 2 * (p_ * r_) / (p_ + r_) if p_ + r_ != 0 else 0.0   # Evaluator.py:392-397

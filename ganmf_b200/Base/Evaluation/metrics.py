@@ -9,10 +9,12 @@ Diversity_MeanInterList :463."""
 import numpy as np
 
 
-def finalize_count_metrics(counts, n_eval, cutoff, n_items):
+def finalize_count_metrics(counts, n_eval, cutoff, n_items, n_ignore=0):
+    """n_ignore = len(ignore_items): ignored items are never recommended, so they only shrink Coverage_Item's
+    denominator (metrics.py:36-46); the Gini / Herfindahl / Shannon objects drop zero-count items anyway."""
     counts = np.asarray(counts, dtype=np.float64)
     out = {}
-    out["COVERAGE_ITEM"] = (counts > 0).sum() / n_items
+    out["COVERAGE_ITEM"] = (counts > 0).sum() / (n_items - n_ignore)
     nz = counts[counts != 0]
     n = len(nz)
     srt = np.sort(nz)

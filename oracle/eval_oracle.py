@@ -141,12 +141,14 @@ def users_to_evaluate(urm_test, min_ratings=1):
     return np.arange(urm_test.shape[0])[np.ediff1d(urm_test.indptr) >= min_ratings]
 
 
-def finalize_count_metrics(counts, n_eval, cutoff, n_items):
+def finalize_count_metrics(counts, n_eval, cutoff, n_items, n_ignore=0):
     """get_metric_value() of the histogram-based objects (metrics.py:30-55,139-295,463-551)
-    from the per-item recommendation counts of one cutoff."""
+    from the per-item recommendation counts of one cutoff.  n_ignore = len(ignore_items): ignored items are
+    never recommended, so the only object they change is Coverage_Item's denominator (metrics.py:36-46; the
+    Gini / Herfindahl / Shannon masks drop zero-count items anyway, :163-167,213-217,267-271)."""
     counts = np.asarray(counts, dtype=np.float64)
     out = {}
-    out["COVERAGE_ITEM"] = (counts > 0).sum() / n_items
+    out["COVERAGE_ITEM"] = (counts > 0).sum() / (n_items - n_ignore)
     nz = counts[counts != 0]
     n = len(nz)
     srt = np.sort(nz)
@@ -166,7 +168,7 @@ def finalize_count_metrics(counts, n_eval, cutoff, n_items):
 
 
 def evaluate(score_fn, urm_train, urm_test, cutoff_list, exclude_seen=True, min_ratings=1,
-             promotion="legacy", block_size=None, return_lists=False):
+             promotion="legacy", block_size=None, return_lists=False, ignore_items=None):
     """EvaluatorHoldout.evaluateRecommender (Evaluator.py:234-414).
 
     score_fn(user_id_array) -> float32 [n, n_items] raw scores (== _compute_item_score).
@@ -197,6 +199,10 @@ def evaluate(score_fn, urm_train, urm_test, cutoff_list, exclude_seen=True, min_
     for s in range(0, len(users), block_size):
         batch = users[s:s + block_size]
         raw = np.asarray(score_fn(batch), dtype=np.float32)
+        if ignore_items is not None and len(ignore_items):
+            # Evaluator.py:369-370 + BaseRecommender.py:103-106,210-211: -inf on the custom items
+            raw = raw.copy()
+            raw[:, np.asarray(ignore_items, dtype=np.int64)] = -np.inf
         lists, scores = recommend(raw, urm_train, batch, max_cutoff, exclude_seen)
         if return_lists:
             all_lists.extend(lists)
@@ -237,7 +243,8 @@ def evaluate(score_fn, urm_train, urm_test, cutoff_list, exclude_seen=True, min_
             for k in ("ROC_AUC", "PRECISION", "PRECISION_RECALL_MIN_DEN", "RECALL", "MAP", "MRR", "NDCG",
                       "HIT_RATE", "ARHR", "RMSE", "NOVELTY", "AVERAGE_POPULARITY"):
                 res[k] = a[k] / n_eval
-            res.update(finalize_count_metrics(a["counts"], n_eval, c, n_items))
+            res.update(finalize_count_metrics(a["counts"], n_eval, c, n_items,
+                                              0 if ignore_items is None else len(ignore_items)))
             res["COVERAGE_USER"] = a["covered_users"] / n_users
             p_, r_ = res["PRECISION"], res["RECALL"]
             res["F1"] = 2 * (p_ * r_) / (p_ + r_) if p_ + r_ != 0 else 0.0

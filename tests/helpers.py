@@ -17,7 +17,9 @@ def load_eval_fixture(name):
                           shape=(n_users, n_items))
     return dict(scores=z["scores"], train=train, test=test, cutoffs=[int(c) for c in z["cutoffs"]],
                 users=z["users"], lists=z["lists"], metric_names=[str(m) for m in z["metric_names"]],
-                results=z["results"])
+                results=z["results"],
+                ignore_items=(z["ignore_items"].astype(np.int64) if "ignore_items" in z.files and
+                              len(z["ignore_items"]) else None))
 
 
 def load_lastfm_kat():

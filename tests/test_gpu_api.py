@@ -55,6 +55,20 @@ def test_fit_recommend_evaluate(mode):
     order = np.argsort(-raw[0 + 5], kind="stable")
     order = [i for i in order if i not in set(seen5.tolist())][:len(full)]
     assert full == order
+    # ignore_items (Evaluator.py:128-134,369-370): never recommended, COVERAGE_ITEM over the remaining items;
+    # every metric equals the oracle's on the model's own scores
+    from oracle import eval_oracle as eo
+    ignore = np.arange(0, train.shape[1], 7)
+    res_i, _ = EvaluatorHoldout(test, cutoff_list=[5, 10], exclude_seen=True, ignore_items=ignore).evaluateRecommender(rec)
+    ores, _ = eo.evaluate(lambda u: rec._compute_item_score(u), train, test, [5, 10], promotion="legacy",
+                          ignore_items=ignore)
+    for c in (5, 10):
+        for m in ("PRECISION", "RECALL", "MAP", "NDCG", "MRR", "HIT_RATE", "COVERAGE_ITEM", "DIVERSITY_GINI",
+                  "SHANNON_ENTROPY", "NOVELTY"):
+            assert float(res_i[c][m]) == pytest.approx(float(ores[c][m]), rel=1e-12), (c, m)
+    assert rec.items_to_ignore_flag is False            # reset after the evaluation (Evaluator.py:410-411)
+    lists_i = rec.recommend(users, cutoff=7)
+    assert lists_i == lists                             # and recommend() is back to the unfiltered ranking
 
 
 def test_early_stopping_scheduler_and_snapshot(tmp_path):
