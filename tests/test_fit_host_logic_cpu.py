@@ -171,3 +171,64 @@ def test_constructor_contract(stand_in):
     assert (g.RECOMMENDER_NAME, d.RECOMMENDER_NAME) == ("GANMF", "DisGANMF")
     with pytest.raises(TypeError):
         d.saveModel("/tmp/x")                                            # DisGANMF.py:264: file_name is required
+
+
+# ------------------------------------------------------------------------------------------------ evaluator host side
+class SumsEngine(object):
+    """Stand-in for the device evaluation stage: hands back the per-cutoff metric SUMS and item histograms the
+    oracle accumulates (in the device's column order), so the test isolates what the host does with them."""
+
+    def __init__(self, ores, cutoffs, n_items):
+        from ganmf_b200 import _lib as L
+        self.sums = np.zeros((len(cutoffs), L.MC_NCOL))
+        self.counts = np.zeros((len(cutoffs), n_items), dtype=np.int64)
+        for ci, c in enumerate(cutoffs):
+            s = dict(ores[c]["_sums"])
+            s["COVERED"] = s.pop("covered_users")
+            for mi, name in enumerate(L.MC_NAMES):
+                self.sums[ci, mi] = float(s[name])
+            self.counts[ci] = ores[c]["_counts"]
+        self.calls = []
+
+    def set_test(self, test, train):
+        self.calls.append("set_test")
+
+    def evaluate(self, users, cutoffs, remove_seen=True):
+        self.calls.append(("evaluate", len(users), list(cutoffs), remove_seen))
+        return self.sums, self.counts
+
+
+@pytest.mark.parametrize("name", ["eval_small_implicit", "eval_small_ratings", "eval_small_shortlists"])
+def test_evaluator_host_side_reproduces_the_reference_results_dict(name):
+    """EvaluatorHoldout.evaluateRecommender: users to evaluate, averaging, F1 of the averaged P and R,
+    COVERAGE_USER, the histogram metrics, key order and the 7-decimal result string (Evaluator.py:95-110,
+    119-179,386-414) -- against the golden run of the unmodified reference evaluator."""
+    from oracle import eval_oracle as eo
+    from tests.helpers import load_eval_fixture
+    from ganmf_b200.Base.Evaluation.Evaluator import EvaluatorHoldout
+    fx = load_eval_fixture(name)
+    # "legacy" = the reference's pinned numpy 1.16 promotion rules, which the device and the host implement;
+    # the golden run was made under numpy >= 2, where a few float32 scalars stay float32 (oracle/eval_oracle.py)
+    ores, n_eval = eo.evaluate(lambda u: fx["scores"][u], fx["train"], fx["test"], fx["cutoffs"], promotion="legacy")
+
+    class Rec(object):
+        _engine = SumsEngine(ores, fx["cutoffs"], fx["train"].shape[1])
+
+        def get_URM_train(self):
+            return fx["train"].copy()
+
+    ev = EvaluatorHoldout(fx["test"], cutoff_list=fx["cutoffs"], exclude_seen=True)
+    assert np.array_equal(np.asarray(ev.usersToEvaluate), fx["users"])               # Evaluator.py:151-163
+    res, txt = ev.evaluateRecommender(Rec())
+    assert Rec._engine.calls == ["set_test", ("evaluate", len(fx["users"]), fx["cutoffs"], True)]
+    for ci, c in enumerate(fx["cutoffs"]):
+        assert sorted(res[c].keys()) == fx["metric_names"]
+        for mi, m in enumerate(fx["metric_names"]):
+            want, got = fx["results"][ci, mi], float(res[c][m])
+            if np.isnan(want):
+                assert np.isnan(got)
+                continue
+            assert got == float(ores[c][m]), (c, m, got, float(ores[c][m]))         # bit for bit in legacy arithmetic
+            assert got == pytest.approx(want, rel=2e-6, abs=1e-9), (c, m, got, want)  # golden: last bits only
+    assert txt == eo.get_result_string({c: {k: ores[c][k] for k in res[c]} for c in fx["cutoffs"]})
+    assert txt.startswith("CUTOFF: %d - ROC_AUC: " % fx["cutoffs"][0]) and txt.count("\n") == len(fx["cutoffs"])
