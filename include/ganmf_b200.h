@@ -59,7 +59,8 @@ void ganmf_destroy(ganmf_ctx* ctx);
 int ganmf_set_stream(ganmf_ctx* ctx, void* cuda_stream);          /* cudaStream_t, NULL = default */
 /* Cap on the number of SMs the persistent tensor-core GEMMs occupy (0 = all).  A data-parallel caller lowers
  * it while a collective is in flight: a GEMM CTA needs a whole SM, so NCCL's CTAs can only run next to a GEMM
- * on SMs the GEMM grid leaves free. */
+ * on SMs the GEMM grid leaves free.  (No reference counterpart: the reference trains on one device,
+ * GANMF.py:142-150; this belongs to the data-parallel extension) */
 int ganmf_set_gemm_sms(ganmf_ctx* ctx, int n_sms);
 int ganmf_synchronize(ganmf_ctx* ctx);
 
@@ -109,7 +110,8 @@ int ganmf_d_apply(ganmf_ctx* ctx, float lr, float reg, int loss_slot);
 int ganmf_g_forward_backward(ganmf_ctx* ctx, int ids_offset, int B, int n_rows_global,
                              float recon_coefficient);
 /* GANMF: the same in two parts so the all-reduce of the item-factor gradient ("g_shared_grad", complete after
- * part 1) overlaps the user-factor gradient GEMM (part 2). */
+ * part 1) overlaps the user-factor gradient GEMM (part 2).  Both parts together are one
+ * sess.run([gtrain, gloss]) up to the optimiser (GANMF.py:200-201); data-parallel extension. */
 int ganmf_g_forward_backward_part(ganmf_ctx* ctx, int ids_offset, int B, int n_rows_global,
                                   float recon_coefficient, int part);
 int ganmf_g_apply(ganmf_ctx* ctx, int B, int n_rows_global, float lr, float reg,
