@@ -168,7 +168,7 @@ def finalize_count_metrics(counts, n_eval, cutoff, n_items, n_ignore=0):
 
 
 def evaluate(score_fn, urm_train, urm_test, cutoff_list, exclude_seen=True, min_ratings=1,
-             promotion="legacy", block_size=None, return_lists=False, ignore_items=None):
+             promotion="legacy", block_size=None, return_lists=False, ignore_items=None, ignore_users=None):
     """EvaluatorHoldout.evaluateRecommender (Evaluator.py:234-414).
 
     score_fn(user_id_array) -> float32 [n, n_items] raw scores (== _compute_item_score).
@@ -178,6 +178,10 @@ def evaluate(score_fn, urm_train, urm_test, cutoff_list, exclude_seen=True, min_
     urm_test = sps.csr_matrix(urm_test)
     n_users, n_items = urm_test.shape
     users = users_to_evaluate(urm_test, min_ratings)
+    n_ignore_users = 0
+    if ignore_users is not None:                                         # Evaluator.py:171-176
+        n_ignore_users = len(ignore_users)
+        users = np.array(sorted(set(users.tolist()) - set(int(u) for u in ignore_users)), dtype=users.dtype)
     max_cutoff = max(cutoff_list)
     if block_size is None:
         block_size = min(1000, int(1e8 / n_items))
@@ -245,7 +249,7 @@ def evaluate(score_fn, urm_train, urm_test, cutoff_list, exclude_seen=True, min_
                 res[k] = a[k] / n_eval
             res.update(finalize_count_metrics(a["counts"], n_eval, c, n_items,
                                               0 if ignore_items is None else len(ignore_items)))
-            res["COVERAGE_USER"] = a["covered_users"] / n_users
+            res["COVERAGE_USER"] = a["covered_users"] / (n_users - n_ignore_users)     # metrics.py:57-80
             p_, r_ = res["PRECISION"], res["RECALL"]
             res["F1"] = 2 * (p_ * r_) / (p_ + r_) if p_ + r_ != 0 else 0.0
         results[c] = {k: res[k] for k in METRIC_NAMES if k in res}

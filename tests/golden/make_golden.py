@@ -9,7 +9,8 @@ Fixtures
                      Base/BaseRecommender.recommend + Base/Evaluation/Evaluator.EvaluatorHoldout
                      (numpy>=2 shim: np.int=int, np.float=float, np.bool=bool) -> all 19 metrics
                      per cutoff + the recommendation lists.  eval_small_ignore: the same with
-                     EvaluatorHoldout(ignore_items=...) (40 of 320 items).
+                     EvaluatorHoldout(ignore_items=...) (40 of 320 items); eval_small_ignore_users:
+                     EvaluatorHoldout(ignore_users=...) (23 of 140 users).
   lastfm_kat.npz     the one surviving reference checkpoint
                      (feature_matching/GANMF_item_LastFM_00/GANMF_item_LastFM/GANMF_item.data-*):
                      generator factors + committed LastFM train/test split + the stored
@@ -39,7 +40,7 @@ def load_reference():
 
 
 def make_eval_fixture(name, n_users, n_items, train_density, test_density, cutoffs, seed, ratings,
-                      short_rows=False, n_ignore=0):
+                      short_rows=False, n_ignore=0, n_ignore_users=0):
     BaseRecommender, EvaluatorHoldout = load_reference()
     rs = np.random.RandomState(seed)
     train = sps.random(n_users, n_items, train_density, format="csr", dtype=np.float32, random_state=rs)
@@ -80,9 +81,14 @@ def make_eval_fixture(name, n_users, n_items, train_density, test_density, cutof
     # ignore_items (Evaluator.py:128-134,369-370,410-411): the evaluator masks them through
     # set_items_to_ignore / remove_CustomItems_flag and shrinks COVERAGE_ITEM's denominator
     ignore = np.sort(rs.choice(n_items, size=n_ignore, replace=False)).astype(np.int64) if n_ignore else None
-    ev = EvaluatorHoldout(test, cutoff_list=list(cutoffs), exclude_seen=True, ignore_items=ignore)
+    # ignore_users (Evaluator.py:171-176): dropped from usersToEvaluate, Coverage_User's denominator shrinks
+    ign_users = np.sort(rs.choice(n_users, size=n_ignore_users, replace=False)).astype(np.int64) \
+        if n_ignore_users else None
+    ev = EvaluatorHoldout(test, cutoff_list=list(cutoffs), exclude_seen=True, ignore_items=ignore,
+                          ignore_users=ign_users)
     results, _ = ev.evaluateRecommender(rec)
-    users = np.array(ev.usersToEvaluate)
+    users = np.array(sorted(ev.usersToEvaluate))
+    assert list(ev.usersToEvaluate) == sorted(ev.usersToEvaluate)   # the set difference iterated in ascending order
     if n_ignore:
         rec.set_items_to_ignore(ignore)
     lists, _ = rec.recommend(users, cutoff=max(cutoffs), remove_seen_flag=True, return_scores=True,
@@ -98,7 +104,8 @@ def make_eval_fixture(name, n_users, n_items, train_density, test_density, cutof
         test_indptr=test.indptr, test_indices=test.indices, test_data=test.data,
         shape=np.array([n_users, n_items]), cutoffs=np.array(cutoffs), users=users, lists=flat,
         metric_names=np.array(metric_names), results=table,
-        ignore_items=ignore if n_ignore else np.zeros(0, dtype=np.int64))
+        ignore_items=ignore if n_ignore else np.zeros(0, dtype=np.int64),
+        ignore_users=ign_users if n_ignore_users else np.zeros(0, dtype=np.int64))
     print(name, "users evaluated", len(users), "P@%d" % cutoffs[0], results[cutoffs[0]]["PRECISION"])
 
 
@@ -176,8 +183,11 @@ def make_quality_targets():
 if __name__ == "__main__":
     if "--only-ignore" in sys.argv:
         make_eval_fixture("eval_small_ignore", 130, 320, 0.06, 0.04, (5, 10, 20), 17, ratings=True, n_ignore=40)
+        make_eval_fixture("eval_small_ignore_users", 140, 200, 0.06, 0.05, (5, 10), 19, ratings=False,
+                          n_ignore_users=23)
         sys.exit(0)
     make_eval_fixture("eval_small_ignore", 130, 320, 0.06, 0.04, (5, 10, 20), 17, ratings=True, n_ignore=40)
+    make_eval_fixture("eval_small_ignore_users", 140, 200, 0.06, 0.05, (5, 10), 19, ratings=False, n_ignore_users=23)
     make_eval_fixture("eval_small_implicit", 150, 400, 0.05, 0.03, (5, 10, 20, 50), 7, ratings=False)
     make_eval_fixture("eval_small_ratings", 120, 300, 0.08, 0.04, (1, 5, 10), 11, ratings=True)
     make_eval_fixture("eval_small_shortlists", 100, 60, 0.10, 0.08, (5, 20, 50), 13, ratings=True,

@@ -19,7 +19,9 @@ def load_eval_fixture(name):
                 users=z["users"], lists=z["lists"], metric_names=[str(m) for m in z["metric_names"]],
                 results=z["results"],
                 ignore_items=(z["ignore_items"].astype(np.int64) if "ignore_items" in z.files and
-                              len(z["ignore_items"]) else None))
+                              len(z["ignore_items"]) else None),
+                ignore_users=(z["ignore_users"].astype(np.int64) if "ignore_users" in z.files and
+                              len(z["ignore_users"]) else None))
 
 
 def load_lastfm_kat():

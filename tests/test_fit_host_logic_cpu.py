@@ -198,7 +198,8 @@ class SumsEngine(object):
         return self.sums, self.counts
 
 
-@pytest.mark.parametrize("name", ["eval_small_implicit", "eval_small_ratings", "eval_small_shortlists"])
+@pytest.mark.parametrize("name", ["eval_small_implicit", "eval_small_ratings", "eval_small_shortlists",
+                                  "eval_small_ignore_users"])
 def test_evaluator_host_side_reproduces_the_reference_results_dict(name):
     """EvaluatorHoldout.evaluateRecommender: users to evaluate, averaging, F1 of the averaged P and R,
     COVERAGE_USER, the histogram metrics, key order and the 7-decimal result string (Evaluator.py:95-110,
@@ -209,7 +210,8 @@ def test_evaluator_host_side_reproduces_the_reference_results_dict(name):
     fx = load_eval_fixture(name)
     # "legacy" = the reference's pinned numpy 1.16 promotion rules, which the device and the host implement;
     # the golden run was made under numpy >= 2, where a few float32 scalars stay float32 (oracle/eval_oracle.py)
-    ores, n_eval = eo.evaluate(lambda u: fx["scores"][u], fx["train"], fx["test"], fx["cutoffs"], promotion="legacy")
+    ores, n_eval = eo.evaluate(lambda u: fx["scores"][u], fx["train"], fx["test"], fx["cutoffs"], promotion="legacy",
+                               ignore_users=fx["ignore_users"])
 
     class Rec(object):
         _engine = SumsEngine(ores, fx["cutoffs"], fx["train"].shape[1])
@@ -217,8 +219,8 @@ def test_evaluator_host_side_reproduces_the_reference_results_dict(name):
         def get_URM_train(self):
             return fx["train"].copy()
 
-    ev = EvaluatorHoldout(fx["test"], cutoff_list=fx["cutoffs"], exclude_seen=True)
-    assert np.array_equal(np.asarray(ev.usersToEvaluate), fx["users"])               # Evaluator.py:151-163
+    ev = EvaluatorHoldout(fx["test"], cutoff_list=fx["cutoffs"], exclude_seen=True, ignore_users=fx["ignore_users"])
+    assert np.array_equal(np.asarray(ev.usersToEvaluate), fx["users"])               # Evaluator.py:151-176
     res, txt = ev.evaluateRecommender(Rec())
     assert Rec._engine.calls == ["set_test", ("evaluate", len(fx["users"]), fx["cutoffs"], True)]
     for ci, c in enumerate(fx["cutoffs"]):

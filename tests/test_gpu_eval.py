@@ -130,7 +130,7 @@ def test_large_scale_properties():
 
 
 @pytest.mark.parametrize("name", ["eval_small_implicit", "eval_small_ratings", "eval_small_shortlists",
-                                  "eval_small_ignore"])
+                                  "eval_small_ignore", "eval_small_ignore_users"])
 def test_evaluator_with_foreign_recommender_matches_reference_run(name):
     """EvaluatorHoldout on a recommender that only exposes _compute_item_score / get_URM_train (as the
     reference's baselines do): all 19 metrics equal the unmodified reference evaluator's output (golden),
@@ -149,10 +149,11 @@ def test_evaluator_with_foreign_recommender_matches_reference_run(name):
             return fx["scores"][user_id_array].copy()
 
     # (eval_small_ignore: the reference run used EvaluatorHoldout(ignore_items=40 of 320 items))
-    ev = EvaluatorHoldout(fx["test"], cutoff_list=fx["cutoffs"], exclude_seen=True, ignore_items=fx["ignore_items"])
+    ev = EvaluatorHoldout(fx["test"], cutoff_list=fx["cutoffs"], exclude_seen=True, ignore_items=fx["ignore_items"],
+                          ignore_users=fx["ignore_users"])
     res, txt = ev.evaluateRecommender(Fixed())
     ores, n_eval = eo.evaluate(lambda u: fx["scores"][u], fx["train"], fx["test"], fx["cutoffs"], promotion="legacy",
-                               ignore_items=fx["ignore_items"])
+                               ignore_items=fx["ignore_items"], ignore_users=fx["ignore_users"])
     for ci, c in enumerate(fx["cutoffs"]):
         for mi, m in enumerate(fx["metric_names"]):
             want = fx["results"][ci, mi]

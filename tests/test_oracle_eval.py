@@ -9,11 +9,12 @@ from tests.helpers import load_eval_fixture, load_lastfm_kat
 
 
 @pytest.mark.parametrize("name", ["eval_small_implicit", "eval_small_ratings", "eval_small_shortlists",
-                                  "eval_small_ignore"])
+                                  "eval_small_ignore", "eval_small_ignore_users"])
 def test_oracle_matches_reference_run_bit_for_bit(name):
     fx = load_eval_fixture(name)
     res, n_eval, lists = eo.evaluate(lambda u: fx["scores"][u], fx["train"], fx["test"], fx["cutoffs"],
-                                     promotion="nep50", return_lists=True, ignore_items=fx["ignore_items"])
+                                     promotion="nep50", return_lists=True, ignore_items=fx["ignore_items"],
+                                     ignore_users=fx["ignore_users"])
     assert n_eval == len(fx["users"])
     for i, l in enumerate(lists):                      # same recommendation lists
         want = fx["lists"][i]
