@@ -132,7 +132,7 @@ class EvaluatorHoldout(Evaluator):
                                                   "MRR", "NDCG", "HIT_RATE", "ARHR", "RMSE", "NOVELTY",
                                                   "AVERAGE_POPULARITY")}
                 res.update(finalize_count_metrics(counts[ci], n_eval, cutoff, self.n_items,
-                                                  len(self.ignore_items_ID) if self.ignore_items_flag else 0))
+                                                  self.ignore_items_ID if self.ignore_items_flag else None))
                 res["COVERAGE_USER"] = s["COVERED"] / (self.n_users - len(self.ignore_users_ID))   # metrics.py:57-80
                 p_, r_ = res["PRECISION"], res["RECALL"]
                 res["F1"] = 2 * (p_ * r_) / (p_ + r_) if p_ + r_ != 0 else 0.0   # Evaluator.py:392-397

@@ -9,10 +9,12 @@ Diversity_MeanInterList :463."""
 import numpy as np
 
 
-def finalize_count_metrics(counts, n_eval, cutoff, n_items, n_ignore=0):
-    """n_ignore = len(ignore_items): ignored items are never recommended, so they only shrink Coverage_Item's
-    denominator (metrics.py:36-46); the Gini / Herfindahl / Shannon objects drop zero-count items anyway."""
+def finalize_count_metrics(counts, n_eval, cutoff, n_items, ignore_items=None):
+    """ignore_items are never recommended (count 0): they shrink Coverage_Item's denominator (metrics.py:36-46)
+    and are deleted from the histogram Herfindahl sums over (:213-217: same values, but numpy's pairwise
+    summation of the shorter array can differ in the last bit); Gini / Shannon drop zero-count items anyway."""
     counts = np.asarray(counts, dtype=np.float64)
+    n_ignore = 0 if ignore_items is None else len(ignore_items)
     out = {}
     out["COVERAGE_ITEM"] = (counts > 0).sum() / (n_items - n_ignore)
     nz = counts[counts != 0]
@@ -20,8 +22,9 @@ def finalize_count_metrics(counts, n_eval, cutoff, n_items, n_ignore=0):
     srt = np.sort(nz)
     index = np.arange(1, n + 1)
     out["DIVERSITY_GINI"] = 2 * np.sum((n + 1 - index) / (n + 1) * srt / np.sum(srt)) if n else 0.0
-    tot = counts.sum()
-    out["DIVERSITY_HERFINDAHL"] = 1 - np.sum((counts / tot) ** 2) if tot != 0 else np.nan
+    kept = counts if not n_ignore else np.delete(counts, np.asarray(ignore_items, dtype=np.int64))
+    tot = kept.sum()
+    out["DIVERSITY_HERFINDAHL"] = 1 - np.sum((kept / tot) ** 2) if tot != 0 else np.nan
     prob = nz / nz.sum() if n else nz
     out["SHANNON_ENTROPY"] = -np.sum(prob * np.log2(prob)) if n else 0.0
     if n_eval == 0:

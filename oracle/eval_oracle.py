@@ -141,12 +141,14 @@ def users_to_evaluate(urm_test, min_ratings=1):
     return np.arange(urm_test.shape[0])[np.ediff1d(urm_test.indptr) >= min_ratings]
 
 
-def finalize_count_metrics(counts, n_eval, cutoff, n_items, n_ignore=0):
+def finalize_count_metrics(counts, n_eval, cutoff, n_items, ignore_items=None):
     """get_metric_value() of the histogram-based objects (metrics.py:30-55,139-295,463-551)
-    from the per-item recommendation counts of one cutoff.  n_ignore = len(ignore_items): ignored items are
-    never recommended, so the only object they change is Coverage_Item's denominator (metrics.py:36-46; the
-    Gini / Herfindahl / Shannon masks drop zero-count items anyway, :163-167,213-217,267-271)."""
+    from the per-item recommendation counts of one cutoff.  ignore_items are never recommended (count 0):
+    they shrink Coverage_Item's denominator (metrics.py:36-46) and are DELETED from the histogram before
+    Herfindahl's sum (:213-217; the values are unchanged but numpy's pairwise summation groups a shorter array
+    differently -- 1 ulp); the Gini / Shannon masks drop every zero-count item anyway (:163-167,267-271)."""
     counts = np.asarray(counts, dtype=np.float64)
+    n_ignore = 0 if ignore_items is None else len(ignore_items)
     out = {}
     out["COVERAGE_ITEM"] = (counts > 0).sum() / (n_items - n_ignore)
     nz = counts[counts != 0]
@@ -154,8 +156,9 @@ def finalize_count_metrics(counts, n_eval, cutoff, n_items, n_ignore=0):
     srt = np.sort(nz)
     index = np.arange(1, n + 1)
     out["DIVERSITY_GINI"] = 2 * np.sum((n + 1 - index) / (n + 1) * srt / np.sum(srt))
-    tot = counts.sum()
-    out["DIVERSITY_HERFINDAHL"] = 1 - np.sum((counts / tot) ** 2) if tot != 0 else np.nan
+    kept = counts if not n_ignore else np.delete(counts, np.asarray(ignore_items, dtype=np.int64))
+    tot = kept.sum()
+    out["DIVERSITY_HERFINDAHL"] = 1 - np.sum((kept / tot) ** 2) if tot != 0 else np.nan
     prob = nz / nz.sum()
     out["SHANNON_ENTROPY"] = -np.sum(prob * np.log2(prob))
     if n_eval == 0:
@@ -247,8 +250,7 @@ def evaluate(score_fn, urm_train, urm_test, cutoff_list, exclude_seen=True, min_
             for k in ("ROC_AUC", "PRECISION", "PRECISION_RECALL_MIN_DEN", "RECALL", "MAP", "MRR", "NDCG",
                       "HIT_RATE", "ARHR", "RMSE", "NOVELTY", "AVERAGE_POPULARITY"):
                 res[k] = a[k] / n_eval
-            res.update(finalize_count_metrics(a["counts"], n_eval, c, n_items,
-                                              0 if ignore_items is None else len(ignore_items)))
+            res.update(finalize_count_metrics(a["counts"], n_eval, c, n_items, ignore_items))
             res["COVERAGE_USER"] = a["covered_users"] / (n_users - n_ignore_users)     # metrics.py:57-80
             p_, r_ = res["PRECISION"], res["RECALL"]
             res["F1"] = 2 * (p_ * r_) / (p_ + r_) if p_ + r_ != 0 else 0.0

@@ -1,0 +1,129 @@
+"""Differential test against the UNMODIFIED reference evaluator, run where /root/reference exists (the build
+container; skipped on the GPU box): random small problems x random evaluator options
+(minRatingsPerUser, exclude_seen, cutoffs, ignore_items, ignore_users, explicit ratings, users who have seen
+almost everything) -> the reference's EvaluatorHoldout, the oracle, and the product's EvaluatorHoldout host side
+(fed with the oracle's metric sums in place of the device stage) must agree on all 19 metrics."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from oracle import eval_oracle as eo
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "Base", "Evaluation")),
+                                reason="needs the reference checkout (build container only)")
+
+
+def reference_classes():
+    np.int, np.float, np.bool = int, float, bool          # aliases the reference still uses (numpy >= 2 shim)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from Base.BaseRecommender import BaseRecommender
+    from Base.Evaluation.Evaluator import EvaluatorHoldout
+    return BaseRecommender, EvaluatorHoldout
+
+
+def make_problem(seed):
+    rs = np.random.RandomState(1000 + seed)
+    n_users, n_items = int(rs.randint(20, 90)), int(rs.randint(30, 160))
+    train = sps.random(n_users, n_items, rs.uniform(0.03, 0.15), format="csr", dtype=np.float32, random_state=rs)
+    train.data[:] = 1.0
+    test = sps.random(n_users, n_items, rs.uniform(0.03, 0.10), format="csr", dtype=np.float32, random_state=rs)
+    test = sps.csr_matrix(test - test.multiply(train.astype(bool)))
+    test.eliminate_zeros()
+    test.data[:] = rs.randint(1, 6, size=test.nnz).astype(np.float32) if seed % 2 else 1.0
+    if seed % 3 == 0:                                       # users who have seen almost everything: short lists
+        train = train.tolil()
+        for u in range(0, n_users, 11):
+            row = np.ones(n_items, dtype=np.float32)
+            row[rs.choice(n_items, size=2 + u % 4, replace=False)] = 0
+            row[test[u].indices] = 0
+            train[u] = row
+        train = sps.csr_matrix(train, dtype=np.float32)
+    scores = np.stack([rs.permutation(n_items) for _ in range(n_users)]).astype(np.float32)
+    scores = (scores * np.float32(0.0078125) - np.float32(1.5)).astype(np.float32)     # distinct per row: no ties
+    opts = dict(minRatingsPerUser=int(rs.randint(1, 4)), exclude_seen=bool(seed % 4 != 1),
+                ignore_items=(np.sort(rs.choice(n_items, size=n_items // 6, replace=False)) if seed % 5 in (2, 3) else None),
+                ignore_users=(np.sort(rs.choice(n_users, size=n_users // 7, replace=False)) if seed % 5 in (3, 4) else None))
+    # (the reference's argpartition needs cutoff < n_items, BaseRecommender.py:214)
+    cutoffs = sorted(set(int(c) for c in rs.choice([1, 3, 5, 10, 20, 50], size=3, replace=False) if c < n_items))
+    return train, test, scores, cutoffs, opts
+
+
+class SumsEngine(object):
+    def __init__(self, ores, cutoffs, n_items):
+        from ganmf_b200 import _lib as L
+        self.sums = np.zeros((len(cutoffs), L.MC_NCOL))
+        self.counts = np.zeros((len(cutoffs), n_items), dtype=np.int64)
+        for ci, c in enumerate(cutoffs):
+            s = dict(ores[c]["_sums"])
+            s["COVERED"] = s.pop("covered_users")
+            for mi, name in enumerate(L.MC_NAMES):
+                self.sums[ci, mi] = float(s[name])
+            self.counts[ci] = ores[c]["_counts"]
+
+    def set_test(self, test, train):
+        pass
+
+    def evaluate(self, users, cutoffs, remove_seen=True):
+        return self.sums, self.counts
+
+    def evaluate_scores(self, score_fn, users, cutoffs, remove_seen=True, block_size=1000):
+        return self.sums, self.counts
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
+@pytest.mark.parametrize("seed", range(48))
+def test_reference_oracle_and_host_side_agree(seed):
+    BaseRecommender, RefEvaluatorHoldout = reference_classes()
+    from ganmf_b200.Base.Evaluation.Evaluator import EvaluatorHoldout
+    train, test, scores, cutoffs, opts = make_problem(seed)
+
+    class Fixed(BaseRecommender):
+        RECOMMENDER_NAME = "Fixed"
+
+        def __init__(self, urm):
+            self.URM_train = urm
+
+        def _compute_item_score(self, user_id_array, items_to_compute=None):
+            return scores[user_id_array].copy()
+
+    ref_ev = RefEvaluatorHoldout(test, cutoff_list=list(cutoffs), **opts)
+    if len(ref_ev.usersToEvaluate) == 0:
+        pytest.skip("no user left to evaluate")
+    ref_users = list(ref_ev.usersToEvaluate)
+    if ref_users != sorted(ref_users):
+        pytest.skip("the reference iterated its user set out of order (float64 sums are order dependent)")
+    want, _ = ref_ev.evaluateRecommender(Fixed(train))
+
+    kw = dict(exclude_seen=opts["exclude_seen"], min_ratings=opts["minRatingsPerUser"],
+              ignore_items=opts["ignore_items"], ignore_users=opts["ignore_users"])
+    got_o, n_eval = eo.evaluate(lambda u: scores[u], train, test, cutoffs, promotion="nep50", **kw)
+    assert n_eval == len(ref_users)
+    legacy, _ = eo.evaluate(lambda u: scores[u], train, test, cutoffs, promotion="legacy", **kw)
+
+    class Rec(object):
+        _engine = SumsEngine(legacy, cutoffs, train.shape[1])
+
+        def get_URM_train(self):
+            return train.copy()
+
+        def _compute_item_score(self, u, items_to_compute=None):
+            return scores[u].copy()
+
+    ev = EvaluatorHoldout(test, cutoff_list=list(cutoffs), **opts)
+    assert list(ev.usersToEvaluate) == ref_users
+    got_h, txt = ev.evaluateRecommender(Rec())
+    for c in cutoffs:
+        assert list(got_h[c].keys()) == [k for k in want[c].keys()]          # same metric keys, same order
+        for m, w in want[c].items():
+            w = float(w)
+            o, h = float(got_o[c][m]), float(got_h[c][m])
+            if np.isnan(w):
+                assert np.isnan(o) and np.isnan(h), (c, m)
+                continue
+            assert o == w, (seed, c, m, o, w)                                   # oracle: bit for bit
+            assert h == pytest.approx(w, rel=2e-6, abs=1e-9), (seed, c, m, h, w)  # host side: legacy promotion
