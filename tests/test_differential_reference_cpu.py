@@ -17,13 +17,20 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "Base", "Eva
                                 reason="needs the reference checkout (build container only)")
 
 
+@pytest.fixture()
 def reference_classes():
-    np.int, np.float, np.bool = int, float, bool          # aliases the reference still uses (numpy >= 2 shim)
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    from Base.BaseRecommender import BaseRecommender
-    from Base.Evaluation.Evaluator import EvaluatorHoldout
-    return BaseRecommender, EvaluatorHoldout
+    """The reference's BaseRecommender / EvaluatorHoldout under numpy >= 2: it still uses the removed aliases
+    np.int / np.float (np.bool exists and must NOT be replaced: numpy.testing calls it).  The aliases and the
+    sys.path entry are removed again so no other test sees them."""
+    np.int, np.float = int, float
+    sys.path.insert(0, REF)
+    try:
+        from Base.BaseRecommender import BaseRecommender
+        from Base.Evaluation.Evaluator import EvaluatorHoldout
+        yield BaseRecommender, EvaluatorHoldout
+    finally:
+        sys.path.remove(REF)
+        del np.int, np.float
 
 
 def make_problem(seed):
@@ -77,8 +84,8 @@ class SumsEngine(object):
 
 @pytest.mark.filterwarnings("ignore::DeprecationWarning")
 @pytest.mark.parametrize("seed", range(48))
-def test_reference_oracle_and_host_side_agree(seed):
-    BaseRecommender, RefEvaluatorHoldout = reference_classes()
+def test_reference_oracle_and_host_side_agree(seed, reference_classes):
+    BaseRecommender, RefEvaluatorHoldout = reference_classes
     from ganmf_b200.Base.Evaluation.Evaluator import EvaluatorHoldout
     train, test, scores, cutoffs, opts = make_problem(seed)
 
