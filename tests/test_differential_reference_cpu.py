@@ -134,3 +134,81 @@ def test_reference_oracle_and_host_side_agree(seed, reference_classes):
                 continue
             assert o == w, (seed, c, m, o, w)                                   # oracle: bit for bit
             assert h == pytest.approx(w, rel=2e-6, abs=1e-9), (seed, c, m, h, w)  # host side: legacy promotion
+
+
+# ------------------------------------------------------------------------------------------------ recommend()
+class OracleBackedEngine(object):
+    """Stand-in for the device engine behind BaseRecommender.recommend: same methods, results from the oracle
+    (idx = -1 where the score is -inf, as the device returns)."""
+
+    def __init__(self, scores, train):
+        self.scores, self.train, self.n_items = scores, train, scores.shape[1]
+
+    def score(self, users):
+        return self.scores[np.asarray(users)].copy()
+
+    def _topk(self, sc, K):
+        idx, val = eo.topk_lowest_index(sc, K)
+        idx = idx.astype(np.int32)
+        idx[np.isneginf(val)] = -1
+        return idx, val
+
+    def recommend(self, users, K, remove_seen=True, return_scores=False):
+        users = np.asarray(users)
+        sc = self.scores[users]
+        sc = eo.remove_seen(sc, self.train, users) if remove_seen else sc.copy()
+        idx, val = self._topk(sc, K)
+        return idx, val, (sc if return_scores else None)
+
+    def mask_topk(self, scores, K, users=None, remove_seen=False, write_back=False):
+        sc = eo.remove_seen(scores, self.train, users) if remove_seen else np.array(scores, copy=True)
+        if write_back:
+            scores[...] = sc
+        return self._topk(sc, K)
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
+@pytest.mark.parametrize("seed", range(16))
+def test_recommend_host_logic_matches_reference(seed, reference_classes):
+    """BaseRecommender.recommend (BaseRecommender.py:155-247): scalar / array users, cutoff=None, seen filter on
+    and off, top-pop and custom-item filters, return_scores -- the product's host wrapper (device stage replaced
+    by the oracle) against the unmodified reference method on the same scores."""
+    RefBase, _ = reference_classes
+    from ganmf_b200.Base.BaseRecommender import BaseRecommender
+    train, test, scores, cutoffs, opts = make_problem(seed)
+    rs = np.random.RandomState(seed)
+    n_users, n_items = scores.shape
+    top_pop = np.sort(rs.choice(n_items, size=5, replace=False))
+    custom = np.sort(rs.choice(n_items, size=7, replace=False))
+
+    class RefRec(RefBase):
+        def __init__(self):
+            self.URM_train = train
+            self.filterTopPop_ItemsID = top_pop
+            self.items_to_ignore_ID = custom
+
+        def _compute_item_score(self, user_id_array, items_to_compute=None):
+            return scores[user_id_array].copy()
+
+    class OurRec(BaseRecommender):
+        def __init__(self):
+            super(OurRec, self).__init__(train)
+            self._engine = OracleBackedEngine(scores, train)
+            self.filterTopPop_ItemsID = top_pop
+            self.items_to_ignore_ID = custom
+
+    ref, ours = RefRec(), OurRec()
+    users = rs.choice(n_users, size=min(12, n_users), replace=False)
+    cases = [dict(cutoff=5), dict(cutoff=min(20, n_items - 1), remove_seen_flag=False),
+             dict(cutoff=3, remove_top_pop_flag=True), dict(cutoff=7, remove_CustomItems_flag=True),
+             dict(cutoff=4, remove_top_pop_flag=True, remove_CustomItems_flag=True, remove_seen_flag=False),
+             dict(cutoff=None)]
+    for kw in cases:
+        want = ref.recommend(users, **kw)
+        got = ours.recommend(users, **kw)
+        assert got == want, (seed, kw)
+        assert ours.recommend(int(users[0]), **kw) == ref.recommend(int(users[0]), **kw)     # scalar -> one list
+        wl, ws = ref.recommend(users, return_scores=True, **kw)
+        gl, gs = ours.recommend(users, return_scores=True, **kw)
+        assert gl == wl and gs.shape == ws.shape
+        assert np.array_equal(np.isneginf(gs), np.isneginf(ws)) and np.array_equal(gs[np.isfinite(gs)], ws[np.isfinite(ws)])
