@@ -212,3 +212,117 @@ def test_recommend_host_logic_matches_reference(seed, reference_classes):
         gl, gs = ours.recommend(users, return_scores=True, **kw)
         assert gl == wl and gs.shape == ws.shape
         assert np.array_equal(np.isneginf(gs), np.isneginf(ws)) and np.array_equal(gs[np.isfinite(gs)], ws[np.isfinite(ws)])
+
+
+# ------------------------------------------------------------------------------------------------ early stopping
+def _reference_scheduler_class():
+    """EarlyStoppingScheduler as written in the reference (Utils_.py): the module itself cannot be imported
+    (seaborn / matplotlib at import time), so the class statement alone is compiled from the source file."""
+    src = open(os.path.join(REF, "Utils_.py")).read()
+    start = src.index("class EarlyStoppingScheduler")
+    end = src.index("\nclass ", start + 10) if "\nclass " in src[start + 10:] else src.index("\ndef ", start + 10)
+    end = min(end, src.index("\ndef ", start + 10))
+    ns = {"np": np}
+    exec(compile(src[start:end], "reference:Utils_.py", "exec"), ns)
+    return ns["EarlyStoppingScheduler"]
+
+
+class _Model(object):
+    def __init__(self):
+        self.log, self.stopped = [], False
+
+    def stop_fit(self):
+        self.stopped = True
+        self.log.append("stop")
+
+    def load_model(self):
+        self.log.append("load")
+
+    def save_current_model(self):
+        self.log.append("save")
+
+
+class _Evaluator(object):
+    def __init__(self, table):
+        self.table, self.i = table, 0
+
+    def evaluateRecommender(self, model):
+        row = self.table[self.i % len(self.table)]
+        self.i += 1
+        return {5: {"MAP": row[0], "NDCG": row[1], "PRECISION": row[2]}, 10: {"MAP": -1.0}}, ""
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_early_stopping_scheduler_matches_reference_source(seed):
+    from ganmf_b200.Utils_ import EarlyStoppingScheduler
+    RefScheduler = _reference_scheduler_class()
+    rs = np.random.RandomState(seed)
+    table = np.round(rs.uniform(0, 0.3, size=(30, 3)), 2 if seed % 2 else 1)      # coarse values: ties happen
+    if seed % 7 == 0:
+        table[:5] = 0.0                                                           # all-zero validations first
+    kw = dict(metrics=[["MAP"], ["MAP", "NDCG"], ["PRECISION", "MAP", "NDCG"]][seed % 3], freq=int(rs.randint(1, 4)),
+              allow_worse=int(rs.randint(0, 5)), after=int(rs.randint(0, 6)))
+    runs = []
+    for cls in (RefScheduler, EarlyStoppingScheduler):
+        model = _Model()
+        sched = cls(model, _Evaluator(table), **kw)
+        epoch = 1
+        while not model.stopped and epoch <= 60:
+            sched(epoch)
+            epoch += 1
+        runs.append((model.log, epoch, [list(map(float, s)) for s in sched.get_scores()],
+                     list(map(float, sched.best_scores)), sched.worse_left))
+    assert runs[0] == runs[1], kw
+
+
+class _Incr(object):
+    """Concrete recommender for the mixin: logs the hooks."""
+
+    def _setup(self, table):
+        self.table, self.i, self.log = table, 0, []
+
+    def _run_epoch(self, n):
+        self.log.append(("epoch", n))
+
+    def _prepare_model_for_validation(self):
+        self.log.append("prepare")
+
+    def _update_best_model(self):
+        self.log.append("best")
+
+    def evaluateRecommender(self, model):
+        v = self.table[self.i % len(self.table)]
+        self.i += 1
+        return {7: {"MAP": v}, 20: {"MAP": -1.0}}, ""
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_incremental_training_mixin_matches_reference(seed, reference_classes, capsys):
+    from Base.Incremental_Training_Early_Stopping import Incremental_Training_Early_Stopping as RefMixin
+    from ganmf_b200.Base.Incremental_Training_Early_Stopping import Incremental_Training_Early_Stopping as OurMixin
+    rs = np.random.RandomState(100 + seed)
+    table = np.round(rs.uniform(0, 0.3, size=25), 2 if seed % 2 else 1).tolist()
+    mode = seed % 3
+    kw = dict(epochs_max=int(rs.randint(1, 30)))
+    if mode >= 1:
+        kw.update(validation_every_n=int(rs.randint(1, 5)), validation_metric="MAP", stop_on_validation=False)
+    if mode == 2:
+        kw.update(stop_on_validation=True, lower_validations_allowed=int(rs.randint(1, 4)),
+                  epochs_min=int(rs.randint(0, kw["epochs_max"] + 1)))
+    runs = []
+    for mixin in (RefMixin, OurMixin):
+        cls = type("Rec", (_Incr, mixin), {})
+        rec = cls()
+        rec._setup(table)
+        ev = rec if mode >= 1 else None
+        try:
+            ret = rec._train_with_early_stopping(evaluator_object=ev, **kw)
+        except TypeError:
+            # the reference formats best_validation_metric=None when an evaluator is given but epochs_max is
+            # shorter than validation_every_n (Incremental_Training_Early_Stopping.py:255); nothing to compare
+            assert mixin is RefMixin
+            pytest.skip("reference crashes when no validation ever ran")
+        runs.append((rec.log, rec.epochs_best, rec.best_validation_metric, rec.get_early_stopping_final_epochs_dict()))
+        returned = ret
+    assert runs[0] == runs[1], kw
+    assert returned == len([e for e in runs[1][0] if isinstance(e, tuple)])        # ours also returns the epochs run
