@@ -124,6 +124,8 @@ def test_reference_oracle_and_host_side_agree(seed, reference_classes):
     ev = EvaluatorHoldout(test, cutoff_list=list(cutoffs), **opts)
     assert list(ev.usersToEvaluate) == ref_users
     got_h, txt = ev.evaluateRecommender(Rec())
+    from Base.Evaluation.Evaluator import get_result_string as ref_result_string
+    assert txt == ref_result_string(got_h)                                   # Evaluator.py:95-110, 7 decimals
     for c in cutoffs:
         assert list(got_h[c].keys()) == [k for k in want[c].keys()]          # same metric keys, same order
         for m, w in want[c].items():
