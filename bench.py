@@ -30,6 +30,16 @@ CFG4 = dict(name="cfg4: synthetic 138000x27000 d=0.5% GANMF-u k=250 E=1024 B=102
 HP = dict(d_lr=1e-4, g_lr=1e-4, d_reg=1e-4, g_reg=0.0, m=10.0, alpha=0.01)
 
 
+def workload(name, world=1):
+    """cfg4 (default, the workload of record: 138 000 users PER GPU) or --workload cfg5 (BASELINE.json configs[4]:
+    2 000 000 x 200 000 at 0.1 %, the users split over the ranks)."""
+    if name == "cfg5":
+        per = 2000000 // max(world, 1)
+        return dict(name="cfg5: synthetic 2000000x200000 d=0.1%% GANMF-u k=250 E=1024 B=1024/GPU, %d users per GPU" % per,
+                    users=per, items=200000, density=0.001, k=250, E=1024, B=1024)
+    return CFG4
+
+
 def synthetic_urm(n_users, n_items, density, seed):
     """Implicit interaction matrix: round(density*n_items) distinct uniform items per user."""
     rs = np.random.RandomState(seed)
@@ -172,7 +182,7 @@ def run_reference(args):
         return 0
     from oracle import train_oracle as to
     cores = use_all_host_threads()
-    c = CFG4
+    c = workload(args.workload)
     B = 256                                                   # bounded sample: 256-row minibatches
     n_users = 4096                                            # user-factor rows kept small: P is not the cost driver
     urm = synthetic_urm(n_users, c["items"], c["density"], 1337)
@@ -192,8 +202,8 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     v = B * args.steps / dt
-    sample = "NumPy restatement of the TF graph, %d steps of B=%d rows at 27000 items, k=250, E=1024 " \
-             "(user-factor table cut to %d rows)" % (args.steps, B, n_users)
+    sample = "NumPy restatement of the TF graph, %d steps of B=%d rows at %d items, k=250, E=1024 " \
+             "(user-factor table cut to %d rows)" % (args.steps, B, c["items"], n_users)
     line = {"impl": "reference", "metric": "GANMF-u train user-rows/s", "value": v, "unit": "rows/s", "n_gpus": 0,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -215,6 +225,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-users", type=int, default=8192)
     ap.add_argument("--quick", action="store_true", help="A/B runs: training throughput + GEMM roofline only")
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5"],
+                    help="cfg4 = workload of record (default); cfg5 = 2M x 200k split over the ranks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -237,7 +249,7 @@ def main():
     from ganmf_b200.engine import Engine
     from ganmf_b200.parallel import DataParallelTrainer
 
-    c = CFG4
+    c = workload(args.workload, world)
     K, W, B = args.steps, args.warmup, c["B"]
     urm = synthetic_urm(c["users"], c["items"], c["density"], 1337 + rank)      # this rank's user shard
     eng = Engine(L.KIND_GANMF, c["users"], c["items"], c["k"], emb_dim=c["E"], max_batch=B, device=local_rank)
@@ -493,8 +505,8 @@ def cpu_baseline(c):
         n += 1
     dt = time.perf_counter() - t0
     return {"value": B * n / dt, "unit": "rows/s", "cores": cores, "kind": "port",
-            "sample": "%d D+G steps of B=%d rows, 27000 items, k=250, E=1024 (NumPy/BLAS, all host threads; "
-                      "user-factor table cut to %d rows)" % (n, B, n_users),
+            "sample": "%d D+G steps of B=%d rows, %d items, k=250, E=1024 (NumPy/BLAS, all host threads; "
+                      "user-factor table cut to %d rows)" % (n, B, c["items"], n_users),
             "eval": cpu_eval_baseline(c)}
 
 
