@@ -84,7 +84,11 @@ class EvaluatorHoldout(Evaluator):
     def _device_sums(self, recommender_object, users):
         """(sums[n_cut, MC_NCOL], counts[n_cut, n_items]) over `users` in ascending order."""
         eng = getattr(recommender_object, "_engine", None)
-        URM_train = recommender_object.get_URM_train()
+        # popularity tables need the users x items matrix: an engine-backed item-mode model may hold URM_train
+        # transposed (after loadModel the reference leaves it so, GANMF.py:32-33,337-342)
+        URM_train = getattr(recommender_object, "_URM_users_items", None) if eng is not None else None
+        if URM_train is None:
+            URM_train = recommender_object.get_URM_train()
         block = min(1000, max(1, int(1e8 / self.n_items)))             # Evaluator.py:238
         score_fn = lambda u: recommender_object._compute_item_score(u)
         if self.ignore_items_flag:

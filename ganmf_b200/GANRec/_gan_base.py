@@ -65,6 +65,7 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
                   allow_worse, freq, after, metrics, sample_every, validation_evaluator, validation_set,
                   earlystopping_kwargs):
         eng = self._build_engine(batch_size)
+        self._has_best = False                     # a fresh engine holds no snapshot of an earlier fit()
         self._hp = dict(batch_size=int(batch_size), d_steps=int(d_steps), g_steps=int(g_steps), d_lr=float(d_lr),
                         g_lr=float(g_lr), d_reg=float(d_reg), g_reg=float(g_reg), m_hinge=float(m),
                         recon_coefficient=float(recon_coefficient))
@@ -80,6 +81,10 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
             return self.epochs_best
         early_stop = None
         if validation_evaluator is not None:
+            # the reference's shadow variables exist (randomly initialised) from graph construction
+            # (GANMF.py:123-128), so EarlyStoppingScheduler may call load_model() before any save_current_model():
+            # the freshly initialised weights are the first snapshot
+            eng.snapshot()
             early_stop = EarlyStoppingScheduler(self, evaluator=validation_evaluator, allow_worse=allow_worse,
                                                 freq=freq, metrics=metrics, after=after)
         epoch = 1

@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libganmf_b200.so")
 
-KIND_GANMF, KIND_DISGANMF = 0, 1
+KIND_GANMF, KIND_DISGANMF, KIND_MF = 0, 1, 2
 ACT = {"linear": 0, None: 0, "tanh": 1, "relu": 2, "sigmoid": 3}
 CSR_TRAIN, CSR_SEEN, CSR_TEST = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
@@ -23,7 +23,8 @@ TOPK_MAX = 128
 class Config(C.Structure):
     _fields_ = [(n, C.c_int) for n in
                 ("kind", "n_rows", "width", "num_factors", "emb_dim", "d_layers", "d_nodes", "d_act",
-                 "max_batch", "item_mode", "row_id_offset", "device", "gemm_path")]
+                 "max_batch", "item_mode", "row_id_offset", "device", "gemm_path",
+                 "global_width", "item_offset", "tp_rank", "tp_world")]
 
 
 _i32p = C.POINTER(C.c_int32)
@@ -41,6 +42,7 @@ SIGNATURES = {
     "ganmf_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "ganmf_synchronize": (C.c_int, [_ctx]),
     "ganmf_set_csr": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f32p]),
+    "ganmf_set_csr_device": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "ganmf_param_count": (C.c_int, [_ctx]),
     "ganmf_param_info": (C.c_int, [_ctx, C.c_int, C.c_char_p, C.c_int, _i32p, _i32p, _i32p]),
     "ganmf_set_param": (C.c_int, [_ctx, C.c_char_p, _f32p, C.c_int64]),
@@ -63,6 +65,9 @@ SIGNATURES = {
     "ganmf_d_forward_phase": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int]),
     "ganmf_set_gemm_sms": (C.c_int, [_ctx, C.c_int]),
     "ganmf_finalize_loss": (C.c_int, [_ctx, C.c_float, C.c_int]),
+    "ganmf_tp_d_phase": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]),
+    "ganmf_tp_g_phase": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]),
+    "ganmf_device_buffer_ld": (C.c_int, [_ctx, C.c_char_p, _i32p]),
     "ganmf_train_epoch": (C.c_int, [_ctx, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                     C.c_float, C.c_float, C.c_float, C.c_float, _f32p, _f32p]),
     "ganmf_read_losses": (C.c_int, [_ctx, _f32p, C.c_int]),
@@ -71,7 +76,7 @@ SIGNATURES = {
     "ganmf_encode": (C.c_int, [_ctx, _i32p, C.c_int, _f32p]),
     "ganmf_mask_topk": (C.c_int, [_ctx, _f32p, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _i32p, _f32p, C.c_int]),
     "ganmf_recommend": (C.c_int, [_ctx, _i32p, C.c_int, C.c_int, C.c_int, _i32p, _f32p, _f32p]),
-    "ganmf_set_eval_tables": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, _f64p, _u8p, _f64p]),
+    "ganmf_set_eval_tables": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, _f64p, _u8p, _f64p, C.c_int]),
     "ganmf_evaluate": (C.c_int, [_ctx, _i32p, C.c_int, _i32p, C.c_int, C.c_int, C.c_int, _f64p, _i64p]),
     "ganmf_eval_begin": (C.c_int, [_ctx, C.c_int, _i32p, C.c_int]),
     "ganmf_eval_scores_block": (C.c_int, [_ctx, _f32p, _i32p, C.c_int, C.c_int, C.c_int]),

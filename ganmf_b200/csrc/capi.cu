@@ -51,6 +51,9 @@ struct Param {
   Mat w;                       // view into the optimiser group's slab
   float *m = nullptr, *v = nullptr, *g = nullptr, *best = nullptr;
   int is_gen = 0;
+  // item-sharded contexts: position of this slice inside the whole tensor (glorot init draws the SAME values a
+  // single-GPU context would, so sharded and unsharded runs start from one model)
+  int row_off = 0, col_off = 0, rows_g = 0, cols_g = 0;
 };
 struct Csr {
   int* indptr = nullptr;
@@ -72,6 +75,9 @@ struct ganmf_ctx {
   bool have_best = false;
   // activations / workspaces
   int B = 0, W = 0, Wp = 0, k = 0, kp = 0, E = 0, Ep = 0;
+  int Wg = 0;                          // columns of the WHOLE training matrix (= W unless item-sharded)
+  int tp_rank = 0, tp_world = 1;       // item-sharded group
+  float tp_g_alpha = 0.f;
   Mat X2, H2, H2s, Res2, dH2, dF, Pb, dPb;
   // DisGANMF: per layer activations h[l] [2B, Hp], dz [2B, Hp], out2/dout2 [2B]
   std::vector<Mat> hs, dzs;
@@ -222,13 +228,20 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
 }
 
 // ------------------------------------------------------------------------------ create/destroy
-static void add_param(ganmf_ctx* c, const char* name, int rows, int cols, int is_gen) {
+// sliced: 0 = whole tensor, 1 = rows are items (slice of the rows), 2 = columns are items
+static void add_param(ganmf_ctx* c, const char* name, int rows, int cols, int is_gen, int sliced = 0) {
   Param p;
   p.name = name;
   p.w.rows = rows; p.w.cols = cols; p.w.ld = rup(cols, 32);
   p.is_gen = is_gen;
+  p.rows_g = sliced == 1 ? c->Wg : rows;
+  p.cols_g = sliced == 2 ? c->Wg : cols;
+  p.row_off = sliced == 1 ? c->cfg.item_offset : 0;
+  p.col_off = sliced == 2 ? c->cfg.item_offset : 0;
   c->params.push_back(p);
 }
+
+static int create_buffers(ganmf_ctx* c);
 
 int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   if (!cfg || !out) return fail("null argument");
@@ -248,13 +261,26 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   if (const char* lc = getenv("GANMF_LAZY_LOG_CAP")) c->log_cap = std::max(1, atoi(lc)); // tests: force log wrap
   c->B = cfg->max_batch; c->W = cfg->width; c->Wp = rup(cfg->width, 32);
   c->k = cfg->num_factors; c->kp = rup(c->k, 32);
+  c->Wg = cfg->global_width > 0 ? cfg->global_width : cfg->width;
+  c->tp_world = cfg->tp_world > 1 ? cfg->tp_world : 1;
+  c->tp_rank = c->tp_world > 1 ? cfg->tp_rank : 0;
+  if (c->tp_world > 1 && (cfg->kind != GANMF_KIND_GANMF || cfg->item_mode || cfg->tp_rank < 0 ||
+                          cfg->tp_rank >= c->tp_world || cfg->item_offset < 0 ||
+                          cfg->item_offset + cfg->width > c->Wg)) {
+    delete c;
+    return fail("item-sharded contexts: GANMF --user only, 0 <= tp_rank < tp_world, slice inside global_width");
+  }
+  if (c->tp_world == 1 && (c->Wg != c->W || cfg->item_offset != 0)) { delete c; return fail("global_width / item_offset need tp_world > 1"); }
+  const int sl = c->tp_world > 1;
   if (cfg->kind == GANMF_KIND_GANMF) {
     if (cfg->emb_dim <= 0) { delete c; return fail("emb_dim must be > 0"); }
     c->E = cfg->emb_dim; c->Ep = rup(c->E, 32);
-    add_param(c, "autoencoder/encoding/kernel", c->W, c->E, 0);
+    add_param(c, "autoencoder/encoding/kernel", c->W, c->E, 0, sl ? 1 : 0);
     add_param(c, "autoencoder/encoding/bias", 1, c->E, 0);
-    add_param(c, "autoencoder/decoding/kernel", c->E, c->W, 0);
-    add_param(c, "autoencoder/decoding/bias", 1, c->W, 0);
+    add_param(c, "autoencoder/decoding/kernel", c->E, c->W, 0, sl ? 2 : 0);
+    add_param(c, "autoencoder/decoding/bias", 1, c->W, 0, sl ? 2 : 0);
+  } else if (cfg->kind == GANMF_KIND_MF) {
+    c->E = 1; c->Ep = 32;                 // no discriminator: factor matrices only
   } else if (cfg->kind == GANMF_KIND_DISGANMF) {
     if (cfg->d_layers < 1 || cfg->d_nodes < 1) { delete c; return fail("bad discriminator shape"); }
     c->E = cfg->d_nodes; c->Ep = rup(c->E, 32);
@@ -275,8 +301,16 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   }
   c->n_d = (int)c->params.size();
   add_param(c, "generator/user_embeddings", cfg->n_rows, c->k, 1);
-  add_param(c, "generator/item_embeddings", c->W, c->k, 1);
+  add_param(c, "generator/item_embeddings", c->W, c->k, 1, sl ? 1 : 0);
 
+  const int rc_alloc = create_buffers(c);
+  if (rc_alloc) { ganmf_destroy(c); return rc_alloc; }     // nothing allocated so far is leaked
+  *out = c;
+  return 0;
+}
+
+static int create_buffers(ganmf_ctx* c) {
+  const ganmf_config* cfg = &c->cfg;
   // discriminator slab: theta | m | v | grad | best, each d_elems floats, tensors back to back
   for (int i = 0; i < c->n_d; ++i) c->d_elems += c->params[i].w.elems();
   RC(dalloc(&c->d_slab, 5 * c->d_elems));
@@ -309,9 +343,9 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   if (cfg->kind == GANMF_KIND_GANMF) {
     RC(mat_alloc(&c->H2, 2 * B, c->E));
     RC(mat_alloc(&c->H2s, 2 * B, c->E));
-    RC(mat_alloc(&c->dH2, 2 * B, c->E));
+    RC(mat_alloc(&c->dH2, 2 * B + 1, c->E));      // + one row: partial encoder-bias gradient of an item-sharded step
     RC(mat_alloc(&c->Res2, 2 * B, c->W));
-  } else {
+  } else if (cfg->kind == GANMF_KIND_DISGANMF) {
     c->hs.resize(cfg->d_layers);
     c->dzs.resize(cfg->d_layers);
     for (int l = 0; l < cfg->d_layers; ++l) {
@@ -336,7 +370,6 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   fill_int_kernel<<<(cfg->n_rows + 255) / 256, 256>>>(c->slot, -1, (size_t)cfg->n_rows);
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
-  *out = c;
   return 0;
 }
 
@@ -438,6 +471,29 @@ int ganmf_set_csr(ganmf_ctx* c, int which, int n_rows, int n_cols, const int32_t
   return 0;
 }
 
+int ganmf_set_csr_device(ganmf_ctx* c, int which, int n_rows, int n_cols, const int32_t* indptr_dev,
+                         const int32_t* indices_dev, const float* data_dev, int64_t nnz) {
+  if (!c || which < 0 || which > 2 || !indptr_dev || nnz < 0 || (nnz > 0 && !indices_dev)) return fail("bad argument");
+  if (which == GANMF_CSR_TRAIN && (n_rows != c->cfg.n_rows || n_cols != c->W))
+    return fail("train CSR is %dx%d, context expects %dx%d", n_rows, n_cols, c->cfg.n_rows, c->W);
+  int last = 0;
+  CU(cudaMemcpy(&last, indptr_dev + n_rows, 4, cudaMemcpyDeviceToHost));
+  if ((int64_t)last != nnz) return fail("indptr[n_rows] = %d but nnz = %lld", last, (long long)nnz);
+  Csr& m = c->csr[which];
+  csr_free(m);
+  m.n_rows = n_rows; m.n_cols = n_cols; m.nnz = nnz;
+  RC(dalloc(&m.indptr, (size_t)n_rows + 1));
+  RC(dalloc(&m.indices, (size_t)nnz));
+  CU(cudaMemcpy(m.indptr, indptr_dev, ((size_t)n_rows + 1) * 4, cudaMemcpyDeviceToDevice));
+  if (nnz) CU(cudaMemcpy(m.indices, indices_dev, (size_t)nnz * 4, cudaMemcpyDeviceToDevice));
+  if (data_dev) {
+    RC(dalloc(&m.data, (size_t)nnz));
+    if (nnz) CU(cudaMemcpy(m.data, data_dev, (size_t)nnz * 4, cudaMemcpyDeviceToDevice));
+  }
+  if (which == GANMF_CSR_TEST) c->have_tables = false;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ lazy user factors
 // Replay the deferred zero-gradient Adam steps: for the rows in ids (device), or for every row.
 static int p_catchup(ganmf_ctx* c, const int* ids_dev, int n) {
@@ -497,11 +553,14 @@ int ganmf_get_param(ganmf_ctx* c, const char* name, float* host, int64_t count) 
 }
 
 // counter-based uniform generator (splitmix64 finaliser): U(-lim, lim) on the real columns only
-__global__ void glorot_kernel(float* w, int rows, int cols, int ld, float lim, unsigned long long seed) {
+// (element (r, cc) of a slice draws the value of element (r + row_off, cc + col_off) of the whole tensor)
+__global__ void glorot_kernel(float* w, int rows, int cols, int ld, float lim, unsigned long long seed,
+                              int row_off, int col_off, int cols_g) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * cols) return;
   const int r = (int)(i / cols), cc = (int)(i % cols);
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+  const unsigned long long ig = (unsigned long long)(r + row_off) * (unsigned long long)cols_g + (cc + col_off);
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (ig + 1);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z ^= z >> 31;
@@ -515,10 +574,11 @@ int ganmf_init_params(ganmf_ctx* c, uint64_t seed) {
   for (auto& p : c->params) {
     CU(cudaMemsetAsync(p.w.p, 0, p.w.elems() * 4, c->st));
     if (p.w.rows > 1 || p.name.find("kernel") != std::string::npos) {     // matrices; biases stay zero
-      const float lim = sqrtf(6.0f / (float)(p.w.rows + p.w.cols));
+      const float lim = sqrtf(6.0f / (float)(p.rows_g + p.cols_g));
       const size_t n = (size_t)p.w.rows * p.w.cols;
       glorot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(p.w.p, p.w.rows, p.w.cols, p.w.ld, lim,
-                                                                   seed * 1000003ull + 7919ull * (++i));
+                                                                   seed * 1000003ull + 7919ull * (++i), p.row_off,
+                                                                   p.col_off, p.cols_g);
       CU(cudaGetLastError());
       c->launches++;
     }
@@ -559,6 +619,8 @@ int ganmf_restore(ganmf_ctx* c) {
 // ------------------------------------------------------------------------------ training
 int ganmf_upload_ids(ganmf_ctx* c, const int32_t* ids, int n) {
   if (!c || n < 0 || n > c->ids_cap) return fail("upload_ids: n=%d exceeds capacity %d", n, c ? c->ids_cap : 0);
+  for (int i = 0; i < n; ++i)              // the gather / optimiser kernels index with these unchecked
+    if (ids[i] < 0 || ids[i] >= c->cfg.n_rows) return fail("row id %d at position %d outside [0, %d)", ids[i], i, c->cfg.n_rows);
   CU(cudaMemcpyAsync(c->ids, ids, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
   return 0;
 }
@@ -571,8 +633,11 @@ static float adam_alpha(ganmf_ctx* c, int which, float lr) {
   return a;
 }
 
-static int check_batch(ganmf_ctx* c, int ids_offset, int B) {
+static int check_batch(ganmf_ctx* c, int ids_offset, int B, bool tp_call = false) {
   if (!c) return fail("null ctx");
+  if (c->cfg.kind == GANMF_KIND_MF) return fail("a factor-only (GANMF_KIND_MF) context does not train");
+  if (c->tp_world > 1 && !tp_call)
+    return fail("item-sharded context: use ganmf_tp_d_phase / ganmf_tp_g_phase (partial sums must be all-reduced)");
   if (B <= 0 || B > c->B) return fail("batch %d outside (0, %d]", B, c->B);
   if (ids_offset < 0 || ids_offset + B > c->ids_cap) return fail("ids range out of bounds");
   if (!c->csr[GANMF_CSR_TRAIN].indptr) return fail("train CSR not set");
@@ -641,7 +706,7 @@ static int ganmf_d_backward_impl(ganmf_ctx* c, int B, int n_global, float m_hing
   const float* rs = c->sc->row_scale;
   if (phase >= 2) goto second_half;
   {
-  const double n_elems = (double)n_global * c->W;
+  const double n_elems = (double)n_global * c->Wg;
   hinge_gate_kernel<<<1, 1, 0, c->st>>>(c->sc, m_hinge, n_elems);
   CU(cudaGetLastError());
   scale_rows_kernel<<<dim3(std::max(1, c->H2.ld / 4 / 128), 2 * B), 128, 0, c->st>>>(
@@ -683,7 +748,7 @@ static int ganmf_d_backward_apply_fused(ganmf_ctx* c, int B, int n_global, float
   if (loss_slot < 0 || loss_slot >= c->losses_cap) return fail("loss slot out of range");
   Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
   const float* rs = c->sc->row_scale;
-  hinge_gate_kernel<<<1, 1, 0, c->st>>>(c->sc, m_hinge, (double)n_global * c->W);
+  hinge_gate_kernel<<<1, 1, 0, c->st>>>(c->sc, m_hinge, (double)n_global * c->Wg);
   CU(cudaGetLastError());
   scale_rows_kernel<<<dim3(std::max(1, c->H2.ld / 4 / 128), 2 * B), 128, 0, c->st>>>(
       c->H2.p, c->H2s.p, c->H2.ld / 4, rs, B);
@@ -758,7 +823,7 @@ static int ganmf_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, fl
   RC(gemm(c, c->H2.row(B), c->H2.ld, 0, Wd->w.p, Wd->w.ld, 1, B, c->W, c->E, e3));
   sqdiff_kernel<<<std::min(B, 296), 256, 0, c->st>>>(c->H2.p, c->H2.row(B), B, c->E, c->H2.ld, &c->sc->fm);
   CU(cudaGetLastError());
-  const double N = (double)n_global * c->W, M = (double)n_global * c->E;
+  const double N = (double)n_global * c->Wg, M = (double)n_global * c->E;
   const float c1 = (float)((1.0 - alpha) * 2.0 / N), c2 = (float)(alpha * 2.0 / M);
   Epilogue e5;                                                                     // G5': dHf
   e5.out = c->dH2.row(B); e5.ldo = c->dH2.ld; e5.alpha = c1;
@@ -794,7 +859,7 @@ static int g_apply_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float
                         int loss_slot, bool v_done = false, float adam_step = 0.f) {
   if (loss_slot < 0 || loss_slot >= c->losses_cap) return fail("loss slot out of range");
   if (c->cfg.kind == GANMF_KIND_GANMF)
-    gloss_kernel<<<1, 1, 0, c->st>>>(c->sc, alpha, (double)n_global * c->W, (double)n_global * c->E);
+    gloss_kernel<<<1, 1, 0, c->st>>>(c->sc, alpha, (double)n_global * c->Wg, (double)n_global * c->E);
   else
     dis_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, 1, alpha, (double)n_global, (double)n_global * c->E);
   CU(cudaGetLastError());
@@ -826,7 +891,7 @@ static int g_apply_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float
     CU(cudaGetLastError());
     c->launches += 4;
   }
-  if (n_global == B) {       // under data parallelism the caller sums l2_shard over ranks first
+  if (n_global == B && c->tp_world == 1) {       // under data / item parallelism the caller sums the l2 terms over ranks first
     finalize_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, reg, c->losses, loss_slot);
     CU(cudaGetLastError());
     c->launches++;
@@ -963,6 +1028,134 @@ static int dis_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, floa
   return gemm(c, c->dF.p, c->dF.ld, 0, V.w.p, V.w.ld, 1, B, c->k, c->W, e9);
 }
 
+// ---- item-sharded GANMF ------------------------------------------------------------
+// Every rank runs the WHOLE minibatch on its item slice: X2 = [R ; F][:, slice], We[slice, :], Wd[:, slice],
+// V[slice, :].  Contractions over items (codes H = X.We, dH = Res.Wd^T, dPb = dF.V, dbe = Wd.dbd) are partial
+// sums the caller all-reduces; everything indexed by items (residuals, dWe, dWd, dbd, dV and their Adam
+// updates) is local, so no weight or weight-gradient ever crosses NVLink -- only [2B, E] / [B, k] activations.
+static int tp_check(ganmf_ctx* c, int ids_offset, int B) {
+  if (!c) return fail("null ctx");
+  if (c->tp_world <= 1) return fail("not an item-sharded context (config.tp_world <= 1)");
+  return check_batch(c, ids_offset, B, true);
+}
+// profiles + generator + partial codes (the bias joins the sum once: on rank 0)
+static int tp_forward_codes(ganmf_ctx* c, int ids_offset, int B) {
+  RC(forward_generator(c, ids_offset, B));
+  Param *We = &c->params[0], *be = &c->params[1];
+  CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
+  Epilogue e2;                                                                     // G2 (partial over items)
+  e2.out = c->H2.p; e2.ldo = c->H2.ld; e2.bias = c->tp_rank == 0 ? be->w.p : nullptr;
+  return gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, 2 * B, c->E, c->W, e2);
+}
+
+int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, float reg, float m_hinge) {
+  RC(tp_check(c, ids_offset, B));
+  Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
+  const float* rs = c->sc->row_scale;
+  switch (phase) {
+    case 1:
+      return tp_forward_codes(c, ids_offset, B);
+    case 2: {                                                                      // G3 on the summed codes
+      Epilogue e3;
+      e3.out = c->Res2.p; e3.ldo = c->Res2.ld; e3.bias = bd->w.p;
+      e3.c1 = c->X2.p; e3.ldc1 = c->X2.ld; e3.beta1 = -1.f;
+      e3.sumsq2 = c->sc->sumsq; e3.row_split = B;
+      return gemm(c, c->H2.p, c->H2.ld, 0, Wd->w.p, Wd->w.ld, 1, 2 * B, c->W, c->E, e3);
+    }
+    case 3: {                                                                      // gate (global sums), dbd, partial dH | dbe
+      hinge_gate_kernel<<<1, 1, 0, c->st>>>(c->sc, m_hinge, (double)B * c->Wg);
+      CU(cudaGetLastError());
+      scale_rows_kernel<<<dim3(std::max(1, c->H2.ld / 4 / 128), 2 * B), 128, 0, c->st>>>(
+          c->H2.p, c->H2s.p, c->H2.ld / 4, rs, B);
+      CU(cudaGetLastError());
+      colsum_kernel<<<(c->W + 31) / 32, dim3(32, 8), 0, c->st>>>(c->Res2.p, 2 * B, c->W, c->Res2.ld, rs, B,
+                                                                nullptr, bd->g);
+      CU(cudaGetLastError());
+      rowdot_kernel<<<c->E, 256, 0, c->st>>>(Wd->w.p, c->E, c->W, Wd->w.ld, bd->g, c->dH2.row(2 * B));
+      CU(cudaGetLastError());
+      c->launches += 4;
+      Epilogue e5;                                                                 // G5 (partial over items)
+      e5.out = c->dH2.p; e5.ldo = c->dH2.ld; e5.row_scale2 = rs; e5.row_split = B;
+      return gemm(c, c->Res2.p, c->Res2.ld, 0, Wd->w.p, Wd->w.ld, 0, 2 * B, c->E, c->W, e5);
+    }
+    case 4: {                                                                      // local weight gradients + Adam
+      CU(cudaMemcpyAsync(be->g, c->dH2.row(2 * B), (size_t)be->w.ld * 4, cudaMemcpyDeviceToDevice, c->st));
+      const float alpha = adam_alpha(c, 0, lr);
+      Epilogue e4;                                                                 // G4: dWd[:, slice] -> Adam
+      e4.out = Wd->w.p; e4.ldo = Wd->w.ld;
+      e4.adam_m = Wd->m; e4.adam_v = Wd->v; e4.adam_alpha = alpha; e4.adam_reg = reg; e4.adam_l2 = &c->sc->l2;
+      RC(gemm(c, c->H2s.p, c->H2s.ld, 1, c->Res2.p, c->Res2.ld, 1, c->E, c->W, 2 * B, e4));
+      Epilogue e6;                                                                 // G6: dWe[slice, :] -> Adam
+      e6.out = We->w.p; e6.ldo = We->w.ld;
+      e6.adam_m = We->m; e6.adam_v = We->v; e6.adam_alpha = alpha; e6.adam_reg = reg; e6.adam_l2 = &c->sc->l2;
+      RC(gemm(c, c->X2.p, c->X2.ld, 1, c->dH2.p, c->dH2.ld, 1, c->W, c->E, 2 * B, e6));
+      // biases: bd is a slice, be is replicated (every rank applies the same update; its l2 counts once)
+      Param* bs[2] = {be, bd};
+      for (int i = 0; i < 2; ++i) {
+        AdamArgs a;
+        memset(&a, 0, sizeof a);
+        a.nseg = 1;
+        a.seg[0].theta = bs[i]->w.p; a.seg[0].m = bs[i]->m; a.seg[0].v = bs[i]->v; a.seg[0].g = bs[i]->g;
+        a.seg[0].ld = bs[i]->w.ld; a.seg[0].n4 = bs[i]->w.elems() / 4;
+        a.alpha = alpha; a.reg = reg;
+        a.l2_out = (i == 1 || c->tp_rank == 0) ? &c->sc->l2 : nullptr;
+        CU(fused_adam(a, c->st));
+      }
+      c->launches += 2;
+      return 0;
+    }
+    default:
+      return fail("ganmf_tp_d_phase: phase must be 1..4");
+  }
+}
+
+int ganmf_tp_g_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, float reg, float alpha) {
+  RC(tp_check(c, ids_offset, B));
+  Param *We = &c->params[0], *Wd = &c->params[2], *bd = &c->params[3];
+  Param& V = c->params[c->n_d + 1];
+  const double N = (double)B * c->Wg, M = (double)B * c->E;
+  const float c1 = (float)((1.0 - alpha) * 2.0 / N), c2 = (float)(alpha * 2.0 / M);
+  switch (phase) {
+    case 1:
+      return tp_forward_codes(c, ids_offset, B);
+    case 2: {
+      Epilogue e3;                                                                 // G3': fake residual (slice)
+      e3.out = c->Res2.row(B); e3.ldo = c->Res2.ld; e3.bias = bd->w.p;
+      e3.c1 = c->X2.row(B); e3.ldc1 = c->X2.ld; e3.beta1 = -1.f;
+      e3.sumsq2 = c->sc->sumsq;
+      RC(gemm(c, c->H2.row(B), c->H2.ld, 0, Wd->w.p, Wd->w.ld, 1, B, c->W, c->E, e3));
+      // feature matching on the summed codes: the same on every rank, NOT summed again
+      sqdiff_kernel<<<std::min(B, 296), 256, 0, c->st>>>(c->H2.p, c->H2.row(B), B, c->E, c->H2.ld, &c->sc->fm);
+      CU(cudaGetLastError());
+      c->launches += 1;
+      Epilogue e5;                                                                 // G5': dHf (partial; the
+      e5.out = c->dH2.row(B); e5.ldo = c->dH2.ld; e5.alpha = c1;                  //  feature-matching term joins once)
+      if (c->tp_rank == 0) {
+        e5.c1 = c->H2.row(B); e5.ldc1 = c->H2.ld; e5.beta1 = c2;
+        e5.c2 = c->H2.p; e5.ldc2 = c->H2.ld; e5.beta2 = -c2;
+      }
+      return gemm(c, c->Res2.row(B), c->Res2.ld, 0, Wd->w.p, Wd->w.ld, 0, B, c->E, c->W, e5);
+    }
+    case 3: {
+      Epilogue e7;                                                                 // G7: dF (slice)
+      e7.out = c->dF.p; e7.ldo = c->dF.ld;
+      e7.c1 = c->Res2.row(B); e7.ldc1 = c->Res2.ld; e7.beta1 = -c1;
+      RC(gemm(c, c->dH2.row(B), c->dH2.ld, 0, We->w.p, We->w.ld, 0, B, c->W, c->E, e7));
+      Epilogue e9;                                                                 // G9: dPb (partial over items)
+      e9.out = c->dPb.p; e9.ldo = c->dPb.ld;
+      RC(gemm(c, c->dF.p, c->dF.ld, 0, V.w.p, V.w.ld, 1, B, c->k, c->W, e9));
+      Epilogue e8;                                                                 // G8: dV (slice)
+      e8.out = V.g; e8.ldo = V.w.ld;
+      return gemm(c, c->dF.p, c->dF.ld, 1, c->Pb.p, c->Pb.ld, 1, c->W, c->k, B, e8);
+    }
+    case 4:
+      c->last_ids_offset = ids_offset;
+      return g_apply_impl(c, ids_offset, B, B, lr, reg, alpha, 0);
+    default:
+      return fail("ganmf_tp_g_phase: phase must be 1..4");
+  }
+}
+
 // ---- public step API -------------------------------------------------------------------------
 int ganmf_d_forward(ganmf_ctx* c, int ids_offset, int B) {
   RC(check_batch(c, ids_offset, B));
@@ -1064,6 +1257,20 @@ int ganmf_finalize_loss(ganmf_ctx* c, float reg, int loss_slot) {
   return 0;
 }
 
+// the device-side loss log grows on demand (the reference has no limit on batches per epoch)
+static int ensure_losses(ganmf_ctx* c, long long n) {
+  if (n <= c->losses_cap) return 0;
+  if (n > (1LL << 30)) return fail("loss log of %lld entries", n);
+  CU(cudaStreamSynchronize(c->st));
+  float* bigger = nullptr;
+  RC(dalloc(&bigger, (size_t)n));
+  CU(cudaMemcpy(bigger, c->losses, (size_t)c->losses_cap * 4, cudaMemcpyDeviceToDevice));
+  cudaFree(c->losses);
+  c->losses = bigger;
+  c->losses_cap = (int)n;
+  return 0;
+}
+
 int ganmf_read_losses(ganmf_ctx* c, float* host, int n) {
   if (!c || n < 0 || n > c->losses_cap) return fail("bad loss count");
   CU(cudaMemcpyAsync(host, c->losses, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
@@ -1077,7 +1284,7 @@ int ganmf_train_epoch(ganmf_ctx* c, const int32_t* perm, int n_ids, int batch, i
   if (!c || !perm || n_ids <= 0 || batch <= 0) return fail("bad argument");
   if (batch > c->B) return fail("batch_size %d exceeds max_batch %d", batch, c->B);
   const int nb = (n_ids + batch - 1) / batch;
-  if ((long long)nb * (d_steps + g_steps) > c->losses_cap) return fail("loss log too small");
+  RC(ensure_losses(c, (long long)nb * (d_steps + g_steps)));
   RC(ganmf_upload_ids(c, perm, n_ids));
   int slot = 0;
   for (int s = 0; s < d_steps; ++s)
@@ -1116,7 +1323,26 @@ int ganmf_device_buffer(ganmf_ctx* c, const char* name, void** ptr, int64_t* n) 
   }
   if (!strcmp(name, "g_shared_grad")) { *ptr = c->v_slab + 3 * c->v_elems; *n = (int64_t)c->v_elems; return 0; }
   if (!strcmp(name, "step_scalars")) { *ptr = c->sc; *n = 7; return 0; }
+  if (!strcmp(name, "tp_h2")) { *ptr = c->H2.p; *n = (int64_t)c->H2.elems(); return 0; }
+  if (!strcmp(name, "tp_dh2")) { *ptr = c->dH2.p; *n = (int64_t)c->dH2.elems(); return 0; }
+  if (!strcmp(name, "tp_dpb")) { *ptr = c->dPb.p; *n = (int64_t)c->dPb.elems(); return 0; }
+  if (!strcmp(name, "user_factors")) {
+    RC(p_flush(c));                          // deferred optimiser steps first: the caller reads the matrix
+    *ptr = c->params[c->n_d].w.p; *n = (int64_t)c->params[c->n_d].w.elems(); return 0;
+  }
+  if (!strcmp(name, "item_factors")) {
+    *ptr = c->params[c->n_d + 1].w.p; *n = (int64_t)c->params[c->n_d + 1].w.elems(); return 0;
+  }
   return fail("unknown buffer %s", name);
+}
+int ganmf_device_buffer_ld(ganmf_ctx* c, const char* name, int* ld) {
+  if (!c || !name || !ld) return fail("null argument");
+  if (!strcmp(name, "tp_h2")) { *ld = c->H2.ld; return 0; }
+  if (!strcmp(name, "tp_dh2")) { *ld = c->dH2.ld; return 0; }
+  if (!strcmp(name, "tp_dpb")) { *ld = c->dPb.ld; return 0; }
+  if (!strcmp(name, "user_factors")) { *ld = c->params[c->n_d].w.ld; return 0; }
+  if (!strcmp(name, "item_factors")) { *ld = c->params[c->n_d + 1].w.ld; return 0; }
+  return fail("no leading dimension for buffer %s", name);
 }
 
 // ------------------------------------------------------------------------------ scoring / eval
@@ -1314,12 +1540,14 @@ static int upload(T** dev, const T* host, size_t n) {
 }
 
 int ganmf_set_eval_tables(ganmf_ctx* c, const float* gain, const float* gain_desc, const float* logtab,
-                          int logtab_n, const double* nov, const uint8_t* haspop, const double* popn) {
+                          int logtab_n, const double* nov, const uint8_t* haspop, const double* popn, int n_items_tables) {
   if (!c) return fail("null ctx");
   const Csr& te = c->csr[GANMF_CSR_TEST];
   if (!te.indptr) return fail("test CSR not set");
   if (logtab_n < TK_MAXK) return fail("logtab needs >= %d entries", TK_MAXK);
   const int n_items = te.n_cols;
+  if (n_items_tables != n_items)
+    return fail("per-item tables have %d entries, the test matrix has %d columns", n_items_tables, n_items);
   RC(upload(&c->tb_gain, gain, (size_t)te.nnz));
   RC(upload(&c->tb_gain_desc, gain_desc, (size_t)te.nnz));
   RC(upload(&c->tb_logtab, logtab, (size_t)logtab_n));

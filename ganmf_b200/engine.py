@@ -19,12 +19,16 @@ class DeviceArray(object):
 
 class Engine(object):
     def __init__(self, kind, n_rows, width, num_factors, emb_dim=0, d_layers=0, d_nodes=0, d_act="linear",
-                 max_batch=32, item_mode=False, row_id_offset=0, device=0, gemm_path=L.GEMM_AUTO):
+                 max_batch=32, item_mode=False, row_id_offset=0, device=0, gemm_path=L.GEMM_AUTO,
+                 global_width=0, item_offset=0, tp_rank=0, tp_world=0):
+        """global_width / item_offset / tp_rank / tp_world: item-sharded training (parallel.ItemShardedTrainer);
+        this engine then holds columns [item_offset, item_offset + width) of the training matrix."""
         self.lib = L.load()
         cfg = L.Config(kind=kind, n_rows=int(n_rows), width=int(width), num_factors=int(num_factors),
                        emb_dim=int(emb_dim), d_layers=int(d_layers), d_nodes=int(d_nodes), d_act=L.ACT[d_act],
                        max_batch=int(max_batch), item_mode=int(bool(item_mode)), row_id_offset=int(row_id_offset),
-                       device=int(device), gemm_path=int(gemm_path))
+                       device=int(device), gemm_path=int(gemm_path), global_width=int(global_width),
+                       item_offset=int(item_offset), tp_rank=int(tp_rank), tp_world=int(tp_world))
         self.cfg = cfg
         self.ctx = L._ctx()
         L.check(self.lib.ganmf_create(C.byref(cfg), C.byref(self.ctx)))
@@ -78,12 +82,17 @@ class Engine(object):
         L.check(self.lib.ganmf_device_buffer(self.ctx, name.encode(), C.byref(ptr), C.byref(n)))
         return DeviceArray(ptr.value, n.value, "<f8" if name == "step_scalars" else "<f4")
 
+    def device_buffer_ld(self, name):
+        ld = C.c_int32()
+        L.check(self.lib.ganmf_device_buffer_ld(self.ctx, name.encode(), C.byref(ld)))
+        return ld.value
+
     # ------------------------------------------------------------------ data
     def set_csr(self, which, m, with_data=True):
         m = sps.csr_matrix(m)
-        if not m.has_sorted_indices:
+        if not m.has_canonical_format:             # URM[uids].toarray() SUMS duplicate (row, col) entries
             m = m.copy()
-            m.sort_indices()
+            m.sum_duplicates()                     # (also sorts the indices of every row)
         _, ip = L.i32(m.indptr)
         idx, ix = L.i32(m.indices)
         if with_data:
@@ -92,6 +101,14 @@ class Engine(object):
             dp = None
         L.check(self.lib.ganmf_set_csr(self.ctx, which, m.shape[0], m.shape[1], ip, ix, dp))
         return m
+
+    def set_csr_device(self, which, n_rows, n_cols, indptr, indices, data=None):
+        """CSR already on the device (torch int32 / float32 tensors or anything with data_ptr()); indices of a row
+        sorted and unique.  Copied device-to-device; the caller may free its arrays afterwards."""
+        nnz = int(indices.numel())
+        L.check(self.lib.ganmf_set_csr_device(self.ctx, which, int(n_rows), int(n_cols), C.c_void_p(indptr.data_ptr()),
+                                              C.c_void_p(indices.data_ptr() if nnz else 0),
+                                              C.c_void_p(data.data_ptr()) if data is not None else None, nnz))
 
     # ------------------------------------------------------------------ parameters
     def param_infos(self):
@@ -182,6 +199,12 @@ class Engine(object):
     def d_forward_phase(self, ids_offset, B, phase):
         L.check(self.lib.ganmf_d_forward_phase(self.ctx, ids_offset, B, phase))
 
+    def tp_d_phase(self, phase, ids_offset, B, lr, reg, m_hinge):
+        L.check(self.lib.ganmf_tp_d_phase(self.ctx, phase, ids_offset, B, lr, reg, m_hinge))
+
+    def tp_g_phase(self, phase, ids_offset, B, lr, reg, recon_coefficient):
+        L.check(self.lib.ganmf_tp_g_phase(self.ctx, phase, ids_offset, B, lr, reg, recon_coefficient))
+
     def finalize_loss(self, reg, loss_slot):
         L.check(self.lib.ganmf_finalize_loss(self.ctx, reg, loss_slot))
 
@@ -238,10 +261,27 @@ class Engine(object):
                                          sc.ctypes.data_as(L._f32p) if sc is not None else None))
         return idx, val, sc
 
-    def set_test(self, urm_test, urm_train_for_popularity):
+    def set_test(self, urm_test, urm_train_for_popularity=None, item_popularity=None):
         """Uploads the held-out matrix and the numpy-made lookup tables of the metric kernels
-        (gains 2^r-1, ln(j+2), per-item novelty / normalised popularity, metrics.py:298-392,693-722)."""
-        key = (id(urm_test), urm_test.nnz, urm_train_for_popularity.shape, urm_train_for_popularity.nnz)
+        (gains 2^r-1, ln(j+2), per-item novelty / normalised popularity, metrics.py:298-392,693-722).
+        The popularity comes from the users x items TRAINING matrix, or (row-sharded evaluation, where no rank
+        holds all rows) from a ready per-item interaction count."""
+        if (urm_train_for_popularity is None) == (item_popularity is None):
+            raise ValueError("pass exactly one of urm_train_for_popularity / item_popularity")
+        if urm_test.shape[1] != self.n_items:
+            raise ValueError("URM_test has %d columns, the model ranks %d items" % (urm_test.shape[1], self.n_items))
+        if item_popularity is not None:
+            item_popularity = np.asarray(item_popularity)
+            if item_popularity.shape != (urm_test.shape[1],):
+                raise ValueError("item_popularity must have one entry per column of URM_test")
+            key = (id(urm_test), urm_test.nnz, "pop", int(item_popularity.sum()))
+        else:
+            if urm_train_for_popularity.shape != urm_test.shape:
+                # e.g. an item-mode model whose URM_train was left transposed (GANMF.py:32-33): the per-item
+                # tables would be indexed out of bounds
+                raise ValueError("URM_train is %r but URM_test is %r: both must be users x items" %
+                                 (urm_train_for_popularity.shape, urm_test.shape))
+            key = (id(urm_test), urm_test.nnz, urm_train_for_popularity.shape, urm_train_for_popularity.nnz)
         if self._test_key == key:
             return
         te = self.set_csr(L.CSR_TEST, urm_test)
@@ -250,9 +290,12 @@ class Engine(object):
         rows = np.repeat(np.arange(te.shape[0]), np.diff(te.indptr))
         rel_sorted_gain = gain[np.lexsort((-gain, rows))] if gain.size else gain
         logtab = np.log(np.arange(L.TOPK_MAX, dtype=np.float32) + 2)
-        tr = sps.csc_matrix(urm_train_for_popularity)
-        tr.eliminate_zeros()
-        pop = np.ediff1d(tr.indptr)
+        if item_popularity is not None:
+            pop = item_popularity.astype(np.int64)
+        else:
+            tr = sps.csc_matrix(urm_train_for_popularity)
+            tr.eliminate_zeros()
+            pop = np.ediff1d(tr.indptr)
         n_inter = pop.sum()
         n_items = len(pop)
         with np.errstate(divide="ignore"):
@@ -265,7 +308,8 @@ class Engine(object):
         nv, nvp = L.f64(nov)
         pn, pnp = L.f64(popn)
         hp = np.ascontiguousarray(haspop)
-        L.check(self.lib.ganmf_set_eval_tables(self.ctx, gp, gdp, ltp, lt.size, nvp, hp.ctypes.data_as(L._u8p), pnp))
+        L.check(self.lib.ganmf_set_eval_tables(self.ctx, gp, gdp, ltp, lt.size, nvp, hp.ctypes.data_as(L._u8p), pnp,
+                                               int(n_items)))
         self._test_key = key
         self._test_keepalive = urm_test
 

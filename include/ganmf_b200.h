@@ -24,7 +24,11 @@ extern "C" {
 
 typedef struct ganmf_ctx ganmf_ctx;
 
-enum { GANMF_KIND_GANMF = 0, GANMF_KIND_DISGANMF = 1 };
+enum { GANMF_KIND_GANMF = 0, GANMF_KIND_DISGANMF = 1,
+       /* factor matrices only (no discriminator, no training): the device scorer / evaluator behind
+        * Base/BaseMatrixFactorizationRecommender.py:94-143 (USER_factors . ITEM_factors^T), and the evaluation
+        * context of an item-sharded training run */
+       GANMF_KIND_MF = 2 };
 enum { GANMF_ACT_LINEAR = 0, GANMF_ACT_TANH = 1, GANMF_ACT_RELU = 2, GANMF_ACT_SIGMOID = 3 };
 enum { GANMF_CSR_TRAIN = 0,   /* rows of the TRAINING orientation (items x users in --item mode) */
        GANMF_CSR_SEEN = 1,    /* users x items, masks seen items in recommend()                   */
@@ -50,6 +54,14 @@ typedef struct ganmf_config {
   int row_id_offset;   /* global id of local row 0 (data-parallel shards; DisGANMF id feature)  */
   int device;          /* CUDA device ordinal                                                   */
   int gemm_path;       /* GANMF_GEMM_*; AUTO picks tcgen05 unless the shape is tiny             */
+  /* Item-sharded (tensor-parallel) training, GANMF only (no reference counterpart,
+   * the reference trains on one device): this context holds columns [item_offset, item_offset + width) of the
+   * training matrix and the matching slices of We (rows), Wd / bd (columns) and V (rows); the user factors and
+   * the encoder bias are replicated.  Mean losses and glorot limits use global_width.  All zero = unsharded. */
+  int global_width;    /* columns of the WHOLE training matrix (0: = width)                     */
+  int item_offset;     /* first global column held by this context                              */
+  int tp_rank;         /* rank inside the item-sharded group                                    */
+  int tp_world;        /* size of the group (0 or 1: unsharded)                                 */
 } ganmf_config;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
@@ -70,6 +82,11 @@ int ganmf_synchronize(ganmf_ctx* ctx);
  *   sorted for GANMF_CSR_TEST. */
 int ganmf_set_csr(ganmf_ctx* ctx, int which, int n_rows, int n_cols, const int32_t* indptr_host,
                   const int32_t* indices_host, const float* data_host);
+/* The same from DEVICE arrays (copied device-to-device; nnz = indptr[n_rows]).  ~ sps.load_npz + upload of
+ * experiments/datasets/*.npz without a host detour when the matrix is built or transposed on the GPU
+ * (GANMF.py:32-33 transposes on the host). */
+int ganmf_set_csr_device(ganmf_ctx* ctx, int which, int n_rows, int n_cols, const int32_t* indptr_dev,
+                         const int32_t* indices_dev, const float* data_dev, int64_t nnz);
 
 /* ---- parameters (TF variable names, GANMF.py:119-121 / DisGANMF.py:58-64) ---------------- */
 int ganmf_param_count(ganmf_ctx* ctx);
@@ -124,6 +141,21 @@ int ganmf_d_apply_ranges(ganmf_ctx* ctx, float lr, float reg, const int64_t* off
 /* Data-parallel G step only (n_rows_global != B): after ganmf_g_apply, sum step_scalars[6] (the l2 of
  * the row-sharded user factors) over ranks, then write loss_slot. */
 int ganmf_finalize_loss(ganmf_ctx* ctx, float reg, int loss_slot);
+/* Item-sharded training (config.tp_world > 1): the same sess.run([dtrain, dloss]) / sess.run([gtrain, gloss])
+ * (GANMF.py:186-187,200-201) on the WHOLE minibatch of B rows restricted to this context's item slice, cut
+ * where partial sums over the item slices must be added up by the caller (NCCL all-reduce, SUM):
+ *   D: phase 1 (profiles, F = Pb.V^T, partial codes)      -> sum "tp_h2"[0 : 2B*ld]
+ *      phase 2 (residuals, energy sums)                    -> sum "step_scalars"[0:2]
+ *      phase 3 (hinge gate, dbd, partial dH and dbe)       -> sum "tp_dh2"[0 : (2B+1)*ld]  (row 2B = dbe)
+ *      phase 4 (dWd, dWe with Adam in the epilogue, biases)-> sum "step_scalars"[3:4], ganmf_finalize_loss
+ *   G: phase 1 (as D)                                      -> sum "tp_h2"[0 : 2B*ld]
+ *      phase 2 (fake residual, feature matching, partial dHf) -> sum "tp_dh2"[B*ld : 2B*ld], "step_scalars"[0:1]
+ *      phase 3 (dF, dV, partial dPb)                       -> sum "tp_dpb"[0 : B*ld]
+ *      phase 4 (Adam on the batch rows of P and on the V slice) -> sum "step_scalars"[3:4], ganmf_finalize_loss
+ * ld = leading dimension reported by ganmf_device_buffer_ld.  Every rank passes the same ids. */
+int ganmf_tp_d_phase(ganmf_ctx* ctx, int phase, int ids_offset, int B, float lr, float reg, float m_hinge);
+int ganmf_tp_g_phase(ganmf_ctx* ctx, int phase, int ids_offset, int B, float lr, float reg,
+                     float recon_coefficient);
 /* One epoch of the reference schedule (GANMF.py:172-203): shuffled row ids in, d_steps full D
  * passes then g_steps full G passes over the same batches, per-batch losses out (host).
  * H2D: n_rows ids; D2H: the losses.  Synchronises once at the end. */
@@ -137,8 +169,12 @@ int ganmf_read_losses(ganmf_ctx* ctx, float* host, int n);        /* loss log [0
  * "d_grads_dec" = dWd|dbd), "d_params" (+ "_enc"/"_dec": the matching parameter ranges),
  * "g_shared_grad" (item-factor gradient),
  * "step_scalars" (7 float64: sumsq_real, sumsq_fake, feature-matching, l2 of replicated tensors,
- * bce_real, bce_fake, l2 of the row-sharded user factors). */
+ * bce_real, bce_fake, l2 of the row-sharded user factors).
+ * Item-sharded training: "tp_h2" ([2*max_batch][ld] codes), "tp_dh2" ([2*max_batch+1][ld] code gradients, the
+ * last used row carries the partial encoder-bias gradient), "tp_dpb" ([max_batch][ld] user-factor gradients).
+ * "user_factors" / "item_factors": the factor matrices [rows][ld] (deferred optimiser steps are applied first). */
 int ganmf_device_buffer(ganmf_ctx* ctx, const char* name, void** dev_ptr, int64_t* n_elems);
+int ganmf_device_buffer_ld(ganmf_ctx* ctx, const char* name, int* ld);
 
 /* ---- scoring / recommendation / evaluation ---------------------------------------------- */
 /* ~ _compute_item_score (GANMF.py:285-292): scores_host[n][n_items], user ids in scoring
@@ -162,7 +198,8 @@ int ganmf_recommend(ganmf_ctx* ctx, const int32_t* user_ids_host, int n, int rem
  * sums_host[n_cutoffs][GANMF_MC_NCOL]; item_counts_host[n_cutoffs][n_items] (nullable). */
 int ganmf_set_eval_tables(ganmf_ctx* ctx, const float* test_gain_host, const float* test_gain_desc_host,
                           const float* logtab_host, int logtab_n, const double* item_novelty_host,
-                          const uint8_t* item_has_pop_host, const double* item_popnorm_host);
+                          const uint8_t* item_has_pop_host, const double* item_popnorm_host,
+                          int n_items_tables /* length of the three per-item tables; must equal the test matrix's columns */);
 int ganmf_evaluate(ganmf_ctx* ctx, const int32_t* user_ids_host, int n_users, const int32_t* cutoffs_host,
                    int n_cutoffs, int remove_seen, int block_size, double* sums_host,
                    int64_t* item_counts_host);

@@ -113,8 +113,9 @@ def test_early_stopping_return_value_and_snapshot_calls(stand_in):
     last = rec.fit(num_factors=2, emb_dim=4, epochs=50, batch_size=16, allow_worse=2, freq=2, after=0,
                    metrics=["MAP"], validation_evaluator=ev, validation_set=None, sample_every=None)
     eng = stand_in.instances[-1]
-    # improvements at epochs 2 and 4 (two snapshots); worse at 6, 8 (tolerated), 10 -> stop + restore best
-    assert (eng.snapshots, eng.restores) == (2, 1)
+    # the initial weights are snapshot once (the reference's shadow variables exist from graph construction,
+    # GANMF.py:123-128); improvements at epochs 2 and 4 (two more); worse at 6, 8 (tolerated), 10 -> stop + restore
+    assert (eng.snapshots, eng.restores) == (3, 1)
     assert last == 10 and len(eng.epochs) == 10                # GANMF.py:244: the epoch it stopped at
     # RecSysExp.py:274-276 turns that into the epoch count of the best model
     assert last - 2 * 2 == 6
