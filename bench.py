@@ -4,12 +4,17 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path, one rank per GPU
     python bench.py --impl reference --steps K --warmup W    # the reference's arithmetic on the host CPU
 
-Workload (BASELINE.json configs[3]): synthetic 138 000 x 27 000 implicit matrix at 0.5 % density,
-GANMF --user, k=250, emb_dim=1024, batch 1024 PER GPU (weak scaling: every GPU owns 138 000 users).
-A "step" = one D update + one G update on one 1024-row minibatch (each row gets one D pass and one G
-pass, which is how BASELINE.md turns epochs into user-rows/s).
+Workload (default, every N): BASELINE.json configs[4] ("cfg5") -- synthetic 2 000 000 x 200 000 implicit matrix
+at 0.1 % density, GANMF --user, k=250, emb_dim=1024, 1024 minibatch rows PER GPU (weak scaling in the batch: the
+matrix is the same 2M x 200k at every N).  N = 1: one context holds everything.  N > 1: the ITEMS are split over
+the ranks (ganmf_b200.parallel.ItemShardedTrainer), every rank runs the whole N*1024-row minibatch on its item
+slice and only [2B, E] / [B, k] activations are all-reduced.  `--workload cfg4` selects BASELINE.json configs[3]
+(138 000 x 27 000, 0.5 %); at N = 1 the default run appends that line as a second record ("records").
+A "step" = one D update + one G update on one minibatch (each row gets one D pass and one G pass, which is how
+BASELINE.md turns epochs into user-rows/s).
 value  = rows/s with the CSR, ids and weights already resident in HBM.
-e2e    = the same through ganmf_train_epoch() (the call GANMF.fit makes): host ids in, losses out.
+e2e    = the same through the public epoch call (ganmf_train_epoch / ItemShardedTrainer.train_epoch, what
+         GANMF.fit calls): pinned host ids in, per-step losses out.
 """
 import argparse
 import json
@@ -25,23 +30,23 @@ import scipy.sparse as sps
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG4 = dict(name="cfg4: synthetic 138000x27000 d=0.5% GANMF-u k=250 E=1024 B=1024/GPU", users=138000, items=27000,
-            density=0.005, k=250, E=1024, B=1024)
+WORKLOADS = {
+    "cfg5": dict(key="cfg5", name="cfg5: synthetic 2000000x200000 d=0.1% GANMF-u k=250 E=1024 B=1024/GPU",
+                 users=2000000, items=200000, density=0.001, k=250, E=1024, B=1024),
+    "cfg4": dict(key="cfg4", name="cfg4: synthetic 138000x27000 d=0.5% GANMF-u k=250 E=1024 B=1024/GPU",
+                 users=138000, items=27000, density=0.005, k=250, E=1024, B=1024),
+}
 HP = dict(d_lr=1e-4, g_lr=1e-4, d_reg=1e-4, g_reg=0.0, m=10.0, alpha=0.01)
+SALT_TRAIN, SALT_TEST = 0x5EED0001, 0x7E570002
 
 
-def workload(name, world=1):
-    """cfg4 (default, the workload of record: 138 000 users PER GPU) or --workload cfg5 (BASELINE.json configs[4]:
-    2 000 000 x 200 000 at 0.1 %, the users split over the ranks)."""
-    if name == "cfg5":
-        per = 2000000 // max(world, 1)
-        return dict(name="cfg5: synthetic 2000000x200000 d=0.1%% GANMF-u k=250 E=1024 B=1024/GPU, %d users per GPU" % per,
-                    users=per, items=200000, density=0.001, k=250, E=1024, B=1024)
-    return CFG4
+def workload(name):
+    return WORKLOADS[name]
 
 
+# ------------------------------------------------------------------------------------ synthetic data
 def synthetic_urm(n_users, n_items, density, seed):
-    """Implicit interaction matrix: round(density*n_items) distinct uniform items per user."""
+    """Host version (CPU arms): round(density*n_items) distinct uniform items per user."""
     rs = np.random.RandomState(seed)
     per = max(1, int(round(density * n_items)))
     cols = rs.randint(0, n_items, size=(n_users, per)).astype(np.int32)
@@ -52,6 +57,52 @@ def synthetic_urm(n_users, n_items, density, seed):
     np.cumsum(keep.sum(1), out=indptr[1:])
     m = sps.csr_matrix((np.ones(int(indptr[-1]), np.float32), cols[keep], indptr.astype(np.int32)),
                        shape=(n_users, n_items))
+    m.has_sorted_indices = True
+    return m
+
+
+def _hash_cols(torch, rows, per, n_items, salt):
+    """[len(rows), per] item ids: counter-based hash of (row, draw) -- any rank can produce any block of the
+    SAME matrix without communication."""
+    M = (1 << 63) - 1
+    j = torch.arange(per, device=rows.device, dtype=torch.int64)[None, :]
+    x = rows[:, None] * (-7046029254386353131) + j * (-4658895280553007687) + salt     # wraps mod 2^64
+    x = (x ^ ((x >> 30) & ((1 << 34) - 1))) * (-4658895280553007687)
+    x = (x ^ ((x >> 27) & ((1 << 37) - 1))) * (-7723592293110705685)
+    x = x ^ ((x >> 31) & ((1 << 33) - 1))
+    return (x & M) % n_items
+
+
+def synth_csr_device(torch, row_lo, row_hi, n_items, per, salt, col_lo=0, col_hi=None, drop_keys=None,
+                     chunk=1 << 17):
+    """Rows [row_lo, row_hi) x columns [col_lo, col_hi) of the hashed matrix as device CSR (int32 indptr, int32
+    indices, local column ids, sorted and unique per row).  drop_keys: sorted int64 keys row*n_items+col to leave
+    out (the held-out matrix must be disjoint from the training matrix)."""
+    col_hi = n_items if col_hi is None else col_hi
+    dev = torch.device("cuda", torch.cuda.current_device())
+    counts, idx = [], []
+    for lo in range(row_lo, row_hi, chunk):
+        rows = torch.arange(lo, min(lo + chunk, row_hi), device=dev, dtype=torch.int64)
+        cols, _ = _hash_cols(torch, rows, per, n_items, salt).sort(dim=1)
+        keep = torch.ones_like(cols, dtype=torch.bool)
+        keep[:, 1:] = cols[:, 1:] != cols[:, :-1]
+        if col_lo > 0 or col_hi < n_items:
+            keep &= (cols >= col_lo) & (cols < col_hi)
+        if drop_keys is not None and drop_keys.numel():
+            keys = rows[:, None] * n_items + cols
+            pos = torch.searchsorted(drop_keys, keys.reshape(-1)).clamp_(max=drop_keys.numel() - 1)
+            keep &= (drop_keys[pos] != keys.reshape(-1)).reshape(keys.shape)
+        counts.append(keep.sum(1))
+        idx.append((cols[keep] - col_lo).to(torch.int32))
+    counts = torch.cat(counts)
+    indptr = torch.zeros(row_hi - row_lo + 1, device=dev, dtype=torch.int64)
+    torch.cumsum(counts, 0, out=indptr[1:])
+    return indptr.to(torch.int32), torch.cat(idx)
+
+
+def csr_to_host(indptr, indices, shape):
+    ip, ix = indptr.cpu().numpy(), indices.cpu().numpy()
+    m = sps.csr_matrix((np.ones(len(ix), np.float32), ix, ip), shape=shape)
     m.has_sorted_indices = True
     return m
 
@@ -126,14 +177,14 @@ class ClockSampler(object):
                 "reasons": reasons, "samples": len(self.sm), "source": self.src}
 
 
-def gemm_algorithmic_bytes(c, fused_adam=False):
-    """Operand + output bytes (each read/written once) of the 13 tensor-core GEMMs of one D+G step pair.
-    fused_adam (single GPU): the dWd / dWe epilogues do not write the gradient but read and write theta, m, v
-    in place (24 B per parameter instead of 4)."""
-    B, I, k, E = c["B"], c["items"], c["k"], c["E"]
+def gemm_algorithmic_bytes(c, world=1):
+    """Operand + output bytes (each read/written once) of the 13 tensor-core GEMMs of one D+G step pair on ONE
+    rank (item-sharded: B rows of the whole minibatch, I / world items).  The dWd / dWe epilogues do not write
+    the gradient but read and write theta, m, v in place (24 B per parameter instead of 4)."""
+    B, I, k, E = c["B"] * world, c["items"] // world, c["k"], c["E"]
     f = 4.0
     g = lambda M, N, K, extra=0: f * (M * K + N * K + M * N * (1 + extra))
-    wg = 5 if fused_adam else 0                   # 6 tensors moved instead of 1
+    wg = 5                                        # 6 tensors moved instead of 1
     d = g(B, I, k) + g(2 * B, E, I) + g(2 * B, I, E, 1) + g(E, I, 2 * B, wg) + g(2 * B, E, I) + g(I, E, 2 * B, wg)
     gs = g(B, I, k) + g(2 * B, E, I) + g(B, I, E, 1) + g(B, E, I, 2) + g(B, I, E, 1) + g(I, k, B) + g(B, k, I)
     return d + gs
@@ -148,6 +199,46 @@ def use_all_host_threads():
     except Exception:
         pass
     return n
+
+
+def flops_per_row(c):
+    return c["items"] * (8 * c["k"] + 30 * c["E"])          # SURVEY.md section 8(d)
+
+
+# ------------------------------------------------------------------------------------ CPU arms
+CPU_SAMPLE = {"cfg5": dict(B=64, n_users=4096), "cfg4": dict(B=1024, n_users=138000)}
+
+
+def cpu_train_sample(c, steps, warmup, budget_s=None):
+    """The reference's TF-1.12 graph restated in NumPy (oracle/train_oracle.py; TensorFlow cannot be installed
+    here), all host threads, on a bounded sample of workload `c`: same item count, k, E and hyper-parameters;
+    cfg4 runs the labelled minibatch (B = 1024) and user table (138 000 rows, dense TF-Adam over it); cfg5 steps
+    on 64-row minibatches with the user table cut to 4096 rows (a B = 1024 step at 200 000 items takes ~1 min on
+    the host).  Returns (rows/s, seconds per step, steps timed, description)."""
+    from oracle import train_oracle as to
+    s = CPU_SAMPLE[c["key"]]
+    B, n_users = s["B"], s["n_users"]
+    urm = synthetic_urm(n_users, c["items"], c["density"], 1337)
+    orc = to.GanmfOracle(to.init_ganmf_params(n_users, c["items"], c["k"], c["E"], seed=1234), HP["d_lr"], HP["g_lr"],
+                         dtype=np.float32)
+    rs = np.random.RandomState(1337)
+
+    def step():
+        ids = rs.permutation(n_users)[:B]
+        R = to.csr_rows_to_dense(urm, ids)
+        orc.d_step(ids, R, d_reg=HP["d_reg"], m=HP["m"])
+        orc.g_step(ids, R, g_reg=HP["g_reg"], recon_coefficient=HP["alpha"])
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < steps and (budget_s is None or n < 2 or time.perf_counter() - t0 < budget_s):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    desc = "%d D+G steps of B=%d rows at %d items, k=%d, E=%d, user-factor table of %d rows (NumPy/BLAS restatement " \
+           "of the TF graph, all host threads)" % (n, B, c["items"], c["k"], c["E"], n_users)
+    return B * n / dt, dt / n, n, desc
 
 
 def cpu_eval_baseline(c, n_users=768):
@@ -169,53 +260,289 @@ def cpu_eval_baseline(c, n_users=768):
             "port of recommend()/EvaluatorHoldout: single-threaded per-user loop as in the reference)" % (n_eval, c["items"])}
 
 
-def flops_per_row(c):
-    return c["items"] * (8 * c["k"] + 30 * c["E"])          # SURVEY.md section 8(d)
-
-
-# ------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
-    """The reference's own CPU path for this metric: its TF-1.12 graph restated in NumPy (TensorFlow cannot
-    be installed here), all host threads, same shapes and hyper-parameters."""
+    """The reference's own CPU path for this metric (oracle port; `cpu_train_sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import train_oracle as to
     cores = use_all_host_threads()
     c = workload(args.workload)
-    B = 256                                                   # bounded sample: 256-row minibatches
-    n_users = 4096                                            # user-factor rows kept small: P is not the cost driver
-    urm = synthetic_urm(n_users, c["items"], c["density"], 1337)
-    p0 = to.init_ganmf_params(n_users, c["items"], c["k"], c["E"], seed=1234)
-    orc = to.GanmfOracle(p0, HP["d_lr"], HP["g_lr"], dtype=np.float32)
-    rs = np.random.RandomState(1337)
-
-    def step():
-        ids = rs.permutation(n_users)[:B]
-        R = to.csr_rows_to_dense(urm, ids)
-        orc.d_step(ids, R, d_reg=HP["d_reg"], m=HP["m"])
-        orc.g_step(ids, R, g_reg=HP["g_reg"], recon_coefficient=HP["alpha"])
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    v = B * args.steps / dt
-    sample = "NumPy restatement of the TF graph, %d steps of B=%d rows at %d items, k=250, E=1024 " \
-             "(user-factor table cut to %d rows)" % (args.steps, B, c["items"], n_users)
+    v, s_per_step, n, desc = cpu_train_sample(c, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "GANMF-u train user-rows/s", "value": v, "unit": "rows/s", "n_gpus": 0,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "steps": n, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": c["name"]},
-            "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": c["name"], "sample": desc},
+            "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "eval": dict(cpu_eval_baseline(c), metric="top-10 eval users/s (score -> seen mask -> top-10 -> metric sums)")}
     print(json.dumps(line))
     return 0
 
 
+def cpu_baseline(c):
+    cores = use_all_host_threads()
+    v, _, n, desc = cpu_train_sample(c, 40, 1, budget_s=15)
+    return {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": desc, "eval": cpu_eval_baseline(c)}
+
+
 # ------------------------------------------------------------------------------------ our arm
+class Bench(object):
+    """One workload on this process group: builds the device state, then measures training and evaluation."""
+
+    def __init__(self, c, args, torch, dist, world, rank, local_rank):
+        from ganmf_b200 import _lib as L
+        from ganmf_b200.engine import Engine
+        from ganmf_b200.parallel import ItemShardedTrainer, item_slices, shard_rows
+        self.c, self.args, self.torch, self.dist, self.world, self.rank = c, args, torch, dist, world, rank
+        self.L = L
+        U, I = c["users"], c["items"]
+        self.per = max(1, int(round(c["density"] * I)))
+        self.Bg = c["B"] * world                                   # rows of the whole minibatch
+        self.lo, self.hi = item_slices(I, world)[rank]
+        kw = dict(global_width=I, item_offset=self.lo, tp_rank=rank, tp_world=world) if world > 1 else {}
+        self.eng = Engine(L.KIND_GANMF, U, self.hi - self.lo, c["k"], emb_dim=c["E"], max_batch=self.Bg,
+                          device=local_rank, **kw)
+        self.eng.set_stream(torch.cuda.current_stream().cuda_stream)
+        ip, ix = synth_csr_device(torch, 0, U, I, self.per, SALT_TRAIN, self.lo, self.hi)
+        self.eng.set_csr_device(L.CSR_TRAIN, U, self.hi - self.lo, ip, ix)
+        self.pop_slice = torch.bincount(ix.long(), minlength=self.hi - self.lo)
+        if world == 1:
+            self.eng.set_csr_device(L.CSR_SEEN, U, I, ip, ix)
+        self.nnz = int(ix.numel())
+        del ip, ix
+        self.eng.init_params(1234)             # slices of ONE model: the same seed draws the same whole tensors
+        self.trainer = ItemShardedTrainer(self.eng) if world > 1 else None
+        self.shard_rows, self.Engine = shard_rows, Engine
+        self.rs = np.random.RandomState(1337)  # the SAME id stream on every rank
+
+    # ---- helpers
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def train_epoch(self, perm):
+        if self.trainer:
+            return self.trainer.train_epoch(perm, self.Bg, 1, 1, HP)
+        return self.eng.train_epoch(perm, self.Bg, 1, 1, HP["d_lr"], HP["g_lr"], HP["d_reg"], HP["g_reg"], HP["m"],
+                                    HP["alpha"])
+
+    def run_steps(self, first, count, slot0=0):
+        """reference schedule on `count` batches: all D updates, then all G updates, same batches"""
+        B, eng, tr = self.Bg, self.eng, self.trainer
+        for i in range(count):
+            off = (first + i) * B
+            if tr:
+                tr.d_step(off, B, HP["d_lr"], HP["d_reg"], HP["m"], slot0 + i)
+            else:
+                eng.d_step(off, B, HP["d_lr"], HP["d_reg"], HP["m"], loss_slot=slot0 + i)
+        for i in range(count):
+            off = (first + i) * B
+            if tr:
+                tr.g_step(off, B, HP["g_lr"], HP["g_reg"], HP["alpha"], slot0 + count + i)
+            else:
+                eng.g_step(off, B, HP["g_lr"], HP["g_reg"], HP["alpha"], loss_slot=slot0 + count + i)
+
+    # ---- training
+    def measure_train(self, local_rank):
+        c, torch, eng, world, rank = self.c, self.torch, self.eng, self.world, self.rank
+        K, W, B = self.args.steps, self.args.warmup, self.Bg
+        # One whole epoch first (untimed): every user row then carries Adam moments and the timed rows owe the
+        # deferred zero-gradient optimiser steps a steady-state epoch gives them (the user-factor optimiser is
+        # lazy, kernels.cuh K6b -- on untouched rows it would have nothing to replay).
+        self.train_epoch(self.rs.permutation(c["users"]).astype(np.int32))
+        perm = self.rs.permutation(c["users"])[:(W + K) * B].astype(np.int32)
+        eng.upload_ids(perm)
+        self.run_steps(0, W)
+        self.barrier()
+        launches0 = eng.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        prof_range = os.environ.get("GANMF_BENCH_PROFILER_RANGE") == "1"   # ncu --profile-from-start off: timed steps only
+        with ClockSampler(local_rank) as clk:
+            self.barrier()
+            if prof_range:
+                torch.cuda.profiler.start()
+            e0.record()
+            self.run_steps(W, K)
+            e1.record()
+            self.barrier()
+            if prof_range:
+                torch.cuda.profiler.stop()
+        ms = self.max_over_ranks(e0.elapsed_time(e1))
+        launches = eng.launch_count() - launches0
+        value = B * K / (ms * 1e-3)
+        losses = self.trainer.read_losses(2 * K) if self.trainer else eng.read_losses(2 * K)
+        if not np.all(np.isfinite(losses)):
+            raise SystemExit("non-finite losses in the timed region: %r" % losses[:8])
+
+        # live roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every launch, on its stream
+        eng.profile(True)
+        self.run_steps(W, K)
+        rec_ms, rec_shape = eng.profile_records()
+        if rank == 0 and os.environ.get("GANMF_BENCH_GEMM_TABLE"):
+            agg = {}
+            for t, (M_, N_, K_, S_) in zip(rec_ms, rec_shape):
+                a = agg.setdefault((int(M_), int(N_), int(K_), int(S_)), [0, 0.0])
+                a[0] += 1
+                a[1] += t
+            with open(os.environ["GANMF_BENCH_GEMM_TABLE"] + "." + c["key"], "w") as f:
+                f.write("# %s, %d GPU(s): tcgen05 GEMM launches inside the timed steps (CUDA events around each launch)\n"
+                        "#     M      N      K splits  calls   ms/call   TFLOP/s\n" % (c["name"], world))
+                for (M_, N_, K_, S_), (cnt, tot) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                    f.write("%7d %6d %6d %6d %6d %9.4f %9.1f\n" % (M_, N_, K_, S_, cnt, tot / cnt,
+                                                                2.0 * M_ * N_ * K_ / (tot / cnt * 1e-3) / 1e12))
+        # the two weight-gradient GEMMs of the D step (dWd, dWe) carry the fused Adam update in their epilogue
+        pure = [(t, sh) for t, sh in zip(rec_ms, rec_shape)
+                if not (int(sh[2]) == 2 * B and int(sh[0]) * int(sh[1]) == (self.hi - self.lo) * c["E"])]
+        pure_ms = float(sum(t for t, _ in pure))
+        pure_flops = float(sum(2.0 * int(sh[0]) * int(sh[1]) * int(sh[2]) for _, sh in pure))
+        gemm_ms, gemm_flops, gemm_launches = eng.profile_read()
+        eng.profile(False)
+        pk = peaks()
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r02_tc_gemm_dram_traffic_%s.json" % c["key"])
+        if world == 1 and os.path.exists(tpath):                # from the committed `ncu --set full` capture
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["dram_bytes_per_launch_mean"], os.path.relpath(tpath, ROOT) + ": " + tj["note"]
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        roofline = {"kernel": "tc_gemm_kernel (tcgen05 kind::tf32, TMA, TMEM; CTA pairs cta_group::2 on the many-tile GEMMs)",
+                    "bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["tf_sust"], "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch_mean": gemm_algorithmic_bytes(c, world) / 13.0,
+                    "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json); kind::tf32 issues at half the "
+                    "bf16 rate, so frac <= 0.5 by construction", "frac_of_tf32_rate": 2 * achieved / pk["tf_sust"],
+                    "achieved_excl_fused_adam_gemms": pure_flops / (pure_ms * 1e-3) / 1e12 if pure_ms > 0 else None,
+                    "note": "the dWd/dWe GEMM epilogues also run TF-Adam on Wd/We in place (24 B/param of HBM "
+                            "traffic inside those 2 of the 13 launches), which lowers their FLOP rate but removes the "
+                            "separate optimiser pass", "rank": 0,
+                    "gemm_launches_per_step": gemm_launches / K, "gemm_share_of_step": gemm_ms / max(ms, 1e-9),
+                    "step_algorithmic_tflops_per_gpu": flops_per_row(c) * c["B"] * K / (ms * 1e-3) / 1e12}
+        out = {"value": value, "ms": ms, "launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
+               "gemm_tflops": achieved, "loss_last": [float(losses[K - 1]), float(losses[2 * K - 1])]}
+        if self.args.quick:
+            return out
+
+        # end to end through the public epoch call (pinned host ids in, losses out)
+        pin = torch.from_numpy(self.rs.permutation(c["users"])[:K * B].astype(np.int32)).pin_memory()
+        self.train_epoch(pin.numpy()[:min(W, K) * B])
+        self.barrier()
+        t0 = time.perf_counter()
+        self.train_epoch(pin.numpy())                              # H2D ids + all steps + D2H losses + sync
+        torch.cuda.synchronize()
+        dt = self.max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
+        out["e2e"] = {"value": B * K / dt, "unit": "rows/s", "h2d_bytes_per_step": 4 * B * world,
+                      "d2h_bytes_per_step": 8 * world,
+                      "api": ("ItemShardedTrainer.train_epoch" if self.trainer else "ganmf_train_epoch (GANMF.fit's "
+                              "per-epoch call)") + ": pinned host row ids in, per-step losses out"}
+        return out
+
+    # ---- evaluation: score -> seen mask -> top-10 -> metric sums, users sharded by rank
+    def measure_eval(self, local_rank):
+        c, torch, dist, L, world, rank = self.c, self.torch, self.dist, self.L, self.world, self.rank
+        U, I = c["users"], c["items"]
+        u_lo, u_hi = self.shard_rows(U, world, rank)
+        n_eval = min(self.args.eval_users, u_hi - u_lo)
+        pop = self.pop_slice
+        if world > 1:
+            # the scorer context of this rank: its user rows of P (replicated by the trainer), ALL item factors
+            # (slices gathered over NVLink), the seen rows of its users
+            sc = self.Engine(L.KIND_MF, u_hi - u_lo, I, c["k"], max_batch=1, device=local_rank)
+            sc.set_stream(torch.cuda.current_stream().cuda_stream)
+            dev = torch.device("cuda", local_rank)
+            ld = self.eng.device_buffer_ld("user_factors")
+            src = torch.as_tensor(self.eng.device_buffer("user_factors"), device=dev)
+            torch.as_tensor(sc.device_buffer("user_factors"), device=dev).copy_(src[u_lo * ld:u_hi * ld])
+            v_all = torch.as_tensor(sc.device_buffer("item_factors"), device=dev)
+            v_own = torch.as_tensor(self.eng.device_buffer("item_factors"), device=dev)
+            from ganmf_b200.parallel import item_slices
+            pop_all = torch.zeros(I, device=dev, dtype=torch.int64)
+            for r, (lo, hi) in enumerate(item_slices(I, world)):
+                if r == rank:
+                    v_all[lo * ld:hi * ld].copy_(v_own)
+                    pop_all[lo:hi].copy_(pop)
+                dist.broadcast(v_all[lo * ld:hi * ld], src=r)
+                dist.broadcast(pop_all[lo:hi], src=r)
+            pop = pop_all
+            ip, ix = synth_csr_device(torch, u_lo, u_hi, I, self.per, SALT_TRAIN)
+            sc.set_csr_device(L.CSR_SEEN, u_hi - u_lo, I, ip, ix)
+        else:
+            sc = self.eng
+            ip, ix = synth_csr_device(torch, 0, n_eval, I, self.per, SALT_TRAIN)
+        # held-out matrix of the evaluated users (hashed with another salt, training entries removed)
+        rows = torch.repeat_interleave(torch.arange(n_eval, device=ix.device, dtype=torch.int64) + u_lo,
+                                       (ip[1:n_eval + 1] - ip[:n_eval]).long())
+        train_keys = rows * I + ix[:int(ip[n_eval])].long()
+        tip, tix = synth_csr_device(torch, u_lo, u_lo + n_eval, I, max(1, self.per // 4), SALT_TEST, drop_keys=train_keys)
+        test = csr_to_host(tip, tix, (n_eval, I))
+        test.resize((u_hi - u_lo, I))
+        del ip, ix, tip, tix, train_keys, rows
+        sc.set_test(test, item_popularity=pop.cpu().numpy())
+        users = np.flatnonzero(np.diff(test.indptr) > 0).astype(np.int32)
+        sc.evaluate(users, [10], remove_seen=True, want_counts=False)       # warm-up: sizes the device buffers
+        ev_s = 1e30
+        for _ in range(3):                                                    # steady state, best of 3 whole calls
+            self.barrier()
+            t0 = time.perf_counter()
+            sums, _ = sc.evaluate(users, [10], remove_seen=True, want_counts=False)
+            torch.cuda.synchronize()
+            ev_s = min(ev_s, time.perf_counter() - t0)
+        ev_ms = self.max_over_ranks(ev_s * 1e3)
+        n_tot = len(users)
+        if world > 1:
+            t = torch.tensor([float(n_tot), float(sums[0, 0])], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t)                                                # only metric sums cross GPUs
+            n_tot, p_sum = int(t[0].item()), float(t[1].item())
+        else:
+            p_sum = float(sums[0, 0])
+        eval_users_s = n_tot / (ev_ms * 1e-3)
+        pk = peaks()
+        return {"metric": "top-10 eval users/s (score -> seen mask -> top-10 -> metric sums)", "value": eval_users_s,
+                "unit": "users/s", "users": n_tot, "hbm_frac_4I_bytes_per_user":
+                eval_users_s / world * 4 * I / 1e9 / pk["hbm"], "e2e": True,
+                "api": "ganmf_evaluate: host user ids in, metric sums out (users sharded by rank, sums all-reduced)",
+                "precision_at_10": p_sum / max(n_tot, 1)}
+
+    def close(self):
+        self.eng.close()
+
+
+def run_workload(c, args, torch, dist, world, rank, local_rank, with_cpu):
+    b = Bench(c, args, torch, dist, world, rank, local_rank)
+    tr = b.measure_train(local_rank)
+    K, W = args.steps, args.warmup
+    line = {"metric": "GANMF-u train user-rows/s", "value": tr["value"], "unit": "rows/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": tr["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": c["name"], "global_batch": c["B"] * world, "csr_nnz_this_rank": b.nnz,
+                       "state": "after one full untimed epoch (all %d rows hold Adam moments)" % c["users"],
+                       "l2": "per-step working set (weights + activations, > 1 GB) exceeds the 126 MB L2",
+                       "parallelism": ("tp%d over items: rank r holds I/%d columns of the matrix and the matching slices "
+                                       "of We/Wd/bd/V with their Adam state; all-reduce of [2B,E] codes, code gradients and "
+                                       "[B,k] user-factor gradients per step (NCCL over NVLink); P replicated" % (world, world))
+                       if world > 1 else "single GPU"},
+            "gpu_launches": tr["launches"], "clocks": tr["clocks"], "roofline": tr["roofline"], "loss_last": tr["loss_last"]}
+    if args.quick:
+        line.update(quick=True, gemm_tflops=tr["gemm_tflops"],
+                    env={k_: v_ for k_, v_ in os.environ.items() if k_.startswith("GANMF_")})
+        b.close()
+        return line
+    line["e2e"] = tr["e2e"]
+    line["eval"] = b.measure_eval(local_rank)
+    if rank == 0 and not args.no_hbm_kernels:
+        line["hbm_kernels"] = hbm_kernel_rooflines(b.eng, torch, b.L, c, peaks(), b.hi - b.lo)
+    b.close()
+    if with_cpu:
+        line["cpu_baseline"] = cpu_baseline(c)
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,10 +550,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--eval-users", type=int, default=8192)
+    ap.add_argument("--no-hbm-kernels", action="store_true")
+    ap.add_argument("--no-second-record", action="store_true")
+    ap.add_argument("--eval-users", type=int, default=32768, help="users evaluated per rank")
     ap.add_argument("--quick", action="store_true", help="A/B runs: training throughput + GEMM roofline only")
-    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5"],
-                    help="cfg4 = workload of record (default); cfg5 = 2M x 200k split over the ranks")
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS),
+                    help="cfg5 = 2M x 200k (default, BASELINE.json configs[4]); cfg4 = 138k x 27k (configs[3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -243,195 +572,15 @@ def main():
     if world > 1:
         from ganmf_b200.parallel import init_nccl
         init_nccl(local_rank)
-    from ganmf_b200 import _lib as L
     from ganmf_b200 import build as _build
     _build.build()
-    from ganmf_b200.engine import Engine
-    from ganmf_b200.parallel import DataParallelTrainer
 
-    c = workload(args.workload, world)
-    K, W, B = args.steps, args.warmup, c["B"]
-    urm = synthetic_urm(c["users"], c["items"], c["density"], 1337 + rank)      # this rank's user shard
-    eng = Engine(L.KIND_GANMF, c["users"], c["items"], c["k"], emb_dim=c["E"], max_batch=B, device=local_rank)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
-    eng.set_csr(L.CSR_TRAIN, urm)
-    eng.set_csr(L.CSR_SEEN, urm, with_data=False)
-    eng.init_params(1234)                                     # same seed on every rank: replicated D and V
-    trainer = DataParallelTrainer(eng, world) if world > 1 else None
-    rs = np.random.RandomState(1337 + rank)
-    # One whole epoch first (135 D + 135 G updates, untimed): every user row then carries Adam moments and
-    # the timed rows owe the deferred zero-gradient optimiser steps a steady-state epoch gives them (the
-    # user-factor optimiser is lazy, kernels.cuh K6b -- on untouched rows it would have nothing to replay).
-    warm = rs.permutation(c["users"]).astype(np.int32)
-    if trainer:
-        trainer.train_epoch(warm, B, 1, 1, HP)
-    else:
-        eng.train_epoch(warm, B, 1, 1, HP["d_lr"], HP["g_lr"], HP["d_reg"], HP["g_reg"], HP["m"], HP["alpha"])
-    n_ids = (W + K) * B
-    perm = rs.permutation(c["users"])[:n_ids].astype(np.int32)
-    eng.upload_ids(perm)
-
-    def run_steps(first, count, slot0=0):
-        """reference schedule on `count` batches: all D updates, then all G updates, same batches"""
-        for i in range(count):
-            off = (first + i) * B
-            if trainer:
-                trainer.d_step(off, B, HP["d_lr"], HP["d_reg"], HP["m"], slot0 + i)
-            else:
-                eng.d_step(off, B, HP["d_lr"], HP["d_reg"], HP["m"], loss_slot=slot0 + i)
-        for i in range(count):
-            off = (first + i) * B
-            if trainer:
-                trainer.g_step(off, B, HP["g_lr"], HP["g_reg"], HP["alpha"], slot0 + count + i)
-            else:
-                eng.g_step(off, B, HP["g_lr"], HP["g_reg"], HP["alpha"], loss_slot=slot0 + count + i)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident throughput --------------------------------------------------------
-    run_steps(0, W)
-    barrier()
-    launches0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    prof_range = os.environ.get("GANMF_BENCH_PROFILER_RANGE") == "1"     # ncu --profile-from-start off: timed steps only
-    with ClockSampler(local_rank) as clk:
-        barrier()
-        if prof_range:
-            torch.cuda.profiler.start()
-        e0.record()
-        run_steps(W, K)
-        e1.record()
-        barrier()
-        if prof_range:
-            torch.cuda.profiler.stop()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = eng.launch_count() - launches0
-    value = world * B * K / (ms * 1e-3)
-    losses = eng.read_losses(2 * K)
-    if not np.all(np.isfinite(losses)):
-        raise SystemExit("non-finite losses in the timed region: %r" % losses[:8])
-
-    # ---- live roofline of the dominant kernel (tcgen05 GEMM), CUDA events around every launch --
-    eng.profile(True)
-    run_steps(W, K)
-    rec_ms, rec_shape = eng.profile_records()
-    if rank == 0 and os.environ.get("GANMF_BENCH_GEMM_TABLE"):
-        agg = {}
-        for t, (M_, N_, K_, S_) in zip(rec_ms, rec_shape):
-            a = agg.setdefault((int(M_), int(N_), int(K_), int(S_)), [0, 0.0])
-            a[0] += 1
-            a[1] += t
-        with open(os.environ["GANMF_BENCH_GEMM_TABLE"], "w") as f:
-            f.write("# tcgen05 GEMM launches inside the timed steps (CUDA events around each launch)\n")
-            f.write("#     M      N      K splits  calls   ms/call   TFLOP/s\n")
-            for (M_, N_, K_, S_), (cnt, tot) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-                f.write("%7d %6d %6d %6d %6d %9.4f %9.1f\n" % (M_, N_, K_, S_, cnt, tot / cnt,
-                                                            2.0 * M_ * N_ * K_ / (tot / cnt * 1e-3) / 1e12))
-    # the two weight-gradient GEMMs of the D step (dWd, dWe) carry the fused Adam update in their epilogue on
-    # the single-GPU path; report the GEMM rate with and without them
-    pure = [(t, sh) for t, sh in zip(rec_ms, rec_shape)
-            if not (world == 1 and int(sh[2]) == 2 * B and int(sh[0]) * int(sh[1]) == c["items"] * c["E"])]
-    pure_ms = float(sum(t for t, _ in pure))
-    pure_flops = float(sum(2.0 * int(sh[0]) * int(sh[1]) * int(sh[2]) for _, sh in pure))
-    gemm_ms, gemm_flops, gemm_launches = eng.profile_read()
-    eng.profile(False)
-    pk = peaks()
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_tc_gemm_dram_traffic.json")
-    if os.path.exists(tpath):                                 # from the committed `ncu --set full` capture
-        tj = json.load(open(tpath))
-        traffic, traffic_src = tj["dram_bytes_per_launch_mean"], "profiles/r01_tc_gemm_dram_traffic.json: " + tj["note"]
-    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"kernel": "tc_gemm_kernel (tcgen05 kind::tf32, TMA, TMEM; CTA pairs cta_group::2 on the many-tile GEMMs)", "bound": "tensor", "achieved": achieved,
-                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch_mean": gemm_algorithmic_bytes(c, fused_adam=(world == 1)) / 13.0,
-                "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json); kind::tf32 issues at half the "
-                "bf16 rate, so frac <= 0.5 by construction", "frac_of_tf32_rate": 2 * achieved / pk["tf_sust"],
-                "achieved_excl_fused_adam_gemms": pure_flops / (pure_ms * 1e-3) / 1e12 if pure_ms > 0 else None,
-                "note": "on 1 GPU the dWd/dWe GEMM epilogues also run TF-Adam on Wd/We in place (24 B/param of HBM "
-                        "traffic inside those 2 of the 13 launches), which lowers their FLOP rate but removes the "
-                        "separate optimiser pass",
-                "gemm_launches_per_step": gemm_launches / K, "gemm_share_of_step": gemm_ms / (ms if world == 1 else
-                                                                                             max(ms, 1e-9)),
-                "step_algorithmic_tflops": flops_per_row(c) * B * K / (ms * 1e-3) / 1e12}
-
-    if args.quick:
-        if rank == 0:
-            print(json.dumps({"metric": "GANMF-u train user-rows/s", "value": value, "unit": "rows/s", "n_gpus": world,
-                              "steps": K, "warmup": W, "ms_per_step": ms / K, "quick": True, "clocks": clk.summary(),
-                              "gemm_tflops": achieved, "gemm_share_of_step": roofline["gemm_share_of_step"],
-                              "env": {k_: v_ for k_, v_ in os.environ.items() if k_.startswith("GANMF_")}}))
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- end to end through the public call (host ids in, losses out) -------------------------
-    e2e = None
-    if world == 1:
-        hp = (B, 1, 1, HP["d_lr"], HP["g_lr"], HP["d_reg"], HP["g_reg"], HP["m"], HP["alpha"])
-        pin = torch.from_numpy(rs.permutation(c["users"])[:K * B].astype(np.int32)).pin_memory()
-        eng.train_epoch(pin.numpy()[:W * B], *hp)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        dl, gl = eng.train_epoch(pin.numpy(), *hp)             # H2D ids + all steps + D2H losses + sync
-        dt = time.perf_counter() - t0
-        e2e = {"value": B * K / dt, "unit": "rows/s", "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 8,
-               "api": "ganmf_train_epoch (GANMF.fit's per-epoch call): pinned host row ids in, per-step losses out"}
-    else:
-        e2e = trainer.e2e_epoch(rs, c["users"], K, B, HP)
-        e2e["value"] = world * B * K / (max_over_ranks(e2e.pop("ms")) * 1e-3)
-
-    # ---- evaluator: score -> seen mask -> top-10 -> metric sums, users sharded by rank ---------
-    n_eval = min(args.eval_users, c["users"])
-    test = synthetic_urm(c["users"], c["items"], c["density"] / 4, 4242 + rank)
-    test = sps.csr_matrix(test - test.multiply(urm))
-    test.eliminate_zeros()
-    test.sort_indices()
-    eng.set_test(test, urm)
-    users = np.flatnonzero(np.diff(test.indptr) > 0)[:n_eval].astype(np.int32)
-    eng.evaluate(users, [10], remove_seen=True, want_counts=False)       # warm-up: sizes the device buffers
-    ev_s = 1e30
-    for _ in range(3):                                                    # steady state, best of 3 whole calls
-        barrier()
-        t0 = time.perf_counter()
-        sums, _ = eng.evaluate(users, [10], remove_seen=True, want_counts=False)
-        torch.cuda.synchronize()
-        ev_s = min(ev_s, time.perf_counter() - t0)
-    ev_ms = max_over_ranks(ev_s * 1e3)
-    eval_users_s = world * len(users) / (ev_ms * 1e-3)
-    eval_info = {"metric": "top-10 eval users/s (score -> seen mask -> top-10 -> metric sums)", "value": eval_users_s,
-                 "unit": "users/s", "users": int(len(users)) * world, "hbm_frac_4I_bytes_per_user":
-                 eval_users_s / world * 4 * c["items"] / 1e9 / pk["hbm"], "e2e": True,
-                 "precision_at_10": float(sums[0, 0] / max(len(users), 1))}
-
-    # ---- HBM-bound kernels timed alone (CUDA events, inputs larger than L2): achieved GB/s vs measured copy peak
-    hbm_kernels = None
-    if rank == 0:
-        hbm_kernels = hbm_kernel_rooflines(eng, torch, L, c, pk)
-
-    line = {"metric": "GANMF-u train user-rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": c["name"], "state": "after one full untimed epoch (all 138000 rows hold Adam moments)",
-                       "l2": "per-step working set (weights 221 MB + activations) exceeds the "
-                       "126 MB L2", "parallelism": "dp%d over users; D and item factors replicated, NCCL reduce-scatter / sharded Adam / all-gather" %
-                       world if world > 1 else "single GPU"},
-            "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e, "roofline": roofline,
-            "eval": eval_info, "hbm_kernels": hbm_kernels,
-            "loss_last": [float(losses[K - 1]), float(losses[2 * K - 1])]}
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(c)
+    c = workload(args.workload)
+    with_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick
+    line = run_workload(c, args, torch, dist, world, rank, local_rank, with_cpu)
+    if world == 1 and args.workload == "cfg5" and not args.quick and not args.no_second_record:
+        # the 1-GPU configuration of BASELINE.json (configs[3]) as a second record of the same run
+        line["records"] = [run_workload(workload("cfg4"), args, torch, dist, world, rank, local_rank, with_cpu)]
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -439,7 +588,7 @@ def main():
     return 0
 
 
-def hbm_kernel_rooflines(eng, torch, L, c, pk):
+def hbm_kernel_rooflines(eng, torch, L, c, pk, width_local):
     """top-k (4*I bytes/user), fused Adam (28 B/param) and CSR gather (4*B*ld written) on their own."""
     out = {}
 
@@ -454,9 +603,10 @@ def hbm_kernel_rooflines(eng, torch, L, c, pk):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps * 1e-3
 
-    n, I = 8192, c["items"]
+    I = c["items"]
     ld = (I + 31) // 32 * 32
-    sc = torch.randn((n, ld), device="cuda", dtype=torch.float32)                      # 885 MB >> L2
+    n = max(1024, min(8192, (3 << 30) // (4 * ld)))                                     # <= 3 GiB of scores, >> L2
+    sc = torch.randn((n, ld), device="cuda", dtype=torch.float32)
     idx = torch.empty((n, 10), device="cuda", dtype=torch.int32)
     val = torch.empty((n, 10), device="cuda", dtype=torch.float32)
     t = timed(lambda: L.check(eng.lib.ganmf_k_topk(eng.ctx, sc.data_ptr(), ld, n, I, 10, idx.data_ptr(),
@@ -465,7 +615,7 @@ def hbm_kernel_rooflines(eng, torch, L, c, pk):
     out["topk_rows_kernel(K=10)"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
                                      "frac": gbs / pk["hbm"], "users_per_s": n / t, "bytes_per_user": 4 * I}
     del sc
-    npar = 2 * I * c["E"]                                                               # the two D kernels
+    npar = min(2 * I * c["E"], 1 << 28)                                                 # the two D kernels (<= 4 GiB)
     th, m, v, g = (torch.zeros(npar, device="cuda", dtype=torch.float32) for _ in range(4))
     t = timed(lambda: L.check(eng.lib.ganmf_k_adam(eng.ctx, th.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(),
                                                    npar, 1e-4, 1e-4)))
@@ -474,40 +624,13 @@ def hbm_kernel_rooflines(eng, torch, L, c, pk):
                                 "frac": gbs / pk["hbm"], "bytes_per_param": 28}
     del th, m, v, g
     B = c["B"]
-    dst = torch.empty((B, ld), device="cuda", dtype=torch.float32)
-    t = timed(lambda: L.check(eng.lib.ganmf_k_csr_gather_dense(eng.ctx, 0, B, dst.data_ptr(), ld)), reps=20)
-    gbs = 4.0 * B * ld / t / 1e9
+    ldw = (width_local + 31) // 32 * 32
+    dst = torch.empty((B, ldw), device="cuda", dtype=torch.float32)
+    t = timed(lambda: L.check(eng.lib.ganmf_k_csr_gather_dense(eng.ctx, 0, B, dst.data_ptr(), ldw)), reps=20)
+    gbs = 4.0 * B * ldw / t / 1e9
     out["csr_gather_dense_kernel"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
-                                      "frac": gbs / pk["hbm"], "note": "110 MB output stays in the 126 MB L2"}
+                                      "frac": gbs / pk["hbm"], "output_bytes": 4 * B * ldw}
     return out
-
-
-def cpu_baseline(c):
-    """Oracle port of the reference graph on the host cores, bounded sample (about 10-30 s)."""
-    from oracle import train_oracle as to
-    cores = use_all_host_threads()
-    B, n_users = 256, 4096
-    urm = synthetic_urm(n_users, c["items"], c["density"], 1337)
-    orc = to.GanmfOracle(to.init_ganmf_params(n_users, c["items"], c["k"], c["E"], seed=1234), HP["d_lr"], HP["g_lr"],
-                         dtype=np.float32)
-    rs = np.random.RandomState(0)
-
-    def step():
-        ids = rs.permutation(n_users)[:B]
-        R = to.csr_rows_to_dense(urm, ids)
-        orc.d_step(ids, R, d_reg=HP["d_reg"], m=HP["m"])
-        orc.g_step(ids, R, g_reg=HP["g_reg"], recon_coefficient=HP["alpha"])
-    step()
-    t0 = time.perf_counter()
-    n = 0
-    while n < 3 or (time.perf_counter() - t0 < 12 and n < 40):
-        step()
-        n += 1
-    dt = time.perf_counter() - t0
-    return {"value": B * n / dt, "unit": "rows/s", "cores": cores, "kind": "port",
-            "sample": "%d D+G steps of B=%d rows, %d items, k=250, E=1024 (NumPy/BLAS, all host threads; "
-                      "user-factor table cut to %d rows)" % (n, B, c["items"], n_users),
-            "eval": cpu_eval_baseline(c)}
 
 
 if __name__ == "__main__":

@@ -65,8 +65,8 @@ SIGNATURES = {
     "ganmf_d_forward_phase": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int]),
     "ganmf_set_gemm_sms": (C.c_int, [_ctx, C.c_int]),
     "ganmf_finalize_loss": (C.c_int, [_ctx, C.c_float, C.c_int]),
-    "ganmf_tp_d_phase": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]),
-    "ganmf_tp_g_phase": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]),
+    "ganmf_tp_d_phase": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]),
+    "ganmf_tp_g_phase": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]),
     "ganmf_device_buffer_ld": (C.c_int, [_ctx, C.c_char_p, _i32p]),
     "ganmf_train_epoch": (C.c_int, [_ctx, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                     C.c_float, C.c_float, C.c_float, C.c_float, _f32p, _f32p]),

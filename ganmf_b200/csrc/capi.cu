@@ -859,7 +859,8 @@ static int g_apply_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float
                         int loss_slot, bool v_done = false, float adam_step = 0.f) {
   if (loss_slot < 0 || loss_slot >= c->losses_cap) return fail("loss slot out of range");
   if (c->cfg.kind == GANMF_KIND_GANMF)
-    gloss_kernel<<<1, 1, 0, c->st>>>(c->sc, alpha, (double)n_global * c->Wg, (double)n_global * c->E);
+    gloss_kernel<<<1, 1, 0, c->st>>>(c->sc, alpha, c->tp_rank == 0 ? alpha : 0.f, (double)n_global * c->Wg,
+                                     (double)n_global * c->E);
   else
     dis_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, 1, alpha, (double)n_global, (double)n_global * c->E);
   CU(cudaGetLastError());
@@ -1048,8 +1049,10 @@ static int tp_forward_codes(ganmf_ctx* c, int ids_offset, int B) {
   return gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, 2 * B, c->E, c->W, e2);
 }
 
-int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, float reg, float m_hinge) {
+int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, float reg, float m_hinge,
+                     int loss_slot) {
   RC(tp_check(c, ids_offset, B));
+  if (loss_slot < 0 || loss_slot >= c->losses_cap) return fail("loss slot out of range");
   Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
   const float* rs = c->sc->row_scale;
   switch (phase) {
@@ -1101,7 +1104,10 @@ int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
         a.l2_out = (i == 1 || c->tp_rank == 0) ? &c->sc->l2 : nullptr;
         CU(fused_adam(a, c->st));
       }
-      c->launches += 2;
+      // per-rank partial loss: the hinge / reconstruction part (identical on every rank) is logged by rank 0
+      finalize_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, reg, c->losses, loss_slot, c->tp_rank == 0 ? 1.f : 0.f, 0.f);
+      CU(cudaGetLastError());
+      c->launches += 3;
       return 0;
     }
     default:
@@ -1109,8 +1115,10 @@ int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
   }
 }
 
-int ganmf_tp_g_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, float reg, float alpha) {
+int ganmf_tp_g_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, float reg, float alpha,
+                     int loss_slot) {
   RC(tp_check(c, ids_offset, B));
+  if (loss_slot < 0 || loss_slot >= c->losses_cap) return fail("loss slot out of range");
   Param *We = &c->params[0], *Wd = &c->params[2], *bd = &c->params[3];
   Param& V = c->params[c->n_d + 1];
   const double N = (double)B * c->Wg, M = (double)B * c->E;
@@ -1143,16 +1151,24 @@ int ganmf_tp_g_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
       RC(gemm(c, c->dH2.row(B), c->dH2.ld, 0, We->w.p, We->w.ld, 0, B, c->W, c->E, e7));
       Epilogue e9;                                                                 // G9: dPb (partial over items)
       e9.out = c->dPb.p; e9.ldo = c->dPb.ld;
-      RC(gemm(c, c->dF.p, c->dF.ld, 0, V.w.p, V.w.ld, 1, B, c->k, c->W, e9));
+      return gemm(c, c->dF.p, c->dF.ld, 0, V.w.p, V.w.ld, 1, B, c->k, c->W, e9);
+    }
+    case 4: {                                                                      // (runs while dPb is summed)
       Epilogue e8;                                                                 // G8: dV (slice)
       e8.out = V.g; e8.ldo = V.w.ld;
       return gemm(c, c->dF.p, c->dF.ld, 1, c->Pb.p, c->Pb.ld, 1, c->W, c->k, B, e8);
     }
-    case 4:
+    case 5:
+      // Adam on the batch rows of the (replicated) user factors and on the item-factor slice; the logged loss
+      // is this rank's share: (1-a) * (slice of the reconstruction sum) / N [+ a * fm on rank 0] + reg/2 * l2
       c->last_ids_offset = ids_offset;
-      return g_apply_impl(c, ids_offset, B, B, lr, reg, alpha, 0);
+      RC(g_apply_impl(c, ids_offset, B, B, lr, reg, alpha, loss_slot));
+      finalize_loss_kernel<<<1, 1, 0, c->st>>>(c->sc, reg, c->losses, loss_slot, 1.f, c->tp_rank == 0 ? 1.f : 0.f);
+      CU(cudaGetLastError());
+      c->launches++;
+      return 0;
     default:
-      return fail("ganmf_tp_g_phase: phase must be 1..4");
+      return fail("ganmf_tp_g_phase: phase must be 1..5");
   }
 }
 

@@ -385,16 +385,22 @@ __global__ void hinge_gate_kernel(StepScalars* s, float m_hinge, double n_elems)
   s->loss_main = Lr32 + fmaxf(0.f, hinge);
 }
 
-// gloss pieces (GANMF.py:133-135): (1-a)*Lf + a*mean((Hr-Hf)^2)
-__global__ void gloss_kernel(StepScalars* s, float alpha, double n_elems, double m_elems) {
+// gloss pieces (GANMF.py:133-135): (1-a)*Lf + a*mean((Hr-Hf)^2).  w_fm = a, except on the ranks > 0 of an
+// item-sharded group, where it is 0: there sumsq[0] holds this rank's item slice of the reconstruction sum, the
+// loss is linear in it, and the per-rank values are summed by the caller (the feature-matching term, identical
+// on every rank, must enter that sum once).
+__global__ void gloss_kernel(StepScalars* s, float alpha, float w_fm, double n_elems, double m_elems) {
   const float Lf = (float)(s->sumsq[0] / n_elems);
   const float fm = (float)(s->fm / m_elems);
-  s->loss_main = (1.f - alpha) * Lf + alpha * fm;
+  s->loss_main = (1.f - alpha) * Lf + w_fm * fm;
 }
 
-// losses[slot] = loss_main + reg * l2 / 2     (l2 accumulated by the Adam kernel, pre-update)
-__global__ void finalize_loss_kernel(const StepScalars* s, float reg, float* losses, int slot) {
-  losses[slot] = s->loss_main + (float)(reg * 0.5 * (s->l2 + s->l2_shard));
+// losses[slot] = loss_main + reg * l2 / 2     (l2 accumulated by the Adam kernel, pre-update).
+// Item-sharded groups log per-rank PARTIAL losses (summed over ranks once per epoch): main_w / shard_w are 0
+// where loss_main / the l2 of a replicated tensor is already counted by another rank.
+__global__ void finalize_loss_kernel(const StepScalars* s, float reg, float* losses, int slot, float main_w = 1.f,
+                                     float shard_w = 1.f) {
+  losses[slot] = main_w * s->loss_main + (float)(reg * 0.5 * (s->l2 + shard_w * s->l2_shard));
 }
 
 // ----------------------------------------------------------------------------- activations

@@ -199,11 +199,11 @@ class Engine(object):
     def d_forward_phase(self, ids_offset, B, phase):
         L.check(self.lib.ganmf_d_forward_phase(self.ctx, ids_offset, B, phase))
 
-    def tp_d_phase(self, phase, ids_offset, B, lr, reg, m_hinge):
-        L.check(self.lib.ganmf_tp_d_phase(self.ctx, phase, ids_offset, B, lr, reg, m_hinge))
+    def tp_d_phase(self, phase, ids_offset, B, lr, reg, m_hinge, loss_slot):
+        L.check(self.lib.ganmf_tp_d_phase(self.ctx, phase, ids_offset, B, lr, reg, m_hinge, loss_slot))
 
-    def tp_g_phase(self, phase, ids_offset, B, lr, reg, recon_coefficient):
-        L.check(self.lib.ganmf_tp_g_phase(self.ctx, phase, ids_offset, B, lr, reg, recon_coefficient))
+    def tp_g_phase(self, phase, ids_offset, B, lr, reg, recon_coefficient, loss_slot):
+        L.check(self.lib.ganmf_tp_g_phase(self.ctx, phase, ids_offset, B, lr, reg, recon_coefficient, loss_slot))
 
     def finalize_loss(self, reg, loss_slot):
         L.check(self.lib.ganmf_finalize_loss(self.ctx, reg, loss_slot))

@@ -205,6 +205,138 @@ class DataParallelTrainer(object):
                 "api": "DataParallelTrainer.train_epoch: host row ids in, per-step losses out"}
 
 
+class ItemShardedTrainer(object):
+    """GANMF training partitioned over ITEMS: rank r holds columns [lo_r, hi_r) of the
+    training matrix and the matching slices of We (rows), Wd / bd (columns) and V (rows); the user factors and the
+    encoder bias are replicated.  Every rank runs the WHOLE minibatch on its slice, so
+
+      * everything indexed by items -- residuals, dWe, dWd, dbd, dV and their Adam updates (fused into the
+        weight-gradient GEMM epilogues, as on one GPU) -- is local: no weight or weight gradient crosses NVLink;
+      * the contractions over items are partial sums, all-reduced (SUM) per step:
+          D: codes [2B, E] -> 2 energy sums (the hinge gate is global) -> code gradients [2B, E] + dbe [E]
+          G: codes [2B, E] -> fake code gradients [B, E] -> user-factor gradients [B, k]
+
+    At cfg5 (I = 200 000, E = 1024, B = 8 x 1024) that is 0.23 GB of activations per D+G step pair instead of the
+    1.64 GB reduce-scatter + 1.64 GB all-gather of the data-parallel weight exchange (and the optimiser traffic of
+    the discriminator is divided by N).  Same arithmetic as one GPU stepping on the whole minibatch, up to the
+    summation order over items.  The loss log holds per-rank partial losses; train_epoch sums them once.
+
+    `engines`: the engine of this process, or (tests, one process) a list of the engines of ALL ranks living on
+    one device -- the sums are then formed in place with torch instead of NCCL.  `buffers`: per-engine dicts of
+    host tensors for a stand-in engine (CPU/gloo tests)."""
+
+    NAMES = ("tp_h2", "tp_dh2", "tp_dpb", "step_scalars")
+
+    def __init__(self, engines, group=None, buffers=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.engines = list(engines) if isinstance(engines, (list, tuple)) else [engines]
+        self.local = len(self.engines) > 1
+        if buffers is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            buffers = []
+            for e in self.engines:
+                e.set_stream(torch.cuda.current_stream().cuda_stream)
+                buffers.append({n: torch.as_tensor(e.device_buffer(n), device=dev) for n in self.NAMES})
+        elif isinstance(buffers, dict):
+            buffers = [buffers]
+        self.buf = buffers
+        e0 = self.engines[0]
+        self.ld_h, self.ld_p = e0.device_buffer_ld("tp_h2"), e0.device_buffer_ld("tp_dpb")
+        self.world = len(self.engines) if self.local else dist.get_world_size(group)
+
+    def _sum(self, name, lo, hi, async_op=False):
+        if self.local:
+            views = [b[name][lo:hi] for b in self.buf]
+            tot = views[0].clone()
+            for v in views[1:]:
+                tot += v
+            for v in views:
+                v.copy_(tot)
+            return None
+        return self.dist.all_reduce(self.buf[0][name][lo:hi], op=self.dist.ReduceOp.SUM, group=self.group,
+                                    async_op=async_op)
+
+    def _phase(self, fn, *a):
+        for e in self.engines:
+            getattr(e, fn)(*a)
+
+    def d_step(self, ids_offset, B, lr, reg, m_hinge, loss_slot):
+        a = (ids_offset, B, lr, reg, m_hinge, loss_slot)
+        self._phase("tp_d_phase", 1, *a)
+        self._sum("tp_h2", 0, 2 * B * self.ld_h)
+        self._phase("tp_d_phase", 2, *a)
+        self._sum("step_scalars", 0, 2)
+        self._phase("tp_d_phase", 3, *a)
+        self._sum("tp_dh2", 0, (2 * B + 1) * self.ld_h)
+        self._phase("tp_d_phase", 4, *a)
+
+    def g_step(self, ids_offset, B, lr, reg, recon_coefficient, loss_slot):
+        a = (ids_offset, B, lr, reg, recon_coefficient, loss_slot)
+        self._phase("tp_g_phase", 1, *a)
+        self._sum("tp_h2", 0, 2 * B * self.ld_h)
+        self._phase("tp_g_phase", 2, *a)
+        self._sum("tp_dh2", B * self.ld_h, 2 * B * self.ld_h)
+        self._phase("tp_g_phase", 3, *a)
+        w = self._sum("tp_dpb", 0, B * self.ld_p, async_op=True)      # travels while the item-factor gradient is computed
+        self._phase("tp_g_phase", 4, *a)
+        if w is not None:
+            w.wait()
+        self._phase("tp_g_phase", 5, *a)
+
+    def read_losses(self, n):
+        """Per-step losses = sum over ranks of the per-rank partial losses."""
+        if self.local:
+            return np.sum([e.read_losses(n) for e in self.engines], axis=0, dtype=np.float32)
+        part = self.engines[0].read_losses(n)
+        if self.world > 1:
+            dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
+            t = self.torch.from_numpy(part).to(dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            part = t.cpu().numpy()
+        return part
+
+    def train_epoch(self, perm, batch_size, d_steps, g_steps, hp):
+        """Reference schedule (GANMF.py:172-203) on the GLOBAL id stream `perm` (the same on every rank;
+        batch_size = rows of the whole minibatch).  Returns (d_losses, g_losses)."""
+        n = len(perm)
+        nb = (n + batch_size - 1) // batch_size
+        for e in self.engines:
+            e.upload_ids(perm)
+        slot = 0
+        for _ in range(d_steps):
+            for b in range(nb):
+                off = b * batch_size
+                self.d_step(off, min(batch_size, n - off), hp["d_lr"], hp["d_reg"], hp["m"], slot)
+                slot += 1
+        nd = slot
+        for _ in range(g_steps):
+            for b in range(nb):
+                off = b * batch_size
+                self.g_step(off, min(batch_size, n - off), hp["g_lr"], hp["g_reg"], hp["alpha"], slot)
+                slot += 1
+        losses = self.read_losses(slot)
+        return losses[:nd], losses[nd:]
+
+    def e2e_epoch(self, rs, n_rows, K, B, hp):
+        """bench.py: host ids in, losses out, wall clock around the whole call (ms)."""
+        perm = rs.permutation(n_rows)[:K * B].astype(np.int32)
+        self.dist.barrier()
+        self.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        self.train_epoch(perm, B, 1, 1, hp)
+        self.torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        return {"ms": ms, "unit": "rows/s", "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 8,
+                "api": "ItemShardedTrainer.train_epoch: host row ids in, per-step losses out"}
+
+
+def item_slices(n_items, world_size):
+    """[lo, hi) column ranges of the item-sharded layout (contiguous, sizes differ by at most one)."""
+    return [shard_rows(n_items, world_size, r) for r in range(world_size)]
+
+
 def shard_rows(n_rows, world_size, rank):
     """Contiguous row range [lo, hi) owned by `rank`."""
     base, rem = divmod(n_rows, world_size)

@@ -145,17 +145,21 @@ int ganmf_finalize_loss(ganmf_ctx* ctx, float reg, int loss_slot);
  * (GANMF.py:186-187,200-201) on the WHOLE minibatch of B rows restricted to this context's item slice, cut
  * where partial sums over the item slices must be added up by the caller (NCCL all-reduce, SUM):
  *   D: phase 1 (profiles, F = Pb.V^T, partial codes)      -> sum "tp_h2"[0 : 2B*ld]
- *      phase 2 (residuals, energy sums)                    -> sum "step_scalars"[0:2]
+ *      phase 2 (residuals, energy sums)                    -> sum "step_scalars"[0:2]   (the hinge gate is global)
  *      phase 3 (hinge gate, dbd, partial dH and dbe)       -> sum "tp_dh2"[0 : (2B+1)*ld]  (row 2B = dbe)
- *      phase 4 (dWd, dWe with Adam in the epilogue, biases)-> sum "step_scalars"[3:4], ganmf_finalize_loss
+ *      phase 4 (dWd, dWe with Adam in the epilogue, biases, loss log)
  *   G: phase 1 (as D)                                      -> sum "tp_h2"[0 : 2B*ld]
- *      phase 2 (fake residual, feature matching, partial dHf) -> sum "tp_dh2"[B*ld : 2B*ld], "step_scalars"[0:1]
- *      phase 3 (dF, dV, partial dPb)                       -> sum "tp_dpb"[0 : B*ld]
- *      phase 4 (Adam on the batch rows of P and on the V slice) -> sum "step_scalars"[3:4], ganmf_finalize_loss
- * ld = leading dimension reported by ganmf_device_buffer_ld.  Every rank passes the same ids. */
-int ganmf_tp_d_phase(ganmf_ctx* ctx, int phase, int ids_offset, int B, float lr, float reg, float m_hinge);
+ *      phase 2 (fake residual, feature matching, partial dHf) -> sum "tp_dh2"[B*ld : 2B*ld]
+ *      phase 3 (dF, partial dPb)                           -> sum "tp_dpb"[0 : B*ld]  (may overlap phase 4)
+ *      phase 4 (dV)
+ *      phase 5 (Adam on the batch rows of P and on the V slice, loss log)
+ * ld = leading dimension reported by ganmf_device_buffer_ld.  Every rank passes the same ids.  The loss log holds
+ * per-rank PARTIAL losses (rank 0: the data term + its l2 share; others: their l2 / reconstruction share): the
+ * step's loss is their SUM over ranks, formed by the caller once per epoch. */
+int ganmf_tp_d_phase(ganmf_ctx* ctx, int phase, int ids_offset, int B, float lr, float reg, float m_hinge,
+                     int loss_slot);
 int ganmf_tp_g_phase(ganmf_ctx* ctx, int phase, int ids_offset, int B, float lr, float reg,
-                     float recon_coefficient);
+                     float recon_coefficient, int loss_slot);
 /* One epoch of the reference schedule (GANMF.py:172-203): shuffled row ids in, d_steps full D
  * passes then g_steps full G passes over the same batches, per-batch losses out (host).
  * H2D: n_rows ids; D2H: the losses.  Synchronises once at the end. */
