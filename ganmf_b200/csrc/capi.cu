@@ -14,6 +14,7 @@
 
 #include "eval_kernels.cuh"
 #include "kernels.cuh"
+#include "score_select.cuh"
 #include "tc_gemm.cuh"
 
 using namespace ganmf;
@@ -105,6 +106,14 @@ struct ganmf_ctx {
   double* usums = nullptr; int* icounts = nullptr; size_t icounts_cap = 0;
   int* cut_dev = nullptr;
   int* eval_users = nullptr; int eval_users_cap = 0;
+  // fused scorer (score_select.cuh): gathered query factors, candidate lists, fallback bookkeeping
+  bool eval_fused = true;              // GANMF_EVAL_FUSED=0: always the materialised split-TF32 scorer (A/B, tests)
+  Mat Qg;
+  float* cand_val = nullptr; int* cand_idx = nullptr; size_t cand_cap = 0;
+  unsigned int* vmax_bits = nullptr;   // max_j ||ranked factor row j|| (float bits)
+  int* fb_count = nullptr; int* fb_rows = nullptr; int* fb_users = nullptr; size_t fb_cap = 0;
+  int* fb_idx = nullptr; float* fb_val = nullptr; size_t fb_topk_cap = 0;
+  long long fused_rows = 0, fallback_rows = 0;      // statistics since ganmf_create
   long long launches = 0;
   int ev_total = 0, ev_done = 0, ev_ncut = 0, ev_K = 0;     // streaming evaluation (ganmf_eval_begin..end)
   int last_ids_offset = 0;
@@ -259,6 +268,7 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   if (const char* pm = getenv("GANMF_PAIR")) c->pair_mode = atoi(pm);                  // A/B switch / tests
   if (const char* nl = getenv("GANMF_NO_LAZY_ADAM")) c->lazy_p = !(nl[0] == '1');       // A/B switch
   if (const char* lc = getenv("GANMF_LAZY_LOG_CAP")) c->log_cap = std::max(1, atoi(lc)); // tests: force log wrap
+  if (const char* ef = getenv("GANMF_EVAL_FUSED")) c->eval_fused = !(ef[0] == '0');     // A/B switch / tests
   c->B = cfg->max_batch; c->W = cfg->width; c->Wp = rup(cfg->width, 32);
   c->k = cfg->num_factors; c->kp = rup(c->k, 32);
   c->Wg = cfg->global_width > 0 ? cfg->global_width : cfg->width;
@@ -395,6 +405,8 @@ void ganmf_destroy(ganmf_ctx* c) {
   cudaFree(c->tb_popn); cudaFree(c->tb_haspop); cudaFree(c->rmse_scratch);
   cudaFree(c->scores); cudaFree(c->topk_idx); cudaFree(c->topk_val); cudaFree(c->uvals);
   cudaFree(c->usums); cudaFree(c->icounts); cudaFree(c->cut_dev); cudaFree(c->eval_users);
+  cudaFree(c->Qg.p); cudaFree(c->cand_val); cudaFree(c->cand_idx); cudaFree(c->vmax_bits);
+  cudaFree(c->fb_count); cudaFree(c->fb_rows); cudaFree(c->fb_users); cudaFree(c->fb_idx); cudaFree(c->fb_val);
   for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
   delete c;
 }
@@ -1493,6 +1505,139 @@ static int mask_and_topk(ganmf_ctx* c, int n, int n_items, int remove_seen, int 
   return 0;
 }
 
+// ---- fused scoring -> mask -> top-K (score_select.cuh) ----------------------------------------------------
+constexpr int FB_BLOCK = 64;           // fallback rows scored exactly per pass
+// |tf32 score - exact| <= gamma * ||q|| * ||v||: both operands rounded to tf32 (2^-11 each if the TMA rounds to
+// nearest, 2^-10 if it truncated -- the bound assumes the worse), products summed in fp32 by the tensor core
+static float fused_gamma(int k) { return 1.05f * (2.0f / 1024.0f + (float)(k + 8) * 1.2e-7f); }
+static bool fused_ok(ganmf_ctx* c, int K) { return c->eval_fused && K <= 24 && c->k <= SS_MAX_KB * TC_BK; }
+
+static int ensure_fused_buffers(ganmf_ctx* c, int block, int K) {
+  const int n_items = c->cfg.item_mode ? c->cfg.n_rows : c->W;
+  if (c->Qg.rows < block) {
+    cudaFree(c->Qg.p);
+    RC(mat_alloc(&c->Qg, block, c->k));
+  }
+  if (c->eval_users_cap < block) {
+    cudaFree(c->eval_users);
+    RC(dalloc(&c->eval_users, (size_t)block));
+    c->eval_users_cap = block;
+  }
+  if ((size_t)block * K > c->topk_cap) {
+    cudaFree(c->topk_idx); cudaFree(c->topk_val);
+    RC(dalloc(&c->topk_idx, (size_t)block * K));
+    RC(dalloc(&c->topk_val, (size_t)block * K));
+    c->topk_cap = (size_t)block * K;
+  }
+  if (!c->vmax_bits) { RC(dalloc(&c->vmax_bits, 1)); RC(dalloc(&c->fb_count, 1)); }
+  if ((size_t)block > c->fb_cap) {
+    cudaFree(c->fb_rows);
+    RC(dalloc(&c->fb_rows, (size_t)block));
+    c->fb_cap = block;
+  }
+  if (!c->fb_users) RC(dalloc(&c->fb_users, (size_t)FB_BLOCK));
+  if ((size_t)FB_BLOCK * K > c->fb_topk_cap) {
+    cudaFree(c->fb_idx); cudaFree(c->fb_val);
+    RC(dalloc(&c->fb_idx, (size_t)FB_BLOCK * K));
+    RC(dalloc(&c->fb_val, (size_t)FB_BLOCK * K));
+    c->fb_topk_cap = (size_t)FB_BLOCK * K;
+  }
+  const size_t sc_need = (size_t)FB_BLOCK * rup(n_items, 32);    // exact score rows of the fallback
+  if (sc_need > c->scores_elems) {
+    cudaFree(c->scores);
+    RC(dalloc(&c->scores, sc_need));
+    c->scores_elems = sc_need;
+  }
+  return 0;
+}
+
+// once per call: bring the lazily updated factors up to date, norm bound of the ranked side
+static int prepare_fused(ganmf_ctx* c) {
+  RC(p_flush(c));
+  const Param& other = c->cfg.item_mode ? c->params[c->n_d] : c->params[c->n_d + 1];
+  CU(cudaMemsetAsync(c->vmax_bits, 0, 4, c->st));
+  row_norm_max_kernel<<<(other.w.rows * 32 + 255) / 256, 256, 0, c->st>>>(other.w.p, other.w.rows, c->k, other.w.ld,
+                                                                         c->vmax_bits);
+  CU(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+// top-K lists (c->topk_idx / c->topk_val, rows [0, n)) of the users at users_dev; prepare_fused() first
+static int fused_topk_block(ganmf_ctx* c, int n, const int* users_dev, int remove_seen, int K) {
+  const Param& rows_of = c->cfg.item_mode ? c->params[c->n_d + 1] : c->params[c->n_d];
+  const Param& other = c->cfg.item_mode ? c->params[c->n_d] : c->params[c->n_d + 1];
+  const int n_items = other.w.rows;
+  const Csr& seen = c->csr[GANMF_CSR_SEEN];
+  if (remove_seen) {
+    if (!seen.indptr) return fail("seen CSR not set");
+    if (seen.n_cols != n_items) return fail("seen CSR has %d columns, scores have %d", seen.n_cols, n_items);
+  }
+  gather_rows_kernel<<<n, 64, 0, c->st>>>(rows_of.w.p, users_dev, c->Qg.p, c->Qg.ld);
+  CU(cudaGetLastError());
+  ScoreSelectCall sc;
+  sc.Q = c->Qg.p; sc.ldq = c->Qg.ld; sc.V = other.w.p; sc.ldv = other.w.ld;
+  sc.n_rows = n; sc.n_items = n_items; sc.k = c->k;
+  sc.KP = K <= 10 ? 16 : 32;
+  sc.segs = score_select_segments(n, n_items, c->gemm_sm_cap > 0 ? c->gemm_sm_cap : 148);
+  sc.users = users_dev;
+  sc.seen_indptr = remove_seen ? seen.indptr : nullptr;
+  sc.seen_indices = remove_seen ? seen.indices : nullptr;
+  const size_t need = (size_t)n * 2 * sc.segs * sc.KP;             // candidate lists of this block
+  if (need > c->cand_cap) {
+    CU(cudaStreamSynchronize(c->st));
+    cudaFree(c->cand_val); cudaFree(c->cand_idx);
+    RC(dalloc(&c->cand_val, need));
+    RC(dalloc(&c->cand_idx, need));
+    c->cand_cap = need;
+  }
+  sc.cand_val = c->cand_val; sc.cand_idx = c->cand_idx;
+  sc.cache = &c->tmaps; sc.max_ctas = c->gemm_sm_cap;
+  cudaError_t e = score_select(sc, c->st);
+  if (e != cudaSuccess) return fail("score_select(n=%d items=%d k=%d) -> %s", n, n_items, c->k, cudaGetErrorString(e));
+  CU(cudaMemsetAsync(c->fb_count, 0, 4, c->st));
+  const int NL = 2 * sc.segs;
+  const float gamma = fused_gamma(c->k);
+  if (sc.KP == 16)
+    rescore_kernel<16><<<(n + 3) / 4, 128, 0, c->st>>>(c->cand_val, c->cand_idx, NL, n, K, c->Qg.p, c->Qg.ld, other.w.p,
+                                                       other.w.ld, c->k, c->vmax_bits, gamma, c->topk_idx, c->topk_val,
+                                                       c->fb_count, c->fb_rows);
+  else
+    rescore_kernel<32><<<(n + 3) / 4, 128, 0, c->st>>>(c->cand_val, c->cand_idx, NL, n, K, c->Qg.p, c->Qg.ld, other.w.p,
+                                                       other.w.ld, c->k, c->vmax_bits, gamma, c->topk_idx, c->topk_val,
+                                                       c->fb_count, c->fb_rows);
+  CU(cudaGetLastError());
+  c->launches += 3;
+  int n_fb = 0;
+  CU(cudaMemcpyAsync(&n_fb, c->fb_count, 4, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  c->fused_rows += n;
+  c->fallback_rows += n_fb;
+  // rows without a certificate: exact score rows -> the materialised mask / top-k kernels -> back to their slots
+  const int ild = rup(n_items, 32);
+  for (int f0 = 0; f0 < n_fb; f0 += FB_BLOCK) {
+    const int nf = std::min(FB_BLOCK, n_fb - f0);
+    exact_score_rows_kernel<<<dim3(std::max(1, 148 * 4 / nf), nf), 256, 0, c->st>>>(
+        c->fb_rows, f0, nf, c->Qg.p, c->Qg.ld, other.w.p, other.w.ld, c->k, n_items, c->scores, ild);
+    gather_ids_kernel<<<1, FB_BLOCK, 0, c->st>>>(users_dev, c->fb_rows, f0, nf, c->fb_users);
+    if (remove_seen) mask_seen_kernel<<<nf, 128, 0, c->st>>>(c->scores, ild, c->fb_users, seen.indptr, seen.indices);
+    CU(cudaGetLastError());
+    CU(topk_rows(c->scores, ild, nf, n_items, K, c->fb_idx, c->fb_val, c->st));
+    scatter_topk_kernel<<<(nf * K + 127) / 128, 128, 0, c->st>>>(c->fb_idx, c->fb_val, c->fb_rows, f0, nf, K, c->topk_idx,
+                                                                c->topk_val);
+    CU(cudaGetLastError());
+    c->launches += 5;
+  }
+  return 0;
+}
+
+int ganmf_eval_stats(ganmf_ctx* c, int64_t* fused_rows, int64_t* fallback_rows) {
+  if (!c) return fail("null ctx");
+  if (fused_rows) *fused_rows = c->fused_rows;
+  if (fallback_rows) *fallback_rows = c->fallback_rows;
+  return 0;
+}
+
 int ganmf_mask_topk(ganmf_ctx* c, float* scores_host, int n, int n_items, const int32_t* users, int remove_seen,
                     int K, int32_t* idx_host, float* val_host, int write_back) {
   if (!c || !scores_host || n <= 0 || n_items <= 0) return fail("bad argument");
@@ -1532,6 +1677,18 @@ int ganmf_recommend(ganmf_ctx* c, const int32_t* users, int n, int remove_seen, 
                     float* val_host, float* masked_scores_host) {
   if (!c || !users || n <= 0) return fail("bad argument");
   RC(check_users(c, users, n));
+  if (K < 1 || K > TK_MAXK) return fail("top-K supports 1 <= K <= %d (got %d)", TK_MAXK, K);
+  if (!masked_scores_host && fused_ok(c, K)) {
+    // nobody asked for the score rows: fused scorer, the n x n_items matrix never exists
+    RC(ensure_fused_buffers(c, n, K));
+    CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    RC(prepare_fused(c));
+    RC(fused_topk_block(c, n, c->eval_users, remove_seen, K));
+    CU(cudaMemcpyAsync(idx_host, c->topk_idx, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->st));
+    if (val_host) CU(cudaMemcpyAsync(val_host, c->topk_val, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+  }
   RC(ensure_eval_buffers(c, n, K, 0));
   const int n_items = n_items_of(c), ild = rup(n_items, 32);
   CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
@@ -1583,12 +1740,24 @@ int ganmf_set_eval_tables(ganmf_ctx* c, const float* gain, const float* gain_des
 // per-user metric values for n rows whose lists are in c->topk_idx; `uvals` points at the first of those
 // rows inside the per-user value table.  The running sums are formed afterwards by accumulate_users().
 static int metrics_block(ganmf_ctx* c, int n, int K, int n_cut, int n_items, bool with_rmse,
-                         const int* users_dev, double* uvals) {
+                         const int* users_dev, double* uvals, bool fused = false, int remove_seen = 0) {
   const int total = n * n_cut;
   user_metrics_kernel<<<(total + 127) / 128, 128, 0, c->st>>>(c->topk_idx, K, users_dev, n, c->cut_dev, n_cut,
                                                             c->tb, uvals, c->icounts, n_items);
   CU(cudaGetLastError());
   c->launches++;
+  if (with_rmse && fused) {
+    // no score matrix exists: exact scores of the test items only (query rows are still in c->Qg)
+    const Param& other = c->cfg.item_mode ? c->params[c->n_d] : c->params[c->n_d + 1];
+    const Csr& te = c->csr[GANMF_CSR_TEST];
+    const Csr& seen = c->csr[GANMF_CSR_SEEN];
+    user_rmse_exact_kernel<<<(n + 3) / 4, 128, 0, c->st>>>(c->Qg.p, c->Qg.ld, other.w.p, other.w.ld, c->k, users_dev, n,
+                                                         n_cut, c->tb, te.data, remove_seen ? seen.indptr : nullptr,
+                                                         remove_seen ? seen.indices : nullptr, c->rmse_scratch, uvals);
+    CU(cudaGetLastError());
+    c->launches++;
+    return 0;
+  }
   if (with_rmse) {
     const Csr& te = c->csr[GANMF_CSR_TEST];
     user_rmse_kernel<<<(n + 63) / 64, 64, 0, c->st>>>(c->scores, rup(n_items, 32), users_dev, n, n_cut, c->tb,
@@ -1630,11 +1799,20 @@ int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_
   // The reference scores min(1000, 1e8/n_items) users at a time to bound HOST memory (Evaluator.py:238);
   // the result does not depend on the block size, so on the device a block is as many users as a
   // 1 GiB score buffer holds (at most 8192): fuller kernels, fewer launches.
-  if (block <= 0) block = (int)std::min<long long>(8192, std::max<long long>(1, (1LL << 28) / rup(n_items, 32)));
-  // buffers are sized for the full block even when this call has fewer users, so later (larger) calls
-  // never re-allocate: cudaMalloc of a GiB-class buffer costs far more than the evaluation itself
-  RC(ensure_eval_buffers(c, block, K, n_cut));
-  block = std::min(block, std::max(n_users, 1));
+  const bool fused = fused_ok(c, K);
+  if (fused) {
+    // fused scorer: no score matrix, so a block is bounded only by the candidate lists (<= 128 K users)
+    block = block > 0 ? block : (1 << 17);
+    block = std::min(block, std::max(n_users, 1));
+    RC(ensure_fused_buffers(c, block, K));
+    RC(ensure_eval_buffers(c, 1, K, n_cut));           // metric tables (usums, icounts, cut_dev)
+  } else {
+    if (block <= 0) block = (int)std::min<long long>(8192, std::max<long long>(1, (1LL << 28) / rup(n_items, 32)));
+    // buffers are sized for the full block even when this call has fewer users, so later (larger) calls
+    // never re-allocate: cudaMalloc of a GiB-class buffer costs far more than the evaluation itself
+    RC(ensure_eval_buffers(c, block, K, n_cut));
+    block = std::min(block, std::max(n_users, 1));
+  }
   if (c->eval_users_cap < n_users) {                       // all user ids go up once
     cudaFree(c->eval_users);
     RC(dalloc(&c->eval_users, (size_t)n_users));
@@ -1650,13 +1828,18 @@ int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_
   CU(cudaMemcpyAsync(c->cut_dev, cutoffs, (size_t)n_cut * 4, cudaMemcpyHostToDevice, c->st));
   CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
   CU(cudaMemsetAsync(c->icounts, 0, (size_t)n_cut * n_items * 4, c->st));
-  RC(prepare_item_factors(c));
+  if (fused) RC(prepare_fused(c));
+  else RC(prepare_item_factors(c));
   for (int s = 0; s < n_users; s += block) {
     const int n = std::min(block, n_users - s);
     const int* ud = c->eval_users + s;
-    RC(score_block(c, n, ud));
-    RC(mask_and_topk(c, n, n_items, remove_seen, K, ud));
-    RC(metrics_block(c, n, K, n_cut, n_items, true, ud, c->uvals + (size_t)s * n_cut * MC_NCOL));
+    if (fused) {
+      RC(fused_topk_block(c, n, ud, remove_seen, K));
+    } else {
+      RC(score_block(c, n, ud));
+      RC(mask_and_topk(c, n, n_items, remove_seen, K, ud));
+    }
+    RC(metrics_block(c, n, K, n_cut, n_items, true, ud, c->uvals + (size_t)s * n_cut * MC_NCOL, fused, remove_seen));
   }
   RC(accumulate_users(c, n_users, n_cut));
   CU(cudaMemcpyAsync(sums_host, c->usums, (size_t)n_cut * MC_NCOL * 8, cudaMemcpyDeviceToHost, c->st));

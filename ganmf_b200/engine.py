@@ -323,6 +323,12 @@ class Engine(object):
                                         counts.ctypes.data_as(L._i64p) if counts is not None else None))
         return sums, counts
 
+    def eval_stats(self):
+        """(rows ranked by the fused scorer, rows that needed the exact fallback) since the engine was created."""
+        a, b = C.c_int64(), C.c_int64()
+        L.check(self.lib.ganmf_eval_stats(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def evaluate_scores(self, score_fn, users, cutoffs, remove_seen=True, block_size=1000):
         """Streaming evaluation of an arbitrary scorer: score_fn(user_ids) -> float32 [n, n_items] on the host;
         mask, top-k and metric arithmetic run on the device."""

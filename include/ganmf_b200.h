@@ -207,6 +207,12 @@ int ganmf_set_eval_tables(ganmf_ctx* ctx, const float* test_gain_host, const flo
 int ganmf_evaluate(ganmf_ctx* ctx, const int32_t* user_ids_host, int n_users, const int32_t* cutoffs_host,
                    int n_cutoffs, int remove_seen, int block_size, double* sums_host,
                    int64_t* item_counts_host);
+/* ganmf_recommend (without score rows) and ganmf_evaluate rank with the fused scorer when the largest cutoff is
+ * <= 24 and num_factors <= 256: one TF32 tensor-core pass keeps per-row candidate lists in its epilogue (scores
+ * never reach HBM), the candidates are re-scored exactly -- fl32(sum_k fp64(p_k v_k)) -- and each list carries a
+ * certificate that it equals the top K of the exact score row; rows without one fall back to exact score rows +
+ * the materialised top-k.  Counters since ganmf_create: rows ranked by the fused scorer / rows that fell back. */
+int ganmf_eval_stats(ganmf_ctx* ctx, int64_t* fused_rows, int64_t* fallback_rows);
 /* The same evaluation for ANY recommender that can produce host score rows (the reference's
  * recommender.recommend(...) call inside Evaluator.py:271-277): begin, then feed blocks of users IN ORDER
  * with their fp32 score rows [n][n_items] (masked in place with -inf on seen items when remove_seen),
