@@ -112,6 +112,7 @@ struct ganmf_ctx {
   float* cand_val = nullptr; int* cand_idx = nullptr; size_t cand_cap = 0;
   unsigned int* vmax_bits = nullptr;   // max_j ||ranked factor row j|| (float bits)
   int* fb_count = nullptr; int* fb_rows = nullptr; int* fb_users = nullptr; size_t fb_cap = 0;
+  unsigned int* row_thr = nullptr;     // [fb_cap] shared per-row rejection thresholds of the fused scorer
   int* fb_idx = nullptr; float* fb_val = nullptr; size_t fb_topk_cap = 0;
   long long fused_rows = 0, fallback_rows = 0;      // statistics since ganmf_create
   long long launches = 0;
@@ -406,6 +407,7 @@ void ganmf_destroy(ganmf_ctx* c) {
   cudaFree(c->scores); cudaFree(c->topk_idx); cudaFree(c->topk_val); cudaFree(c->uvals);
   cudaFree(c->usums); cudaFree(c->icounts); cudaFree(c->cut_dev); cudaFree(c->eval_users);
   cudaFree(c->Qg.p); cudaFree(c->cand_val); cudaFree(c->cand_idx); cudaFree(c->vmax_bits);
+  cudaFree(c->row_thr);
   cudaFree(c->fb_count); cudaFree(c->fb_rows); cudaFree(c->fb_users); cudaFree(c->fb_idx); cudaFree(c->fb_val);
   for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
   delete c;
@@ -1531,8 +1533,9 @@ static int ensure_fused_buffers(ganmf_ctx* c, int block, int K) {
   }
   if (!c->vmax_bits) { RC(dalloc(&c->vmax_bits, 1)); RC(dalloc(&c->fb_count, 1)); }
   if ((size_t)block > c->fb_cap) {
-    cudaFree(c->fb_rows);
+    cudaFree(c->fb_rows); cudaFree(c->row_thr);
     RC(dalloc(&c->fb_rows, (size_t)block));
+    RC(dalloc(&c->row_thr, (size_t)block));
     c->fb_cap = block;
   }
   if (!c->fb_users) RC(dalloc(&c->fb_users, (size_t)FB_BLOCK));
@@ -1556,8 +1559,8 @@ static int prepare_fused(ganmf_ctx* c) {
   RC(p_flush(c));
   const Param& other = c->cfg.item_mode ? c->params[c->n_d] : c->params[c->n_d + 1];
   CU(cudaMemsetAsync(c->vmax_bits, 0, 4, c->st));
-  row_norm_max_kernel<<<(other.w.rows * 32 + 255) / 256, 256, 0, c->st>>>(other.w.p, other.w.rows, c->k, other.w.ld,
-                                                                         c->vmax_bits);
+  row_norm_max_kernel<<<((other.w.rows + 3) / 4 * 32 + 255) / 256, 256, 0, c->st>>>(other.w.p, other.w.rows, c->k,
+                                                                                    other.w.ld, c->vmax_bits);
   CU(cudaGetLastError());
   c->launches++;
   return 0;
@@ -1592,6 +1595,8 @@ static int fused_topk_block(ganmf_ctx* c, int n, const int* users_dev, int remov
     c->cand_cap = need;
   }
   sc.cand_val = c->cand_val; sc.cand_idx = c->cand_idx;
+  sc.row_thr = c->row_thr;
+  CU(cudaMemsetAsync(c->row_thr, 0, (size_t)n * 4, c->st));
   sc.cache = &c->tmaps; sc.max_ctas = c->gemm_sm_cap;
   cudaError_t e = score_select(sc, c->st);
   if (e != cudaSuccess) return fail("score_select(n=%d items=%d k=%d) -> %s", n, n_items, c->k, cudaGetErrorString(e));
@@ -1600,11 +1605,11 @@ static int fused_topk_block(ganmf_ctx* c, int n, const int* users_dev, int remov
   const float gamma = fused_gamma(c->k);
   if (sc.KP == 16)
     rescore_kernel<16><<<(n + 3) / 4, 128, 0, c->st>>>(c->cand_val, c->cand_idx, NL, n, K, c->Qg.p, c->Qg.ld, other.w.p,
-                                                       other.w.ld, c->k, c->vmax_bits, gamma, c->topk_idx, c->topk_val,
+                                                       other.w.ld, c->k, c->vmax_bits, c->row_thr, gamma, c->topk_idx, c->topk_val,
                                                        c->fb_count, c->fb_rows);
   else
     rescore_kernel<32><<<(n + 3) / 4, 128, 0, c->st>>>(c->cand_val, c->cand_idx, NL, n, K, c->Qg.p, c->Qg.ld, other.w.p,
-                                                       other.w.ld, c->k, c->vmax_bits, gamma, c->topk_idx, c->topk_val,
+                                                       other.w.ld, c->k, c->vmax_bits, c->row_thr, gamma, c->topk_idx, c->topk_val,
                                                        c->fb_count, c->fb_rows);
   CU(cudaGetLastError());
   c->launches += 3;

@@ -47,7 +47,18 @@ struct SelArgs {
   const int* seen_indices;
   float* cand_val;                     // [n_rows][2*segs][KP]
   int* cand_idx;
+  unsigned int* row_thr;               // [n_rows] shared rejection threshold of a row (monotone key, 0 = none)
 };
+
+// monotone float <-> uint key (larger float = larger key; key 0 is below every float incl. -inf)
+__device__ __forceinline__ unsigned int thr_key(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float thr_val(unsigned int k) {
+  if (k == 0u) return -INFINITY;
+  return __uint_as_float((k >> 31) ? (k & 0x7FFFFFFFu) : ~k);
+}
 
 template <int KP>
 struct SelSmem {
@@ -188,6 +199,15 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int si[KP];
 #pragma unroll
       for (int j = 0; j < KP; ++j) { sv[j] = -INFINITY; si[j] = -1; }
+      // Rejection threshold shared by ALL lists of the row (both column halves, every item segment, whichever
+      // SM runs them): each list publishes its KP-th best with an atomic max, every list rejects what does not
+      // beat the published value.  Any value ever published is the KP-th best of SOME subset of the row's
+      // rankable items, so no member of the row's top KP (over all items) is ever rejected, and everything that
+      // is rejected or evicted scores at most the final published value -- the tau of the certificate.  A row's
+      // insertions drop from (lists x KP ln(n/KP)) to about KP ln(I/KP) in total.
+      unsigned int* thr_slot = args.row_thr + (live ? row : 0);
+      float thr_ext = live ? thr_val(__ldcg(thr_slot)) : INFINITY;
+      float thr_pub = thr_ext;
       // seen-item cursor of this (row, half): entries are consumed in increasing column order, the next one is
       // always already in a register
       int sp = 0, se = 0, ns0 = 0x7fffffff, ns1 = 0x7fffffff;
@@ -207,6 +227,8 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       for (int t = t0; t < t1; ++t, ++ti) {
         const uint32_t acc = ti & 1;
+        // what the other lists of this row have published meanwhile (the load is consumed a tile later)
+        const unsigned int thr_seen = live ? __ldcg(thr_slot) : 0u;
         ptx::mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll 1
@@ -230,7 +252,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             ns1 = sp + 1 < se ? __ldg(args.seen_indices + sp + 1) : 0x7fffffff;
           }
           if (!live) skip = 0xFFFFFFFFu;
-          const float thr0 = sv[KP - 1];
+          const float thr0 = fmaxf(sv[KP - 1], thr_ext);
           // quick reject: nothing of this chunk beats the row's KP-th best (the common case once the list has
           // warmed up); masked columns may only cause a false alarm here, they are excluded again below
           float mx = __uint_as_float(r[0]);
@@ -240,9 +262,14 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const float v = __uint_as_float(r[e]);
-            if (v > sv[KP - 1] && !((skip >> e) & 1u)) sel_insert<KP>(sv, si, v, n0 + e);
+            if (v > fmaxf(sv[KP - 1], thr_ext) && !((skip >> e) & 1u)) sel_insert<KP>(sv, si, v, n0 + e);
           }
         }
+        if (live && sv[KP - 1] > thr_pub) {             // publish (fire and forget)
+          atomicMax(thr_slot, thr_key(sv[KP - 1]));
+          thr_pub = sv[KP - 1];
+        }
+        thr_ext = fmaxf(thr_ext, thr_val(thr_seen));
       }
       if (live) {
         const size_t o = ((size_t)row * NL + (seg * 2 + half)) * KP;
@@ -274,6 +301,7 @@ struct ScoreSelectCall {
   int segs;                           // item segments (lists per row = 2 * segs)
   const int* users; const int* seen_indptr; const int* seen_indices;
   float* cand_val; int* cand_idx;
+  unsigned int* row_thr;              // [n_rows], zeroed by the caller
   TmapCache* cache = nullptr;
   int max_ctas = 0;
 };
@@ -318,7 +346,7 @@ inline cudaError_t score_select_launch(const ScoreSelectCall& c, const CUtensorM
   a.row_blocks = (c.n_rows + SS_ROWS - 1) / SS_ROWS;
   a.idesc = make_idesc_tf32(SS_BN, 0, 0, 2 * TC_BM);
   a.users = c.users; a.seen_indptr = c.seen_indptr; a.seen_indices = c.seen_indices;
-  a.cand_val = c.cand_val; a.cand_idx = c.cand_idx;
+  a.cand_val = c.cand_val; a.cand_idx = c.cand_idx; a.row_thr = c.row_thr;
   const int sms = (c.max_ctas > 0 && c.max_ctas < num_sms) ? c.max_ctas : num_sms;
   const int units = a.row_blocks * a.segs;
   const int pairs = units < sms / 2 ? units : sms / 2;
@@ -359,16 +387,53 @@ __device__ __forceinline__ float exact_dot_warp(const float* __restrict__ q, con
   return (float)acc;
 }
 
-// max_j ||V[j, :]||_2 -> *out (float bits, atomicMax on the non-negative pattern); one warp per row
+// Four exact scores at once (k <= 256: the query row sits in registers as 8 doubles per lane): the 32 loads of a
+// group are in flight together and the four reductions interleave, so re-scoring runs at memory latency / 4.
+__device__ __forceinline__ void load_query_regs(const float* __restrict__ q, int k, int lane, double (&qd)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qd[i] = lane + 32 * i < k ? (double)__ldg(q + lane + 32 * i) : 0.0;
+}
+__device__ __forceinline__ void exact_dot4_warp(const double (&qd)[8], const float* __restrict__ V, int ldv,
+                                                const int (&items)[4], int k, int lane, float (&out)[4]) {
+  float x[4][8];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float* v = V + (size_t)items[u] * ldv + lane;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[u][i] = lane + 32 * i < k ? __ldg(v + 32 * i) : 0.f;
+  }
+  double acc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    acc[u] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[u] = fma(qd[i], (double)x[u][i], acc[u]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) out[u] = (float)acc[u];
+}
+
+// max_j ||V[j, :]||_2 -> *out (float bits, atomicMax on the non-negative pattern); one warp per 4 rows, 16-byte loads
 __global__ void row_norm_max_kernel(const float* __restrict__ V, int rows, int k, int ld, unsigned int* out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const float* v = V + (size_t)warp * ld;
-  float s = 0.f;
-  for (int i = lane; i < k; i += 32) { const float x = v[i]; s = fmaf(x, x, s); }
+  const int k4 = k >> 2;
+  for (int r = warp * 4; r < min(warp * 4 + 4, rows); ++r) {
+    const float4* v4 = reinterpret_cast<const float4*>(V + (size_t)r * ld);       // ld is a multiple of 32
+    float s = 0.f;
+    for (int i = lane; i < k4; i += 32) {
+      const float4 x = __ldg(v4 + i);
+      s = fmaf(x.x, x.x, s); s = fmaf(x.y, x.y, s); s = fmaf(x.z, x.z, s); s = fmaf(x.w, x.w, s);
+    }
+    for (int i = (k4 << 2) + lane; i < k; i += 32) { const float x = V[(size_t)r * ld + i]; s = fmaf(x, x, s); }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) atomicMax(out, __float_as_uint(sqrtf(s) * 1.0001f));
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) atomicMax(out, __float_as_uint(sqrtf(s) * 1.0001f));
+  }
 }
 
 // Total order of the evaluator: higher score first, then lower item index (== topk_key's order for finite scores)
@@ -383,7 +448,8 @@ template <int KP>
 __global__ void __launch_bounds__(128)
 rescore_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int NL, int n_rows, int K,
                const float* __restrict__ Q, int ldq, const float* __restrict__ V, int ldv, int k,
-               const unsigned int* __restrict__ vmax_bits, float gamma, int* __restrict__ out_idx,
+               const unsigned int* __restrict__ vmax_bits, const unsigned int* __restrict__ row_thr, float gamma,
+               int* __restrict__ out_idx,
                float* __restrict__ out_val, int* __restrict__ fb_count, int* __restrict__ fb_rows) {
   constexpr int CPL = SS_MAX_LISTS * KP / 32;            // candidates per lane (upper bound)
   constexpr int RMAX = 2;                                // re-scored entries per lane (64 per row)
@@ -395,19 +461,14 @@ rescore_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_
   const int* ci = cand_idx + (size_t)row * C;
   float v[CPL];
   int id[CPL];
-  float tau = -INFINITY;
+  // everything a list of this row rejected or evicted scored (tf32) at most the row's final shared threshold
+  const float tau = thr_val(__ldg(row_thr + row));
 #pragma unroll
   for (int j = 0; j < CPL; ++j) {
     const int p = j * 32 + lane;
     v[j] = -INFINITY; id[j] = -1;
-    if (p < C) {
-      v[j] = cv[p]; id[j] = ci[p];
-      // a list's last entry is its final threshold: everything it rejected scored at most that (tf32)
-      if ((p % KP) == KP - 1 && id[j] >= 0) tau = fmaxf(tau, v[j]);
-    }
+    if (p < C) { v[j] = cv[p]; id[j] = ci[p]; }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
   // a_K: K-th largest tf32 score among the candidates (order (value desc, position asc) makes them distinct)
   float cur_v = INFINITY;
   int cur_p = -1, n_valid = 0;
@@ -439,28 +500,38 @@ rescore_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_
   const float eps = gamma * sqrtf(qq) * 1.0001f * __uint_as_float(__ldg(vmax_bits));
   const float keep_from = aK - 2.f * eps;                // members of the exact top K score at least this in tf32
   // exact re-scoring of the survivors, spread over the lanes (entry e lives in lane e % 32, slot e / 32)
+  __shared__ int s_items[4][32 * RMAX];
+  int* my_items = s_items[threadIdx.x >> 5];
   float rv[RMAX];
   int ri[RMAX];
 #pragma unroll
   for (int s = 0; s < RMAX; ++s) { rv[s] = -INFINITY; ri[s] = -1; }
   int n_res = 0;
-  bool overflow = false;
 #pragma unroll
   for (int j = 0; j < CPL; ++j) {
-    unsigned bal = __ballot_sync(0xffffffffu, id[j] >= 0 && v[j] >= keep_from);
-    while (bal) {
-      const int src = __ffs(bal) - 1;
-      bal &= bal - 1;
-      const int item = __shfl_sync(0xffffffffu, id[j], src);
-      const float ex = exact_dot_warp(q, V + (size_t)item * ldv, k, lane);
-      if (n_res < 32 * RMAX) {
-        if (lane == (n_res & 31)) {
+    const bool keep = id[j] >= 0 && v[j] >= keep_from;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int pos = n_res + __popc(bal & ((1u << lane) - 1u));
+    if (keep && pos < 32 * RMAX) my_items[pos] = id[j];
+    n_res += __popc(bal);
+  }
+  const bool overflow = n_res > 32 * RMAX;
+  n_res = min(n_res, 32 * RMAX);
+  __syncwarp();
+  double qd[8];
+  load_query_regs(q, k, lane, qd);
+  for (int e0 = 0; e0 < n_res; e0 += 4) {
+    int items[4];
+    float ex[4];
 #pragma unroll
-          for (int s = 0; s < RMAX; ++s) if (s == (n_res >> 5)) { rv[s] = ex; ri[s] = item; }
-        }
-        ++n_res;
-      } else {
-        overflow = true;
+    for (int u = 0; u < 4; ++u) items[u] = my_items[min(e0 + u, n_res - 1)];
+    exact_dot4_warp(qd, V, ldv, items, k, lane, ex);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u;
+      if (e < n_res && lane == (e & 31)) {
+#pragma unroll
+        for (int s = 0; s < RMAX; ++s) if (s == (e >> 5)) { rv[s] = ex[u]; ri[s] = items[u]; }
       }
     }
   }
@@ -548,21 +619,42 @@ user_rmse_exact_kernel(const float* __restrict__ Q, int ldq, const float* __rest
   const float* q = Q + (size_t)r * ldq;
   float* e = scratch + ts;
   int n = 0;
-  for (int i = 0; i < T; ++i) {
-    const int item = tb.test_indices[ts + i];
-    bool seen = false;
-    if (seen_indptr) {
+  double qd[8];
+  load_query_regs(q, k, lane, qd);                        // (the fused route guarantees k <= 256)
+  for (int i0 = 0; i0 < T; i0 += 32) {
+    // lane l looks at test entry i0 + l: is the item seen (masked to -inf, dropped)?
+    const int i = i0 + lane;
+    bool use = i < T;
+    const int item = use ? tb.test_indices[ts + i] : 0;
+    if (use && seen_indptr) {
       int lo = seen_indptr[u], hi = seen_indptr[u + 1] - 1;
       while (lo <= hi) {
         const int mid = (lo + hi) >> 1, v = seen_indices[mid];
-        if (v == item) { seen = true; break; }
+        if (v == item) { use = false; break; }
         if (v < item) lo = mid + 1; else hi = mid - 1;
       }
     }
-    if (seen) continue;                                   // -inf score: not finite, dropped
-    const float d = exact_dot_warp(q, V + (size_t)item * ldv, k, lane) - test_data[ts + i];
-    const float sq = d * d;
-    if (isfinite(sq)) { if (lane == 0) e[n] = sq; ++n; }
+    unsigned bal = __ballot_sync(0xffffffffu, use);
+    while (bal) {                                         // four unseen test items per pass, in entry order
+      int src[4], items[4];
+      float ex[4];
+      int cnt = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (bal) { src[j] = __ffs(bal) - 1; bal &= bal - 1; ++cnt; }
+        else src[j] = src[0];                             // (padding: re-scores the first item, result unused)
+        items[j] = __shfl_sync(0xffffffffu, item, src[j]);
+      }
+      exact_dot4_warp(qd, V, ldv, items, k, lane, ex);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < cnt) {
+          const float d = ex[j] - test_data[ts + i0 + src[j]];
+          const float sq = d * d;
+          if (isfinite(sq)) { if (lane == 0) e[n] = sq; ++n; }
+        }
+      }
+    }
   }
   __syncwarp();
   if (lane == 0) {
