@@ -85,6 +85,8 @@ struct ganmf_ctx {
   Mat dhtmp;
   float *out2 = nullptr, *dout2 = nullptr, *idf = nullptr;
   float* ws = nullptr; size_t ws_floats = 0;
+  bool presplit = false;               // the GEMM being issued already has split-TF32 operands (scoring)
+  float* s3[2] = {nullptr, nullptr}; size_t s3_cap[2] = {0, 0};     // split-TF32 operand copies (GANMF_GEMM_TC3)
   StepScalars* sc = nullptr;
   float* losses = nullptr; int losses_cap = 0;
   int* ids = nullptr; int ids_cap = 0;
@@ -164,9 +166,38 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   int path = force_path != GANMF_GEMM_AUTO ? force_path : c->cfg.gemm_path;
   const bool aligned = !(lda & 3) && !(ldb & 3) && !((uintptr_t)A & 15) && !((uintptr_t)B & 15);
-  if (path == GANMF_GEMM_AUTO)
-    path = (aligned && (double)M * N * K >= (double)(1 << 18)) ? GANMF_GEMM_TC : GANMF_GEMM_SIMT;
+  if (path == GANMF_GEMM_AUTO) {
+    // DisGANMF trains on split-TF32 operands by default: the BCE gradients of the real and the fake half cancel in
+    // the weight-gradient sums, so plain TF32 rounding shows at ~1e-2 on wide nets (tests/test_gpu_baseline_shapes.py)
+    const int tc = c->cfg.kind == GANMF_KIND_DISGANMF ? GANMF_GEMM_TC3 : GANMF_GEMM_TC;
+    path = (aligned && (double)M * N * K >= (double)(1 << 18)) ? tc : GANMF_GEMM_SIMT;
+  }
+  if (path == GANMF_GEMM_TC3 && c->presplit) path = GANMF_GEMM_TC;
+  if (path == GANMF_GEMM_TC3 && (double)M * N * K < (double)(1 << 18)) path = GANMF_GEMM_SIMT;   // tiny: exact fp32 FMA
   if (path == GANMF_GEMM_TC && !aligned) return fail("tcgen05 GEMM needs 16-byte aligned operands");
+  if (path == GANMF_GEMM_TC3) {
+    // fp32-accurate tensor-core GEMM: x = hi + lo (tf32 each); A -> [hi|hi|lo], B -> [hi|lo|hi], one pass over 3K
+    // computes hi.hi + hi.lo + lo.hi (the dropped lo.lo term is ~2^-22 relative).  3x the MMA work plus one
+    // read/write of each operand; used where TF32 rounding is visible through cancellation (DisGANMF).
+    const int ld3 = rup(3 * K, 32);
+    const float* src[2] = {A, B};
+    const int lds[2] = {lda, ldb}, mns[2] = {a_mn, b_mn}, ext[2] = {M, N};
+    for (int o = 0; o < 2; ++o) {
+      const size_t need = (size_t)ext[o] * ld3;
+      if (need > c->s3_cap[o]) {
+        CU(cudaStreamSynchronize(c->st));
+        cudaFree(c->s3[o]);
+        RC(dalloc(&c->s3[o], need));
+        c->s3_cap[o] = need;
+        c->tmaps = TmapCache();               // (descriptors of the freed buffer must not be reused)
+      }
+      split3_any_kernel<<<dim3((ext[o] + 31) / 32, (K + 31) / 32), 256, 0, c->st>>>(src[o], lds[o], mns[o], ext[o], K,
+                                                                                 c->s3[o], ld3, o);
+      CU(cudaGetLastError());
+    }
+    c->launches += 2;
+    return gemm(c, c->s3[0], ld3, 0, c->s3[1], ld3, 0, M, N, 3 * K, ep, GANMF_GEMM_TC);
+  }
   if (path == GANMF_GEMM_SIMT) {
     c->launches += 1;
     CU(simt_gemm(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, c->st));
@@ -400,6 +431,7 @@ void ganmf_destroy(ganmf_ctx* c) {
   for (auto& m : c->hs) cudaFree(m.p);
   for (auto& m : c->dzs) cudaFree(m.p);
   cudaFree(c->out2); cudaFree(c->dout2); cudaFree(c->idf);
+  cudaFree(c->s3[0]); cudaFree(c->s3[1]);
   cudaFree(c->ws); cudaFree(c->sc); cudaFree(c->losses); cudaFree(c->ids); cudaFree(c->slot);
   for (int i = 0; i < 3; ++i) csr_free(c->csr[i]);
   cudaFree(c->tb_gain); cudaFree(c->tb_gain_desc); cudaFree(c->tb_logtab); cudaFree(c->tb_nov);
@@ -1440,7 +1472,10 @@ static int score_block(ganmf_ctx* c, int n, const int* users_dev = nullptr) {
   c->launches++;
   Epilogue e;
   e.out = c->scores; e.ldo = rup(n_items, 32);
-  return gemm(c, c->Fb.p, c->Fb.ld, 0, c->Ob.p, c->Ob.ld, 0, n, n_items, 3 * c->k, e);
+  c->presplit = true;                       // operands are already split: never split them again
+  const int rc = gemm(c, c->Fb.p, c->Fb.ld, 0, c->Ob.p, c->Ob.ld, 0, n, n_items, 3 * c->k, e);
+  c->presplit = false;
+  return rc;
 }
 
 static int n_items_of(ganmf_ctx* c) { return c->cfg.item_mode ? c->cfg.n_rows : c->W; }

@@ -91,6 +91,42 @@ __global__ void split3_rows_kernel(const float* __restrict__ src, int ld_src, co
   }
 }
 
+// The same split for ANY operand of a GEMM (split-TF32 "precise" mode of the training GEMMs): src is the logical
+// [MN][K] operand, stored K-major ([MN][K], ld >= K) or MN-major ([K][MN], ld >= MN); dst is K-major
+// [MN][3K] = [hi | hi | lo] (b_layout = 0) or [hi | lo | hi] (b_layout = 1).  32 x 32 tiles through shared
+// memory so both the read and the write are coalesced whatever the source major-ness.
+__global__ void __launch_bounds__(256)
+split3_any_kernel(const float* __restrict__ src, int ld_src, int mn_major, int MN, int K, float* __restrict__ dst,
+                  int ld_dst, int b_layout) {
+  __shared__ float tile[32][33];
+  const int mn0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    float x = 0.f;
+    if (mn_major) {                                                   // rows of src = k, contiguous = mn
+      const int kk = k0 + r, mn = mn0 + tx;
+      if (kk < K && mn < MN) x = src[(size_t)kk * ld_src + mn];
+      tile[tx][r] = x;                                                // tile[mn][k]
+    } else {                                                          // rows of src = mn, contiguous = k
+      const int mn = mn0 + r, kk = k0 + tx;
+      if (kk < K && mn < MN) x = src[(size_t)mn * ld_src + kk];
+      tile[r][tx] = x;
+    }
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int mn = mn0 + r, kk = k0 + tx;
+    if (mn >= MN || kk >= K) continue;
+    const float x = tile[r][tx];
+    const float hi = ptx::round_tf32(x);
+    const float lo = ptx::round_tf32(x - hi);
+    float* d = dst + (size_t)mn * ld_dst;
+    d[kk] = hi;
+    d[K + kk] = b_layout ? lo : hi;
+    d[2 * K + kk] = b_layout ? hi : lo;
+  }
+}
+
 // first column of the DisGANMF discriminator input: float(row id)  (DisGANMF.py:110-111)
 // (ids are LOCAL rows of this GPU's shard; id_offset = global id of local row 0)
 __global__ void ids_to_float_kernel(const int* __restrict__ ids, float* __restrict__ out, int B, int id_offset) {

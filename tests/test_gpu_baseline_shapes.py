@@ -1,0 +1,140 @@
+"""Step parity at the shapes BASELINE.json names: the committed splits with the best_params of
+test_results/*, and five steps at the cfg4 synthetic shape.  Same contract as tests/test_gpu_train_parity.py: identical
+initial weights and minibatch id stream, per-step losses and updated parameters within rel 1e-3 of the fp32 oracle.
+
+DisGANMF runs its tensor-core GEMMs on split-TF32 operands (GANMF_GEMM_TC3, three MMAs per product): the BCE gradients
+of the real and the fake half cancel in the weight-gradient sums, which makes plain TF32 rounding visible at ~1e-2 on
+wide nets; the test of the wide configuration records that too."""
+import numpy as np
+import pytest
+
+from oracle import train_oracle as to
+from tests.helpers import load_quality_targets, load_split
+from tests.test_gpu_train_parity import REL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def pick_batches(n_rows, B, n_first):
+    _, batches = next(iter(to.epoch_index_stream(n_rows, B, 1, seed=1337)))
+    out = batches[:n_first]
+    if len(batches) > n_first:
+        out = out + [batches[-1]]                  # the (usually short) last batch of the epoch
+    return out
+
+
+def run_engine(eng, batches, d_args, g_args):
+    perm = np.concatenate(batches).astype(np.int32)
+    eng.upload_ids(perm)
+    off, slot = 0, 0
+    for b in batches:
+        eng.d_step(off, len(b), *d_args, loss_slot=slot)
+        off += len(b)
+        slot += 1
+    off = 0
+    for b in batches:
+        eng.g_step(off, len(b), *g_args, loss_slot=slot)
+        off += len(b)
+        slot += 1
+    return eng.read_losses(slot)
+
+
+def check(losses, want, got, ref, rel=REL):
+    np.testing.assert_allclose(losses, want, rtol=rel)
+    worst = max((rel_err(got[n], ref[n]), n) for n in ref)
+    assert worst[0] <= rel, worst
+
+
+def test_cfg2_ganmf_item_lastfm_steps_parity():
+    """GANMF --item on the committed LastFM split: rows are the 17 632 items, profiles are 1 884 users wide."""
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    bp = load_quality_targets()["GANMF_item_LastFM"]["best_params"]
+    urm = load_split("LastFM")["train"].T.tocsr()                    # GANMF.py:32-33
+    n_rows, width = urm.shape
+    k, E, B = int(bp["num_factors"]), int(bp["emb_dim"]), int(bp["batch_size"])
+    assert (n_rows, width, k, E, B) == (17632, 1884, 146, 680, 512)
+    p0 = to.init_ganmf_params(n_rows, width, k, E, seed=7)
+    eng = Engine(L.KIND_GANMF, n_rows, width, k, emb_dim=E, max_batch=B, item_mode=True)
+    eng.set_csr(L.CSR_TRAIN, urm)
+    eng.set_params(p0)
+    eng.reset_optimizers()
+    batches = pick_batches(n_rows, B, 6)
+    losses = run_engine(eng, batches, (bp["d_lr"], bp["d_reg"], bp["m"]), (bp["g_lr"], 0.0, bp["recon_coefficient"]))
+    orc = to.GanmfOracle(p0, bp["d_lr"], bp["g_lr"], dtype=np.float32)
+    want = [orc.d_step(b, to.csr_rows_to_dense(urm, b), d_reg=bp["d_reg"], m=bp["m"]) for b in batches]
+    want += [orc.g_step(b, to.csr_rows_to_dense(urm, b), g_reg=0.0, recon_coefficient=bp["recon_coefficient"])
+             for b in batches]
+    check(losses, want, eng.get_params(), orc.p)
+    eng.close()
+
+
+def disganmf_case(name, ds, item_mode, n_first, gemm_path):
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    bp = load_quality_targets()[name]["best_params"]
+    urm = load_split(ds)["train"]
+    urm = urm.T.tocsr() if item_mode else urm.tocsr()
+    n_rows, width = urm.shape
+    k, B, layers, nodes = int(bp["num_factors"]), int(bp["batch_size"]), int(bp["d_layers"]), int(bp["d_nodes"])
+    act = bp["d_hidden_act"]
+    p0 = to.init_disganmf_params(n_rows, width, k, layers, nodes, seed=3)
+    eng = Engine(L.KIND_DISGANMF, n_rows, width, k, d_layers=layers, d_nodes=nodes, d_act=act, max_batch=B,
+                 item_mode=item_mode, gemm_path=getattr(L, gemm_path))
+    eng.set_csr(L.CSR_TRAIN, urm)
+    eng.set_params(p0)
+    eng.reset_optimizers()
+    batches = pick_batches(n_rows, B, n_first)
+    losses = run_engine(eng, batches, (bp["d_lr"], bp["d_reg"], 1.0), (bp["g_lr"], 0.0, bp["recon_coefficient"]))
+    orc = to.DisGanmfOracle(p0, layers, act, bp["d_lr"], bp["g_lr"], dtype=np.float32)
+    want = [orc.d_step(b, to.csr_rows_to_dense(urm, b), d_reg=bp["d_reg"]) for b in batches]
+    want += [orc.g_step(b, to.csr_rows_to_dense(urm, b), g_reg=0.0, recon_coefficient=bp["recon_coefficient"])
+             for b in batches]
+    got = eng.get_params()
+    eng.close()
+    return (n_rows, width, k, B, layers, nodes), losses, np.array(want), got, orc.p
+
+
+def test_cfg3_disganmf_user_hetrec2011_steps_parity():
+    """DisGANMF --user, hetrec2011 split: 2113 rows, profiles 10 109 wide (+ the id column), one 4-unit layer."""
+    shape, losses, want, got, ref = disganmf_case("DisGANMF_user_hetrec2011", "Movielenshetrec2011", False, 12, "GEMM_AUTO")
+    assert shape == (2113, 10109, 243, 64, 1, 4)
+    check(losses, want, got, ref)
+
+
+def test_cfg3_disganmf_item_hetrec2011_steps_parity():
+    """DisGANMF --item, hetrec2011 split: 10 109 rows, 4 hidden layers of 1024 units, B = 256 -- the wide case.
+    Default path of DisGANMF (split-TF32 GEMMs) meets the contract; plain TF32 is measured next to it."""
+    shape, losses, want, got, ref = disganmf_case("DisGANMF_item_hetrec2011", "Movielenshetrec2011", True, 8, "GEMM_AUTO")
+    assert shape == (10109, 2113, 25, 256, 4, 1024)
+    check(losses, want, got, ref)
+    _, l32, _, g32, _ = disganmf_case("DisGANMF_item_hetrec2011", "Movielenshetrec2011", True, 8, "GEMM_TC")
+    drift = max(rel_err(g32[n], ref[n]) for n in ref)
+    print("plain TF32 on the 4x1024 net: worst tensor rel err %.2e, worst loss rel err %.2e" %
+          (drift, float(np.max(np.abs(l32 - want) / np.abs(want)))))
+    assert drift < 0.1                                 # sanity only: TF32 is not the shipping path here
+
+
+def test_cfg4_synthetic_shape_five_steps_parity():
+    """BASELINE.json configs[3]: I = 27 000, k = 250, E = 1024, B = 1024 (split-K over K = 27 000, CTA pairs, fused-Adam
+    epilogues) -- five D and five G steps against the oracle (~1 s per step on the host)."""
+    import bench
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    c = bench.workload("cfg4")
+    n_rows, I, k, E, B = 8192, c["items"], c["k"], c["E"], c["B"]            # user table cut: the shapes of a step do not depend on it
+    urm = bench.synthetic_urm(n_rows, I, c["density"], 11)
+    p0 = to.init_ganmf_params(n_rows, I, k, E, seed=5)
+    hp = bench.HP
+    eng = Engine(L.KIND_GANMF, n_rows, I, k, emb_dim=E, max_batch=B)
+    eng.set_csr(L.CSR_TRAIN, urm)
+    eng.set_params(p0)
+    eng.reset_optimizers()
+    batches = pick_batches(n_rows, B, 5)[:5]
+    losses = run_engine(eng, batches, (hp["d_lr"], hp["d_reg"], hp["m"]), (hp["g_lr"], hp["g_reg"], hp["alpha"]))
+    orc = to.GanmfOracle(p0, hp["d_lr"], hp["g_lr"], dtype=np.float32)
+    want = [orc.d_step(b, to.csr_rows_to_dense(urm, b), d_reg=hp["d_reg"], m=hp["m"]) for b in batches]
+    want += [orc.g_step(b, to.csr_rows_to_dense(urm, b), g_reg=hp["g_reg"], recon_coefficient=hp["alpha"])
+             for b in batches]
+    check(losses, want, eng.get_params(), orc.p)
+    eng.close()
