@@ -63,10 +63,14 @@ class BaseRecommender(object):
             extra_mask.append(np.asarray(self.filterTopPop_ItemsID, dtype=np.int64))
         if remove_CustomItems_flag:                            # :210-211
             extra_mask.append(np.asarray(self.items_to_ignore_ID, dtype=np.int64))
-        if cutoff > L.TOPK_MAX or extra_mask:
-            # rare API-edge cases (full rankings, custom item filters): scores come back masked from the
-            # device and the same mask -> top-k kernel runs on the edited matrix in chunks of 128 ranks
-            scores = eng.score(user_id_array)
+        host_edit = getattr(self, "_scores_need_host_edit", None)
+        own_scores = items_to_compute is not None or (host_edit is not None and host_edit(user_id_array))
+        if cutoff > L.TOPK_MAX or extra_mask or own_scores:
+            # rare API-edge cases (full rankings, custom item filters, restricted item sets, biases / cold users of a
+            # matrix-factorisation baseline): the score rows are edited on the host as the reference does and the
+            # device mask -> top-k kernel runs on the edited matrix in chunks of 128 ranks
+            scores = (np.ascontiguousarray(self._compute_item_score(user_id_array, items_to_compute=items_to_compute),
+                                           dtype=np.float32) if own_scores else eng.score(user_id_array))
             if extra_mask:
                 scores[:, np.concatenate(extra_mask)] = -np.inf
             idx = self._topk_large(eng, scores, user_id_array, int(cutoff), remove_seen_flag)

@@ -83,7 +83,8 @@ class EvaluatorHoldout(Evaluator):
     # ------------------------------------------------------------------------------------------
     def _device_sums(self, recommender_object, users):
         """(sums[n_cut, MC_NCOL], counts[n_cut, n_items]) over `users` in ascending order."""
-        eng = getattr(recommender_object, "_engine", None)
+        eng = (recommender_object._device_engine() if hasattr(recommender_object, "_device_engine")
+               else getattr(recommender_object, "_engine", None))
         # popularity tables need the users x items matrix: an engine-backed item-mode model may hold URM_train
         # transposed (after loadModel the reference leaves it so, GANMF.py:32-33,337-342)
         URM_train = getattr(recommender_object, "_URM_users_items", None) if eng is not None else None
@@ -102,6 +103,13 @@ class EvaluatorHoldout(Evaluator):
                 sc = np.array(base_fn(u), dtype=np.float32, copy=True)
                 sc[:, ignore] = -np.inf
                 return sc
+        host_edit = getattr(recommender_object, "_scores_need_host_edit", None)
+        if eng is not None and host_edit is not None and host_edit(users):
+            # a factor model whose score rows are edited on the host (biases, cold users): stream them through the
+            # device mask -> top-k -> metric stage like any foreign recommender's
+            eng.set_test(self.URM_test, URM_train)
+            return eng.evaluate_scores(score_fn, users, self.cutoff_list, remove_seen=self.exclude_seen,
+                                       block_size=block)
         if eng is None:
             # any recommender exposing _compute_item_score (e.g. the reference's own baselines): its host score
             # rows are pushed, block by block as Evaluator.py:238 sizes them, through the device
@@ -118,6 +126,19 @@ class EvaluatorHoldout(Evaluator):
         if self.ignore_items_flag:
             return eng.evaluate_scores(score_fn, users, self.cutoff_list, remove_seen=self.exclude_seen,
                                        block_size=block)
+        try:
+            import torch.distributed as dist
+            sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        except ImportError:
+            sharded = False
+        if sharded:
+            # under torchrun every rank holds the model (replicated factors): each evaluates a contiguous range of
+            # the ascending user list, only metric sums and item histograms cross GPUs, and
+            # the running sums are continued rank after rank -- same bits as the single-GPU evaluation
+            from ...parallel import shard_rows, sharded_eval_sums
+            lo, hi = shard_rows(len(users), dist.get_world_size(), dist.get_rank())
+            sums, counts, _ = sharded_eval_sums(eng, users[lo:hi], self.cutoff_list, self.exclude_seen, dist=dist)
+            return sums, counts
         return eng.evaluate(users, self.cutoff_list, remove_seen=self.exclude_seen)
 
     def evaluateRecommender(self, recommender_object):

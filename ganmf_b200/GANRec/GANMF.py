@@ -42,4 +42,6 @@ class GANMF(GanRecommenderBase):
                               earlystopping_kwargs)
 
     def autoencoder_codes(self):                                       # GANMF.py:304-307: R . We + be for all rows
+        if self._trainer is not None:
+            return self._trainer.encode(np.arange(self.num_users))
         return self._engine.encode(np.arange(self.num_users))

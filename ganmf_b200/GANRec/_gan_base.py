@@ -13,6 +13,17 @@ from ..Utils_ import EarlyStoppingScheduler
 from ..engine import Engine
 
 
+def _dist_state():
+    """(torch.distributed, world size, rank) when a process group is up (torchrun), else (None, 1, 0)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_world_size(), dist.get_rank()
+    except ImportError:
+        pass
+    return None, 1, 0
+
+
 class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
     RECOMMENDER_NAME = "GAN_Base"
     KIND = None
@@ -36,6 +47,9 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
         self.items_to_ignore_ID = np.array([], dtype=int)
         self.filterTopPop_ItemsID = np.array([], dtype=int)
         self._engine = None
+        self._trainer = None            # ItemShardedTrainer when fit() runs under torchrun (GANMF, world size > 1)
+        self._scorer = None             # factor-only context holding the gathered factors of an item-sharded model
+        self._scorer_dirty = True
         self._stop_training = False
         self.train_d_loss, self.train_g_loss = [], []
         self.params = self.best_params = None
@@ -44,16 +58,43 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
     def _engine_kwargs(self):
         raise NotImplementedError()
 
-    def _build_engine(self, batch_size, device=0, gemm_path=L.GEMM_AUTO):
+    def _build_engine(self, batch_size, device=None, gemm_path=L.GEMM_AUTO):
+        """One process (the reference's situation, GANMF.py:142-150): one context on one GPU.  Under torchrun
+        (torch.distributed initialised, world size N > 1) a GANMF model is ITEM-SHARDED over the N GPUs
+        (parallel.ItemShardedTrainer): every rank holds 1/N of the columns of the training matrix and of
+        We / Wd / bd / V, steps on the same minibatch stream as a single GPU would, and all-reduces activations.
+        DisGANMF has no sharded step: every rank then trains an identical replica."""
         if self._engine is not None:
             self._engine.close()
+        if self._scorer is not None:
+            self._scorer.close()
+        self._trainer, self._scorer, self._scorer_dirty = None, None, True
+        dist, world, rank = _dist_state()
+        if device is None:
+            device = 0
+            if dist is not None:
+                import torch
+                device = torch.cuda.current_device()
         train_rows = self._URM_users_items.T.tocsr() if self.mode == 'item' else self._URM_users_items
-        eng = Engine(self.KIND, train_rows.shape[0], train_rows.shape[1], max_batch=int(batch_size),
-                     item_mode=(self.mode == 'item'), device=device, gemm_path=gemm_path, **self._engine_kwargs())
-        eng.set_csr(L.CSR_TRAIN, train_rows)
-        eng.set_csr(L.CSR_SEEN, self._URM_users_items, with_data=False)
-        eng.init_params(self.seed)
-        self._engine = eng
+        n_rows, width = train_rows.shape
+        if world > 1 and self.KIND == L.KIND_GANMF:
+            from ..parallel import ItemShardedTrainer, item_slices
+            lo, hi = item_slices(width, world)[rank]
+            eng = Engine(self.KIND, n_rows, hi - lo, max_batch=int(batch_size), item_mode=(self.mode == 'item'),
+                         device=device, gemm_path=gemm_path, global_width=width, item_offset=lo, tp_rank=rank,
+                         tp_world=world, **self._engine_kwargs())
+            eng.set_csr(L.CSR_TRAIN, train_rows[:, lo:hi].tocsr())
+            eng.init_params(self.seed)           # every rank draws ITS slice of the same whole tensors
+            self._engine = eng
+            self._trainer = ItemShardedTrainer(eng)
+            self._tp_slice = (lo, hi, width)
+        else:
+            eng = Engine(self.KIND, n_rows, width, max_batch=int(batch_size), item_mode=(self.mode == 'item'),
+                         device=device, gemm_path=gemm_path, **self._engine_kwargs())
+            eng.set_csr(L.CSR_TRAIN, train_rows)
+            eng.set_csr(L.CSR_SEEN, self._URM_users_items, with_data=False)
+            eng.init_params(self.seed)
+            self._engine = eng
         names = [(n, g) for n, _, _, g in eng.param_infos()]
         # same grouping as the reference's self.params / self.best_params (GANMF.py:119-128)
         self.params = {'D': [n for n, g in names if not g], 'G': [n for n, g in names if g]}
@@ -119,8 +160,23 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
     def _run_epoch(self, num_epoch):
         np.random.shuffle(self._all_users)                             # GANMF.py:175 (global numpy RNG, cumulative)
         h = self._hp
-        dl, gl = self._engine.train_epoch(self._all_users, h['batch_size'], h['d_steps'], h['g_steps'], h['d_lr'],
-                                          h['g_lr'], h['d_reg'], h['g_reg'], h['m_hinge'], h['recon_coefficient'])
+        if self._trainer is not None:
+            # every rank must step on the SAME minibatches: rank 0's shuffle is the one that counts
+            import torch
+            dist = self._trainer.dist
+            t = torch.from_numpy(np.ascontiguousarray(self._all_users, dtype=np.int64))
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            t = t.to(dev)
+            dist.broadcast(t, src=0)
+            self._all_users[:] = t.cpu().numpy()
+            dl, gl = self._trainer.train_epoch(self._all_users.astype(np.int32), h['batch_size'], h['d_steps'],
+                                               h['g_steps'], dict(d_lr=h['d_lr'], g_lr=h['g_lr'], d_reg=h['d_reg'],
+                                                                  g_reg=h['g_reg'], m=h['m_hinge'],
+                                                                  alpha=h['recon_coefficient']))
+            self._scorer_dirty = True
+        else:
+            dl, gl = self._engine.train_epoch(self._all_users, h['batch_size'], h['d_steps'], h['g_steps'], h['d_lr'],
+                                              h['g_lr'], h['d_reg'], h['g_reg'], h['m_hinge'], h['recon_coefficient'])
         self.last_d_losses, self.last_g_losses = dl, gl
         self.train_d_loss.append(float(np.mean(dl)) if dl.size else float('nan'))    # GANMF.py:205-209
         self.train_g_loss.append(float(np.mean(gl)) if gl.size else float('nan'))
@@ -142,18 +198,88 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
 
     def load_model(self):                                              # GANMF.py:253-255 (restore best snapshot)
         self._engine.restore()
+        self._scorer_dirty = True
 
     def get_URM_train(self):
         return self.URM_train.copy()
 
+    # ------------------------------------------------------------------ scoring side
+    def _device_engine(self):
+        """The context that scores and ranks.  One GPU: the training context itself.  Item-sharded model: a
+        factor-only context (GANMF_KIND_MF) on every rank holding ALL item factors (the slices are gathered over
+        NVLink, device to device) and the replicated user factors; refreshed lazily after training steps."""
+        if self._trainer is None:
+            return self._engine
+        import torch
+        dist = self._trainer.dist
+        eng = self._engine
+        if self._scorer is None:
+            lo, hi, width = self._tp_slice
+            self._scorer = Engine(L.KIND_MF, eng.n_rows, width, eng.cfg.num_factors, max_batch=1,
+                                  item_mode=(self.mode == 'item'), device=eng.cfg.device)
+            self._scorer.set_csr(L.CSR_SEEN, self._URM_users_items, with_data=False)
+            self._scorer_dirty = True
+        if self._scorer_dirty:
+            from ..parallel import item_slices
+            lo, hi, width = self._tp_slice
+            dev = torch.device("cuda", eng.cfg.device)
+            ld = eng.device_buffer_ld("user_factors")
+            wrap = lambda e, n: torch.as_tensor(e.device_buffer(n), device=dev)
+            wrap(self._scorer, "user_factors").copy_(wrap(eng, "user_factors"))       # replicated (deferred steps applied)
+            v_all, v_own = wrap(self._scorer, "item_factors"), wrap(eng, "item_factors")
+            for r, (a, b) in enumerate(item_slices(width, dist.get_world_size())):
+                if r == dist.get_rank():
+                    v_all[a * ld:b * ld].copy_(v_own)
+                dist.broadcast(v_all[a * ld:b * ld], src=r)
+            torch.cuda.synchronize()
+            self._scorer_dirty = False
+        return self._scorer
+
+    def _full_params(self):
+        """All tensors under their TF names; an item-sharded model gathers its slices (host side, API-sized models)."""
+        own = self._engine.get_params()
+        if self._trainer is None:
+            return own
+        dist = self._trainer.dist
+        parts = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, own)
+        out = {}
+        for n in own:
+            if n in ("autoencoder/encoding/kernel", "generator/item_embeddings"):
+                out[n] = np.concatenate([q[n] for q in parts], axis=0)
+            elif n == "autoencoder/decoding/kernel":
+                out[n] = np.concatenate([q[n] for q in parts], axis=1)
+            elif n == "autoencoder/decoding/bias":
+                out[n] = np.concatenate([q[n] for q in parts], axis=0)
+            else:
+                out[n] = own[n]
+        return out
+
+    def _install_params(self, params):
+        if self._trainer is None:
+            self._engine.set_params(params)
+            return
+        lo, hi, _ = self._tp_slice
+        sl = {}
+        for n, v in params.items():
+            v = np.asarray(v)
+            if n in ("autoencoder/encoding/kernel", "generator/item_embeddings", "autoencoder/decoding/bias"):
+                sl[n] = v[lo:hi]
+            elif n == "autoencoder/decoding/kernel":
+                sl[n] = v[:, lo:hi]
+            else:
+                sl[n] = v
+        self._engine.set_params(sl)
+        self._scorer_dirty = True
+
     def _compute_item_score(self, user_id_array, items_to_compute=None):   # GANMF.py:285-292
-        return self._engine.score(np.asarray(user_id_array).reshape(-1))
+        return self._device_engine().score(np.asarray(user_id_array).reshape(-1))
 
     def user_factors(self):                                            # GANMF.py:294-297
-        return self._engine.get_param("generator/user_embeddings")
+        return self._device_engine().get_param("generator/user_embeddings")
 
     def item_factors(self):                                            # GANMF.py:299-302
-        return self._engine.get_param("generator/item_embeddings")
+        return self._device_engine().get_param("generator/item_embeddings")
 
     # ------------------------------------------------------------------ disk
     def _build_params(self):
@@ -166,7 +292,9 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
         with open(os.path.join(folder_path, 'build_params.pkl'), 'wb') as f:
             pickle.dump(self._build_params(), f, pickle.HIGHEST_PROTOCOL)
         name = self.RECOMMENDER_NAME + '_' + self.mode if file_name is None else file_name
-        np.savez(os.path.join(folder_path, name + '.npz'), **self._engine.get_params())
+        params = self._full_params()
+        if _dist_state()[2] == 0:                                      # one writer under torchrun
+            np.savez(os.path.join(folder_path, name + '.npz'), **params)
 
     def loadModel(self, folder_path, file_name=None):
         with open(os.path.join(folder_path, 'build_params.pkl'), 'rb') as f:
@@ -178,11 +306,17 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
         tf_data = os.path.join(folder_path, name + '.data-00000-of-00001')
         if os.path.exists(npz):
             z = np.load(npz)
-            eng.set_params({k: z[k] for k in z.files})
+            self._install_params({k: z[k] for k in z.files})
         elif os.path.exists(tf_data):                                  # a model saved by the reference itself
             from ..tf_bundle import read_tf_bundle
             shapes = {n: ((c,) if n.endswith('bias') else (r, c)) for n, r, c, _ in eng.param_infos()}
-            eng.set_params(read_tf_bundle(tf_data, shapes))
+            if self._trainer is not None:
+                lo, hi, width = self._tp_slice
+                full = {"autoencoder/encoding/kernel": 0, "generator/item_embeddings": 0, "autoencoder/decoding/bias": 0,
+                        "autoencoder/decoding/kernel": 1}
+                shapes = {n: tuple(width if (n in full and ax == full[n]) else d for ax, d in enumerate(sh))
+                          for n, sh in shapes.items()}
+            self._install_params(read_tf_bundle(tf_data, shapes))
         else:
             raise IOError("no saved model %s(.npz|.data-00000-of-00001) in %s" % (name, folder_path))
         if self.mode == 'item':
@@ -197,8 +331,8 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
 
     def set_weights(self, params):
         """Install exported initial weights (parity harness)."""
-        self._engine.set_params(params)
+        self._install_params(params)
         self._engine.reset_optimizers()
 
     def get_weights(self):
-        return self._engine.get_params()
+        return self._full_params()

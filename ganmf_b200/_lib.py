@@ -78,6 +78,8 @@ SIGNATURES = {
     "ganmf_recommend": (C.c_int, [_ctx, _i32p, C.c_int, C.c_int, C.c_int, _i32p, _f32p, _f32p]),
     "ganmf_set_eval_tables": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, _f64p, _u8p, _f64p, C.c_int]),
     "ganmf_evaluate": (C.c_int, [_ctx, _i32p, C.c_int, _i32p, C.c_int, C.c_int, C.c_int, _f64p, _i64p]),
+    "ganmf_evaluate_values": (C.c_int, [_ctx, _i32p, C.c_int, _i32p, C.c_int, C.c_int, C.c_int]),
+    "ganmf_evaluate_sums": (C.c_int, [_ctx, _f64p, _f64p, _i64p]),
     "ganmf_eval_stats": (C.c_int, [_ctx, _i64p, _i64p]),
     "ganmf_eval_begin": (C.c_int, [_ctx, C.c_int, _i32p, C.c_int]),
     "ganmf_eval_scores_block": (C.c_int, [_ctx, _f32p, _i32p, C.c_int, C.c_int, C.c_int]),

@@ -119,6 +119,7 @@ struct ganmf_ctx {
   long long fused_rows = 0, fallback_rows = 0;      // statistics since ganmf_create
   long long launches = 0;
   int ev_total = 0, ev_done = 0, ev_ncut = 0, ev_K = 0;     // streaming evaluation (ganmf_eval_begin..end)
+  int ev_pending_users = -1, ev_pending_ncut = 0;           // ganmf_evaluate_values done, sums not yet formed
   int last_ids_offset = 0;
   int last_n_global = 0;      // DisGANMF: rows of the global minibatch of the pending D update
   float last_alpha_d = 0.f;
@@ -306,11 +307,11 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   c->Wg = cfg->global_width > 0 ? cfg->global_width : cfg->width;
   c->tp_world = cfg->tp_world > 1 ? cfg->tp_world : 1;
   c->tp_rank = c->tp_world > 1 ? cfg->tp_rank : 0;
-  if (c->tp_world > 1 && (cfg->kind != GANMF_KIND_GANMF || cfg->item_mode || cfg->tp_rank < 0 ||
+  if (c->tp_world > 1 && (cfg->kind != GANMF_KIND_GANMF || cfg->tp_rank < 0 ||
                           cfg->tp_rank >= c->tp_world || cfg->item_offset < 0 ||
                           cfg->item_offset + cfg->width > c->Wg)) {
     delete c;
-    return fail("item-sharded contexts: GANMF --user only, 0 <= tp_rank < tp_world, slice inside global_width");
+    return fail("item-sharded contexts: GANMF only, 0 <= tp_rank < tp_world, slice inside global_width");
   }
   if (c->tp_world == 1 && (c->Wg != c->W || cfg->item_offset != 0)) { delete c; return fail("global_width / item_offset need tp_world > 1"); }
   const int sl = c->tp_world > 1;
@@ -1829,7 +1830,15 @@ static int eval_prologue(ganmf_ctx* c, const int32_t* cutoffs, int n_cut, int* K
 
 int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_t* cutoffs, int n_cut,
                    int remove_seen, int block, double* sums_host, int64_t* counts_host) {
-  if (!c || !users || !cutoffs || !sums_host || n_users < 0) return fail("bad argument");
+  if (!sums_host) return fail("bad argument");
+  RC(ganmf_evaluate_values(c, users, n_users, cutoffs, n_cut, remove_seen, block));
+  return ganmf_evaluate_sums(c, nullptr, sums_host, counts_host);
+}
+
+int ganmf_evaluate_values(ganmf_ctx* c, const int32_t* users, int n_users, const int32_t* cutoffs, int n_cut,
+                          int remove_seen, int block) {
+  if (!c || !users || !cutoffs || n_users < 0) return fail("bad argument");
+  c->ev_pending_users = -1;
   int K;
   RC(eval_prologue(c, cutoffs, n_cut, &K));
   RC(check_users(c, users, n_users));
@@ -1866,7 +1875,6 @@ int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_
   }
   CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n_users * 4, cudaMemcpyHostToDevice, c->st));
   CU(cudaMemcpyAsync(c->cut_dev, cutoffs, (size_t)n_cut * 4, cudaMemcpyHostToDevice, c->st));
-  CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
   CU(cudaMemsetAsync(c->icounts, 0, (size_t)n_cut * n_items * 4, c->st));
   if (fused) RC(prepare_fused(c));
   else RC(prepare_item_factors(c));
@@ -1881,7 +1889,18 @@ int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_
     }
     RC(metrics_block(c, n, K, n_cut, n_items, true, ud, c->uvals + (size_t)s * n_cut * MC_NCOL, fused, remove_seen));
   }
-  RC(accumulate_users(c, n_users, n_cut));
+  c->ev_pending_users = n_users; c->ev_pending_ncut = n_cut;
+  return 0;
+}
+
+int ganmf_evaluate_sums(ganmf_ctx* c, const double* carry_in, double* sums_host, int64_t* counts_host) {
+  if (!c || !sums_host) return fail("bad argument");
+  if (c->ev_pending_users < 0) return fail("ganmf_evaluate_values first");
+  const int n_users = c->ev_pending_users, n_cut = c->ev_pending_ncut;
+  const int n_items = n_items_of(c);
+  if (carry_in) CU(cudaMemcpyAsync(c->usums, carry_in, (size_t)n_cut * MC_NCOL * 8, cudaMemcpyHostToDevice, c->st));
+  else CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
+  if (n_users > 0) RC(accumulate_users(c, n_users, n_cut));
   CU(cudaMemcpyAsync(sums_host, c->usums, (size_t)n_cut * MC_NCOL * 8, cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));
   if (counts_host) {
@@ -1889,6 +1908,7 @@ int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_
     CU(cudaMemcpy(tmp.data(), c->icounts, tmp.size() * 4, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < tmp.size(); ++i) counts_host[i] = tmp[i];
   }
+  c->ev_pending_users = -1;
   return 0;
 }
 

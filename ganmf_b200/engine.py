@@ -323,6 +323,27 @@ class Engine(object):
                                         counts.ctypes.data_as(L._i64p) if counts is not None else None))
         return sums, counts
 
+    def evaluate_values(self, users, cutoffs, remove_seen=True, block_size=0):
+        """First half of evaluate(): per-user metric values of `users` (kept on the device)."""
+        ua, up = L.i32(users)
+        ca, cp = L.i32(cutoffs)
+        self._ev_ncut = ca.size
+        L.check(self.lib.ganmf_evaluate_values(self.ctx, up, ua.size, cp, ca.size, int(remove_seen), int(block_size)))
+
+    def evaluate_sums(self, carry_in=None, want_counts=True):
+        """Second half: running sums over those users IN ORDER, continuing from carry_in (the sums of the users
+        that precede them on other GPUs)."""
+        sums = np.zeros((self._ev_ncut, L.MC_NCOL), dtype=np.float64)
+        counts = np.zeros((self._ev_ncut, self.n_items), dtype=np.int64) if want_counts else None
+        cin = None
+        if carry_in is not None:
+            cin = np.ascontiguousarray(carry_in, dtype=np.float64)
+            assert cin.shape == sums.shape
+        L.check(self.lib.ganmf_evaluate_sums(self.ctx, cin.ctypes.data_as(L._f64p) if cin is not None else None,
+                                             sums.ctypes.data_as(L._f64p),
+                                             counts.ctypes.data_as(L._i64p) if counts is not None else None))
+        return sums, counts
+
     def eval_stats(self):
         """(rows ranked by the fused scorer, rows that needed the exact fallback) since the engine was created."""
         a, b = C.c_int64(), C.c_int64()

@@ -319,17 +319,22 @@ class ItemShardedTrainer(object):
         losses = self.read_losses(slot)
         return losses[:nd], losses[nd:]
 
-    def e2e_epoch(self, rs, n_rows, K, B, hp):
-        """bench.py: host ids in, losses out, wall clock around the whole call (ms)."""
-        perm = rs.permutation(n_rows)[:K * B].astype(np.int32)
-        self.dist.barrier()
-        self.torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        self.train_epoch(perm, B, 1, 1, hp)
-        self.torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) * 1e3
-        return {"ms": ms, "unit": "rows/s", "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 8,
-                "api": "ItemShardedTrainer.train_epoch: host row ids in, per-step losses out"}
+    def encode(self, rows):
+        """autoencoder_codes (GANMF.py:304-307) of an item-sharded model: R[rows] . We + be, the partial products over
+        the item slices summed like the codes of a training step (phase 1 of the D step)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        e0 = self.engines[0]
+        B, E = e0.cfg.max_batch, e0.cfg.emb_dim
+        out = np.empty((rows.size, E), dtype=np.float32)
+        for s in range(0, rows.size, B):
+            ids = rows[s:s + B]
+            for e in self.engines:
+                e.upload_ids(ids)
+            self._phase("tp_d_phase", 1, 0, ids.size, 0.0, 0.0, 1.0, 0)
+            self._sum("tp_h2", 0, 2 * ids.size * self.ld_h)
+            h = self.buf[0]["tp_h2"][:ids.size * self.ld_h].reshape(ids.size, self.ld_h)[:, :E]
+            out[s:s + ids.size] = h.cpu().numpy()
+        return out
 
 
 def item_slices(n_items, world_size):
@@ -345,14 +350,37 @@ def shard_rows(n_rows, world_size, rank):
 
 
 def sharded_eval_sums(engine, users_local, cutoffs, remove_seen, dist=None, group=None):
-    """Evaluation sharded by user rows: only the metric sums (and the per-item histograms) cross GPUs."""
+    """Evaluation sharded by user rows: only the metric sums (and the per-item histograms) cross GPUs.
+
+    `users_local` must be this rank's CONTIGUOUS range of the ascending global user list (rank order = user order).
+    Every rank computes the per-user metric values of its users in parallel; the running sums are then continued
+    rank after rank (rank r starts from the sums of ranks < r), so the result equals the single-GPU running sums over
+    all users bit for bit (the reference keeps one running float per metric, Evaluator.py:305-335).  The serial part
+    is the ordered accumulation alone (~12 ns per user)."""
     import torch
-    sums, counts = engine.evaluate(users_local, cutoffs, remove_seen=remove_seen)
+    engine.evaluate_values(users_local, cutoffs, remove_seen=remove_seen)
     n = np.array([len(users_local)], dtype=np.float64)
-    if dist is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-        for a in (sums, counts, n):
-            t = torch.from_numpy(a).to(dev)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-            a[...] = t.cpu().numpy()
+    if dist is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        sums, counts = engine.evaluate_sums(None)
+        return sums, counts, int(n[0])
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    ranks = [dist.get_global_rank(group, r) for r in range(world)] if group is not None else list(range(world))
+    carry = None
+    from . import _lib as L
+    shape = (len(cutoffs), L.MC_NCOL)
+    if rank > 0:
+        t = torch.zeros(shape, dtype=torch.float64, device=dev)
+        dist.recv(t, src=ranks[rank - 1], group=group)
+        carry = t.cpu().numpy()
+    sums, counts = engine.evaluate_sums(carry)
+    t = torch.from_numpy(sums).to(dev)
+    if rank < world - 1:
+        dist.send(t, dst=ranks[rank + 1], group=group)
+    dist.broadcast(t, src=ranks[world - 1], group=group)          # the last rank holds the sums over all users
+    sums = t.cpu().numpy()
+    for a in (counts, n):
+        t = torch.from_numpy(a).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        a[...] = t.cpu().numpy()
     return sums, counts, int(n[0])

@@ -209,6 +209,14 @@ int ganmf_set_eval_tables(ganmf_ctx* ctx, const float* test_gain_host, const flo
 int ganmf_evaluate(ganmf_ctx* ctx, const int32_t* user_ids_host, int n_users, const int32_t* cutoffs_host,
                    int n_cutoffs, int remove_seen, int block_size, double* sums_host,
                    int64_t* item_counts_host);
+/* The same in two calls, for evaluation sharded by user rows over several GPUs: every rank
+ * computes the per-user metric values of ITS contiguous range of the ascending user list (parallel), then the
+ * running sums are formed rank after rank -- rank r starts from the sums of ranks < r (carry_in_host,
+ * [n_cutoffs][GANMF_MC_NCOL]; NULL = zeros) -- so the final sums equal the single-GPU running sums over all users
+ * bit for bit (Evaluator.py:305-335 keeps ONE running sum per metric).  Item counts are plain integer sums. */
+int ganmf_evaluate_values(ganmf_ctx* ctx, const int32_t* user_ids_host, int n_users, const int32_t* cutoffs_host,
+                          int n_cutoffs, int remove_seen, int block_size);
+int ganmf_evaluate_sums(ganmf_ctx* ctx, const double* carry_in_host, double* sums_host, int64_t* item_counts_host);
 /* ganmf_recommend (without score rows) and ganmf_evaluate rank with the fused scorer when the largest cutoff is
  * <= 24 and num_factors <= 256: one TF32 tensor-core pass keeps per-row candidate lists in its epilogue (scores
  * never reach HBM), the candidates are re-scored exactly -- fl32(sum_k fp64(p_k v_k)) -- and each list carries a

@@ -197,3 +197,60 @@ def test_mf_context_scores_like_a_ganmf_context():
         a.d_step(0, 4, 1e-4, 0.0, 1.0)
     a.close()
     b.close()
+
+
+def test_matrix_factorization_base_recommender_on_device():
+    """Base/BaseMatrixFactorizationRecommender.py:94-143 mirror: factors set by a subclass' fit(), ranking and
+    evaluation on the device; biases and cold users take the host-edited score route of the reference."""
+    from ganmf_b200.Base.BaseMatrixFactorizationRecommender import BaseMatrixFactorizationRecommender
+    from ganmf_b200.Base.Evaluation.Evaluator import EvaluatorHoldout
+    rs = np.random.RandomState(21)
+    n_users, n_items, k = 240, 900, 20
+    train = sps.random(n_users, n_items, 0.03, format="csr", dtype=np.float32, random_state=rs)
+    train.data[:] = 1
+    train = train.tolil()
+    train[7, :] = 0                                     # a cold user
+    train = sps.csr_matrix(train)
+    train.eliminate_zeros()
+    test = sps.random(n_users, n_items, 0.02, format="csr", dtype=np.float32, random_state=rs)
+    test = sps.csr_matrix(test - test.multiply(train))
+    test.eliminate_zeros()
+    test.data[:] = 1
+
+    class PureSVDLike(BaseMatrixFactorizationRecommender):
+        RECOMMENDER_NAME = "PureSVDLike"
+
+        def fit(self):
+            self.USER_factors = rs.standard_normal((n_users, k)).astype(np.float32)
+            self.ITEM_factors = rs.standard_normal((n_items, k)).astype(np.float32)
+
+    rec = PureSVDLike(train)
+    rec.fit()
+    sc = exact_scores(rec.USER_factors, rec.ITEM_factors)
+    warm = np.array([u for u in range(40) if u != 7], dtype=np.int32)
+    lists = rec.recommend(warm, cutoff=10)
+    want = host_topk(sc[warm], train, warm, 10)
+    assert lists == [[int(i) for i in row if i >= 0] for row in want]
+    assert rec.recommend(np.array([7]), cutoff=10) == [[]]                    # cold user: -inf everywhere (:124-139)
+    raw = rec._compute_item_score(np.array([3, 7]))
+    assert np.all(np.isneginf(raw[1])) and np.allclose(raw[0], sc[3], rtol=1e-5, atol=1e-5)
+    only = np.array([5, 17, 300])
+    lim = rec._compute_item_score(np.array([3]), items_to_compute=only)      # :112-114
+    assert np.all(np.isneginf(np.delete(lim[0], only))) and np.all(np.isfinite(lim[0, only]))
+    # evaluator: equals the oracle on the recommender's own score rows (cold user included -> host-edited route)
+    res, _ = EvaluatorHoldout(test, cutoff_list=[5, 10], exclude_seen=True).evaluateRecommender(rec)
+    ores, _ = eo.evaluate(lambda u: rec._compute_item_score(u), train, test, [5, 10], promotion="legacy")
+    for c in (5, 10):
+        for m in ("PRECISION", "RECALL", "MAP", "NDCG", "MRR", "HIT_RATE", "COVERAGE_ITEM", "NOVELTY"):
+            assert float(res[c][m]) == pytest.approx(float(ores[c][m]), rel=1e-12), (c, m)
+    # biases (:119-122)
+    rec.use_bias = True
+    rec.ITEM_bias = rs.standard_normal(n_items).astype(np.float32)
+    rec.USER_bias = rs.standard_normal(n_users).astype(np.float32)
+    rec.GLOBAL_bias = np.float32(0.3)
+    b = rec._compute_item_score(np.array([3]))
+    assert np.allclose(b[0], sc[3] + rec.ITEM_bias + rec.GLOBAL_bias + rec.USER_bias[3], rtol=1e-5, atol=1e-5)
+    got = rec.recommend(np.array([3]), cutoff=5)[0]
+    s3 = b[0].copy()
+    s3[train.indices[train.indptr[3]:train.indptr[4]]] = -np.inf
+    assert got == [int(i) for i in np.argsort(-s3, kind="stable")[:5]]

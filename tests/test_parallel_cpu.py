@@ -46,8 +46,17 @@ class FakeEngine(object):
     def finalize_loss(self, reg, slot):
         self.log.append("finalize")
 
-    def evaluate(self, users, cutoffs, remove_seen=True):
-        return np.full((len(cutoffs), 3), float(len(users))), np.full((len(cutoffs), 5), self.rank + 1, dtype=np.int64)
+    n_items = 5
+
+    def evaluate_values(self, users, cutoffs, remove_seen=True):
+        self._ev = (len(users), len(cutoffs))
+
+    def evaluate_sums(self, carry_in=None):
+        from ganmf_b200._lib import MC_NCOL
+        n, nc = self._ev
+        base = np.zeros((nc, MC_NCOL)) if carry_in is None else np.array(carry_in)
+        # NOT associative on purpose: the chain must be continued in rank order from the carried value
+        return base * 2.0 + float(n), np.full((nc, 5), self.rank + 1, dtype=np.int64)
 
 
 def _worker(rank, world, port, q):
@@ -84,7 +93,8 @@ def test_dp_step_collectives_gloo():
         assert log[2] == ("d_apply", [3.0] * 4)                    # gradients summed before Adam
         assert log[3] == ("g_fb", 16)
         assert log[4] == ("g_apply", [30.0] * 3, 3.0) and log[5] == "finalize"
-        assert n == 7 and sums == [[7.0] * 3] * 2 and counts == [[3] * 5] * 2
+        # rank 0: 0*2 + 3 = 3; rank 1 continues from it: 3*2 + 4 = 10; every rank ends up with the last rank's sums
+        assert n == 7 and sums == [[10.0] * 13] * 2 and counts == [[3] * 5] * 2
 
 
 class FakeGanmfEngine(object):
