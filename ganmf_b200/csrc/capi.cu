@@ -110,16 +110,27 @@ struct ganmf_ctx {
   int* eval_users = nullptr; int eval_users_cap = 0;
   // fused scorer (score_select.cuh): gathered query factors, candidate lists, fallback bookkeeping
   bool eval_fused = true;              // GANMF_EVAL_FUSED=0: always the materialised split-TF32 scorer (A/B, tests)
-  Mat Qg;
-  float* cand_val = nullptr; int* cand_idx = nullptr; size_t cand_cap = 0;
+  // two buffer sets: while the tensor cores score block i+1, the re-scoring / metric kernels of block i run on
+  // side streams (they fit next to the one persistent GEMM CTA per SM)
+  struct FusedBuf {
+    Mat Qg;                              // gathered query factors of the block
+    float* cand_val = nullptr; int* cand_idx = nullptr; size_t cand_cap = 0;
+    unsigned int* row_thr = nullptr;     // shared per-row rejection thresholds
+    int* fb_rows = nullptr; size_t rows_cap = 0;
+    int* fb_count = nullptr; int* h_count = nullptr;     // device counter + pinned host copy
+    int* topk_idx = nullptr; float* topk_val = nullptr; size_t topk_cap = 0;
+    cudaEvent_t ev_sel = nullptr, ev_res = nullptr, ev_fin = nullptr;
+  } fbuf[2];
+  cudaStream_t st_res = nullptr, st_fin = nullptr;
+  cudaEvent_t ev_setup = nullptr, ev_pipe_done = nullptr;
   unsigned int* vmax_bits = nullptr;   // max_j ||ranked factor row j|| (float bits)
-  int* fb_count = nullptr; int* fb_rows = nullptr; int* fb_users = nullptr; size_t fb_cap = 0;
-  unsigned int* row_thr = nullptr;     // [fb_cap] shared per-row rejection thresholds of the fused scorer
+  int* fb_users = nullptr;
   int* fb_idx = nullptr; float* fb_val = nullptr; size_t fb_topk_cap = 0;
   long long fused_rows = 0, fallback_rows = 0;      // statistics since ganmf_create
   long long launches = 0;
   int ev_total = 0, ev_done = 0, ev_ncut = 0, ev_K = 0;     // streaming evaluation (ganmf_eval_begin..end)
   int ev_pending_users = -1, ev_pending_ncut = 0;           // ganmf_evaluate_values done, sums not yet formed
+  bool ev_sums_done = false;                                // ... or formed block by block already (ganmf_evaluate)
   int last_ids_offset = 0;
   int last_n_global = 0;      // DisGANMF: rows of the global minibatch of the pending D update
   float last_alpha_d = 0.f;
@@ -439,9 +450,17 @@ void ganmf_destroy(ganmf_ctx* c) {
   cudaFree(c->tb_popn); cudaFree(c->tb_haspop); cudaFree(c->rmse_scratch);
   cudaFree(c->scores); cudaFree(c->topk_idx); cudaFree(c->topk_val); cudaFree(c->uvals);
   cudaFree(c->usums); cudaFree(c->icounts); cudaFree(c->cut_dev); cudaFree(c->eval_users);
-  cudaFree(c->Qg.p); cudaFree(c->cand_val); cudaFree(c->cand_idx); cudaFree(c->vmax_bits);
-  cudaFree(c->row_thr);
-  cudaFree(c->fb_count); cudaFree(c->fb_rows); cudaFree(c->fb_users); cudaFree(c->fb_idx); cudaFree(c->fb_val);
+  for (auto& b : c->fbuf) {
+    cudaFree(b.Qg.p); cudaFree(b.cand_val); cudaFree(b.cand_idx); cudaFree(b.row_thr); cudaFree(b.fb_rows);
+    cudaFree(b.fb_count); cudaFree(b.topk_idx); cudaFree(b.topk_val);
+    if (b.h_count) cudaFreeHost(b.h_count);
+    for (cudaEvent_t ev : {b.ev_sel, b.ev_res, b.ev_fin}) if (ev) cudaEventDestroy(ev);
+  }
+  if (c->st_res) cudaStreamDestroy(c->st_res);
+  if (c->st_fin) cudaStreamDestroy(c->st_fin);
+  if (c->ev_setup) cudaEventDestroy(c->ev_setup);
+  if (c->ev_pipe_done) cudaEventDestroy(c->ev_pipe_done);
+  cudaFree(c->vmax_bits); cudaFree(c->fb_users); cudaFree(c->fb_idx); cudaFree(c->fb_val);
   for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
   delete c;
 }
@@ -1550,30 +1569,46 @@ constexpr int FB_BLOCK = 64;           // fallback rows scored exactly per pass
 static float fused_gamma(int k) { return 1.05f * (2.0f / 1024.0f + (float)(k + 8) * 1.2e-7f); }
 static bool fused_ok(ganmf_ctx* c, int K) { return c->eval_fused && K <= 24 && c->k <= SS_MAX_KB * TC_BK; }
 
-static int ensure_fused_buffers(ganmf_ctx* c, int block, int K) {
+static int ensure_fused_buffers(ganmf_ctx* c, int block, int K, int n_sets) {
   const int n_items = c->cfg.item_mode ? c->cfg.n_rows : c->W;
-  if (c->Qg.rows < block) {
-    cudaFree(c->Qg.p);
-    RC(mat_alloc(&c->Qg, block, c->k));
+  if (!c->st_res) {
+    CU(cudaStreamCreateWithFlags(&c->st_res, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->st_fin, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_setup, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_pipe_done, cudaEventDisableTiming));
+  }
+  for (int i = 0; i < n_sets; ++i) {
+    ganmf_ctx::FusedBuf& b = c->fbuf[i];
+    if (!b.ev_sel) {
+      CU(cudaEventCreateWithFlags(&b.ev_sel, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&b.ev_res, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&b.ev_fin, cudaEventDisableTiming));
+      RC(dalloc(&b.fb_count, 1));
+      CU(cudaMallocHost((void**)&b.h_count, 4));
+    }
+    if (b.Qg.rows < block) {
+      cudaFree(b.Qg.p);
+      RC(mat_alloc(&b.Qg, block, c->k));
+    }
+    if ((size_t)block > b.rows_cap) {
+      cudaFree(b.fb_rows); cudaFree(b.row_thr);
+      RC(dalloc(&b.fb_rows, (size_t)block));
+      RC(dalloc(&b.row_thr, (size_t)block));
+      b.rows_cap = block;
+    }
+    if ((size_t)block * K > b.topk_cap) {
+      cudaFree(b.topk_idx); cudaFree(b.topk_val);
+      RC(dalloc(&b.topk_idx, (size_t)block * K));
+      RC(dalloc(&b.topk_val, (size_t)block * K));
+      b.topk_cap = (size_t)block * K;
+    }
   }
   if (c->eval_users_cap < block) {
     cudaFree(c->eval_users);
     RC(dalloc(&c->eval_users, (size_t)block));
     c->eval_users_cap = block;
   }
-  if ((size_t)block * K > c->topk_cap) {
-    cudaFree(c->topk_idx); cudaFree(c->topk_val);
-    RC(dalloc(&c->topk_idx, (size_t)block * K));
-    RC(dalloc(&c->topk_val, (size_t)block * K));
-    c->topk_cap = (size_t)block * K;
-  }
-  if (!c->vmax_bits) { RC(dalloc(&c->vmax_bits, 1)); RC(dalloc(&c->fb_count, 1)); }
-  if ((size_t)block > c->fb_cap) {
-    cudaFree(c->fb_rows); cudaFree(c->row_thr);
-    RC(dalloc(&c->fb_rows, (size_t)block));
-    RC(dalloc(&c->row_thr, (size_t)block));
-    c->fb_cap = block;
-  }
+  if (!c->vmax_bits) RC(dalloc(&c->vmax_bits, 1));
   if (!c->fb_users) RC(dalloc(&c->fb_users, (size_t)FB_BLOCK));
   if ((size_t)FB_BLOCK * K > c->fb_topk_cap) {
     cudaFree(c->fb_idx); cudaFree(c->fb_val);
@@ -1602,8 +1637,9 @@ static int prepare_fused(ganmf_ctx* c) {
   return 0;
 }
 
-// top-K lists (c->topk_idx / c->topk_val, rows [0, n)) of the users at users_dev; prepare_fused() first
-static int fused_topk_block(ganmf_ctx* c, int n, const int* users_dev, int remove_seen, int K) {
+// stage 1 (tensor cores): query rows of the block -> candidate lists.  prepare_fused() first.
+static int fused_select(ganmf_ctx* c, ganmf_ctx::FusedBuf& b, int n, const int* users_dev, int remove_seen, int K,
+                        cudaStream_t st) {
   const Param& rows_of = c->cfg.item_mode ? c->params[c->n_d + 1] : c->params[c->n_d];
   const Param& other = c->cfg.item_mode ? c->params[c->n_d] : c->params[c->n_d + 1];
   const int n_items = other.w.rows;
@@ -1612,10 +1648,10 @@ static int fused_topk_block(ganmf_ctx* c, int n, const int* users_dev, int remov
     if (!seen.indptr) return fail("seen CSR not set");
     if (seen.n_cols != n_items) return fail("seen CSR has %d columns, scores have %d", seen.n_cols, n_items);
   }
-  gather_rows_kernel<<<n, 64, 0, c->st>>>(rows_of.w.p, users_dev, c->Qg.p, c->Qg.ld);
+  gather_rows_kernel<<<n, 64, 0, st>>>(rows_of.w.p, users_dev, b.Qg.p, b.Qg.ld);
   CU(cudaGetLastError());
   ScoreSelectCall sc;
-  sc.Q = c->Qg.p; sc.ldq = c->Qg.ld; sc.V = other.w.p; sc.ldv = other.w.ld;
+  sc.Q = b.Qg.p; sc.ldq = b.Qg.ld; sc.V = other.w.p; sc.ldv = other.w.ld;
   sc.n_rows = n; sc.n_items = n_items; sc.k = c->k;
   sc.KP = K <= 10 ? 16 : 32;
   sc.segs = score_select_segments(n, n_items, c->gemm_sm_cap > 0 ? c->gemm_sm_cap : 148);
@@ -1623,53 +1659,77 @@ static int fused_topk_block(ganmf_ctx* c, int n, const int* users_dev, int remov
   sc.seen_indptr = remove_seen ? seen.indptr : nullptr;
   sc.seen_indices = remove_seen ? seen.indices : nullptr;
   const size_t need = (size_t)n * 2 * sc.segs * sc.KP;             // candidate lists of this block
-  if (need > c->cand_cap) {
-    CU(cudaStreamSynchronize(c->st));
-    cudaFree(c->cand_val); cudaFree(c->cand_idx);
-    RC(dalloc(&c->cand_val, need));
-    RC(dalloc(&c->cand_idx, need));
-    c->cand_cap = need;
+  if (need > b.cand_cap) {
+    CU(cudaDeviceSynchronize());
+    cudaFree(b.cand_val); cudaFree(b.cand_idx);
+    RC(dalloc(&b.cand_val, need));
+    RC(dalloc(&b.cand_idx, need));
+    b.cand_cap = need;
   }
-  sc.cand_val = c->cand_val; sc.cand_idx = c->cand_idx;
-  sc.row_thr = c->row_thr;
-  CU(cudaMemsetAsync(c->row_thr, 0, (size_t)n * 4, c->st));
+  sc.cand_val = b.cand_val; sc.cand_idx = b.cand_idx;
+  sc.row_thr = b.row_thr;
+  CU(cudaMemsetAsync(b.row_thr, 0, (size_t)n * 4, st));
   sc.cache = &c->tmaps; sc.max_ctas = c->gemm_sm_cap;
-  cudaError_t e = score_select(sc, c->st);
+  cudaError_t e = score_select(sc, st);
   if (e != cudaSuccess) return fail("score_select(n=%d items=%d k=%d) -> %s", n, n_items, c->k, cudaGetErrorString(e));
-  CU(cudaMemsetAsync(c->fb_count, 0, 4, c->st));
-  const int NL = 2 * sc.segs;
+  c->launches += 2;
+  return 0;
+}
+
+// stage 2: exact re-scoring + certificate -> top-K lists of the block, number of uncertified rows -> b.h_count
+static int fused_rescore(ganmf_ctx* c, ganmf_ctx::FusedBuf& b, int n, int K, cudaStream_t st) {
+  const Param& other = c->cfg.item_mode ? c->params[c->n_d] : c->params[c->n_d + 1];
+  const int n_items = other.w.rows;
+  const int NL = 2 * score_select_segments(n, n_items, c->gemm_sm_cap > 0 ? c->gemm_sm_cap : 148);
   const float gamma = fused_gamma(c->k);
-  if (sc.KP == 16)
-    rescore_kernel<16><<<(n + 3) / 4, 128, 0, c->st>>>(c->cand_val, c->cand_idx, NL, n, K, c->Qg.p, c->Qg.ld, other.w.p,
-                                                       other.w.ld, c->k, c->vmax_bits, c->row_thr, gamma, c->topk_idx, c->topk_val,
-                                                       c->fb_count, c->fb_rows);
+  CU(cudaMemsetAsync(b.fb_count, 0, 4, st));
+  if (K <= 10)
+    rescore_kernel<16><<<(n + 3) / 4, 128, 0, st>>>(b.cand_val, b.cand_idx, NL, n, K, b.Qg.p, b.Qg.ld, other.w.p,
+                                                    other.w.ld, c->k, c->vmax_bits, b.row_thr, gamma, b.topk_idx,
+                                                    b.topk_val, b.fb_count, b.fb_rows);
   else
-    rescore_kernel<32><<<(n + 3) / 4, 128, 0, c->st>>>(c->cand_val, c->cand_idx, NL, n, K, c->Qg.p, c->Qg.ld, other.w.p,
-                                                       other.w.ld, c->k, c->vmax_bits, c->row_thr, gamma, c->topk_idx, c->topk_val,
-                                                       c->fb_count, c->fb_rows);
+    rescore_kernel<32><<<(n + 3) / 4, 128, 0, st>>>(b.cand_val, b.cand_idx, NL, n, K, b.Qg.p, b.Qg.ld, other.w.p,
+                                                    other.w.ld, c->k, c->vmax_bits, b.row_thr, gamma, b.topk_idx,
+                                                    b.topk_val, b.fb_count, b.fb_rows);
   CU(cudaGetLastError());
-  c->launches += 3;
-  int n_fb = 0;
-  CU(cudaMemcpyAsync(&n_fb, c->fb_count, 4, cudaMemcpyDeviceToHost, c->st));
-  CU(cudaStreamSynchronize(c->st));
+  CU(cudaMemcpyAsync(b.h_count, b.fb_count, 4, cudaMemcpyDeviceToHost, st));
+  c->launches++;
+  return 0;
+}
+
+// stage 3 (needs the host-side count): rows without a certificate get exact score rows -> the materialised
+// mask / top-k kernels -> back to their slots
+static int fused_fallback(ganmf_ctx* c, ganmf_ctx::FusedBuf& b, int n, const int* users_dev, int remove_seen, int K,
+                          int n_fb, cudaStream_t st) {
+  const Param& other = c->cfg.item_mode ? c->params[c->n_d] : c->params[c->n_d + 1];
+  const int n_items = other.w.rows;
+  const Csr& seen = c->csr[GANMF_CSR_SEEN];
   c->fused_rows += n;
   c->fallback_rows += n_fb;
-  // rows without a certificate: exact score rows -> the materialised mask / top-k kernels -> back to their slots
   const int ild = rup(n_items, 32);
   for (int f0 = 0; f0 < n_fb; f0 += FB_BLOCK) {
     const int nf = std::min(FB_BLOCK, n_fb - f0);
-    exact_score_rows_kernel<<<dim3(std::max(1, 148 * 4 / nf), nf), 256, 0, c->st>>>(
-        c->fb_rows, f0, nf, c->Qg.p, c->Qg.ld, other.w.p, other.w.ld, c->k, n_items, c->scores, ild);
-    gather_ids_kernel<<<1, FB_BLOCK, 0, c->st>>>(users_dev, c->fb_rows, f0, nf, c->fb_users);
-    if (remove_seen) mask_seen_kernel<<<nf, 128, 0, c->st>>>(c->scores, ild, c->fb_users, seen.indptr, seen.indices);
+    exact_score_rows_kernel<<<dim3(std::max(1, 148 * 4 / nf), nf), 256, 0, st>>>(
+        b.fb_rows, f0, nf, b.Qg.p, b.Qg.ld, other.w.p, other.w.ld, c->k, n_items, c->scores, ild);
+    gather_ids_kernel<<<1, FB_BLOCK, 0, st>>>(users_dev, b.fb_rows, f0, nf, c->fb_users);
+    if (remove_seen) mask_seen_kernel<<<nf, 128, 0, st>>>(c->scores, ild, c->fb_users, seen.indptr, seen.indices);
     CU(cudaGetLastError());
-    CU(topk_rows(c->scores, ild, nf, n_items, K, c->fb_idx, c->fb_val, c->st));
-    scatter_topk_kernel<<<(nf * K + 127) / 128, 128, 0, c->st>>>(c->fb_idx, c->fb_val, c->fb_rows, f0, nf, K, c->topk_idx,
-                                                                c->topk_val);
+    CU(topk_rows(c->scores, ild, nf, n_items, K, c->fb_idx, c->fb_val, st));
+    scatter_topk_kernel<<<(nf * K + 127) / 128, 128, 0, st>>>(c->fb_idx, c->fb_val, b.fb_rows, f0, nf, K, b.topk_idx,
+                                                             b.topk_val);
     CU(cudaGetLastError());
     c->launches += 5;
   }
   return 0;
+}
+
+// recommend(): one block, everything in stream order on the context's stream; lists end up in c->fbuf[0]
+static int fused_topk_block(ganmf_ctx* c, int n, const int* users_dev, int remove_seen, int K) {
+  ganmf_ctx::FusedBuf& b = c->fbuf[0];
+  RC(fused_select(c, b, n, users_dev, remove_seen, K, c->st));
+  RC(fused_rescore(c, b, n, K, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return fused_fallback(c, b, n, users_dev, remove_seen, K, *b.h_count, c->st);
 }
 
 int ganmf_eval_stats(ganmf_ctx* c, int64_t* fused_rows, int64_t* fallback_rows) {
@@ -1721,12 +1781,12 @@ int ganmf_recommend(ganmf_ctx* c, const int32_t* users, int n, int remove_seen, 
   if (K < 1 || K > TK_MAXK) return fail("top-K supports 1 <= K <= %d (got %d)", TK_MAXK, K);
   if (!masked_scores_host && fused_ok(c, K)) {
     // nobody asked for the score rows: fused scorer, the n x n_items matrix never exists
-    RC(ensure_fused_buffers(c, n, K));
+    RC(ensure_fused_buffers(c, n, K, 1));
     CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
     RC(prepare_fused(c));
     RC(fused_topk_block(c, n, c->eval_users, remove_seen, K));
-    CU(cudaMemcpyAsync(idx_host, c->topk_idx, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->st));
-    if (val_host) CU(cudaMemcpyAsync(val_host, c->topk_val, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(idx_host, c->fbuf[0].topk_idx, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->st));
+    if (val_host) CU(cudaMemcpyAsync(val_host, c->fbuf[0].topk_val, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     return 0;
   }
@@ -1781,10 +1841,13 @@ int ganmf_set_eval_tables(ganmf_ctx* c, const float* gain, const float* gain_des
 // per-user metric values for n rows whose lists are in c->topk_idx; `uvals` points at the first of those
 // rows inside the per-user value table.  The running sums are formed afterwards by accumulate_users().
 static int metrics_block(ganmf_ctx* c, int n, int K, int n_cut, int n_items, bool with_rmse,
-                         const int* users_dev, double* uvals, bool fused = false, int remove_seen = 0) {
+                         const int* users_dev, double* uvals, ganmf_ctx::FusedBuf* fb = nullptr, int remove_seen = 0,
+                         cudaStream_t st = nullptr) {
   const int total = n * n_cut;
-  user_metrics_kernel<<<(total + 127) / 128, 128, 0, c->st>>>(c->topk_idx, K, users_dev, n, c->cut_dev, n_cut,
-                                                            c->tb, uvals, c->icounts, n_items);
+  const bool fused = fb != nullptr;
+  if (!fused) st = c->st;
+  user_metrics_kernel<<<(total + 127) / 128, 128, 0, st>>>(fused ? fb->topk_idx : c->topk_idx, K, users_dev, n, c->cut_dev,
+                                                         n_cut, c->tb, uvals, c->icounts, n_items);
   CU(cudaGetLastError());
   c->launches++;
   if (with_rmse && fused) {
@@ -1792,7 +1855,7 @@ static int metrics_block(ganmf_ctx* c, int n, int K, int n_cut, int n_items, boo
     const Param& other = c->cfg.item_mode ? c->params[c->n_d] : c->params[c->n_d + 1];
     const Csr& te = c->csr[GANMF_CSR_TEST];
     const Csr& seen = c->csr[GANMF_CSR_SEEN];
-    user_rmse_exact_kernel<<<(n + 3) / 4, 128, 0, c->st>>>(c->Qg.p, c->Qg.ld, other.w.p, other.w.ld, c->k, users_dev, n,
+    user_rmse_exact_kernel<<<(n + 3) / 4, 128, 0, st>>>(fb->Qg.p, fb->Qg.ld, other.w.p, other.w.ld, c->k, users_dev, n,
                                                          n_cut, c->tb, te.data, remove_seen ? seen.indptr : nullptr,
                                                          remove_seen ? seen.indices : nullptr, c->rmse_scratch, uvals);
     CU(cudaGetLastError());
@@ -1809,10 +1872,11 @@ static int metrics_block(ganmf_ctx* c, int n, int K, int n_cut, int n_items, boo
   return 0;
 }
 // sums[cutoff][metric] = sum over users IN ORDER (Evaluator.py:305-335 keeps one running sum)
-static int accumulate_users(ganmf_ctx* c, int n_users, int n_cut) {
+static int accumulate_users(ganmf_ctx* c, int n_users, int n_cut, size_t first_user = 0, cudaStream_t st = nullptr) {
   const int ncols = n_cut * MC_NCOL;                     // <= 32 * 13 = 416 < OA_THREADS? no: handled below
   if (ncols > OA_THREADS) return fail("too many (cutoff, metric) columns for the ordered accumulation");
-  ordered_accumulate_kernel<<<1, OA_THREADS, 0, c->st>>>(c->uvals, n_users, ncols, c->usums);
+  // (continues the running sums already in c->usums: blocks of users are fed in order)
+  ordered_accumulate_kernel<<<1, OA_THREADS, 0, st ? st : c->st>>>(c->uvals + first_user * ncols, n_users, ncols, c->usums);
   CU(cudaGetLastError());
   c->launches++;
   return 0;
@@ -1828,17 +1892,27 @@ static int eval_prologue(ganmf_ctx* c, const int32_t* cutoffs, int n_cut, int* K
   return 0;
 }
 
+static int evaluate_values_impl(ganmf_ctx* c, const int32_t* users, int n_users, const int32_t* cutoffs, int n_cut,
+                                int remove_seen, int block, bool inline_sums);
+
 int ganmf_evaluate(ganmf_ctx* c, const int32_t* users, int n_users, const int32_t* cutoffs, int n_cut,
                    int remove_seen, int block, double* sums_host, int64_t* counts_host) {
   if (!sums_host) return fail("bad argument");
-  RC(ganmf_evaluate_values(c, users, n_users, cutoffs, n_cut, remove_seen, block));
+  // one GPU: the ordered running sums are formed block by block behind the scoring of the next block
+  RC(evaluate_values_impl(c, users, n_users, cutoffs, n_cut, remove_seen, block, true));
   return ganmf_evaluate_sums(c, nullptr, sums_host, counts_host);
 }
 
 int ganmf_evaluate_values(ganmf_ctx* c, const int32_t* users, int n_users, const int32_t* cutoffs, int n_cut,
                           int remove_seen, int block) {
+  return evaluate_values_impl(c, users, n_users, cutoffs, n_cut, remove_seen, block, false);
+}
+
+static int evaluate_values_impl(ganmf_ctx* c, const int32_t* users, int n_users, const int32_t* cutoffs, int n_cut,
+                                int remove_seen, int block, bool inline_sums) {
   if (!c || !users || !cutoffs || n_users < 0) return fail("bad argument");
   c->ev_pending_users = -1;
+  c->ev_sums_done = false;
   int K;
   RC(eval_prologue(c, cutoffs, n_cut, &K));
   RC(check_users(c, users, n_users));
@@ -1850,10 +1924,13 @@ int ganmf_evaluate_values(ganmf_ctx* c, const int32_t* users, int n_users, const
   // 1 GiB score buffer holds (at most 8192): fuller kernels, fewer launches.
   const bool fused = fused_ok(c, K);
   if (fused) {
-    // fused scorer: no score matrix, so a block is bounded only by the candidate lists (<= 128 K users)
-    block = block > 0 ? block : (1 << 17);
+    // fused scorer: no score matrix.  Blocks of <= 64 K users, two buffer sets: the re-scoring, metric and running-sum
+    // kernels of block i run on side streams while the tensor cores score block i+1.
+    if (block <= 0)
+      block = n_users <= (1 << 15) ? (n_users <= (1 << 14) ? n_users : (n_users / 2 + SS_ROWS - 1) / SS_ROWS * SS_ROWS)
+                                   : std::min(1 << 16, std::max(1 << 14, (n_users / 4 + SS_ROWS - 1) / SS_ROWS * SS_ROWS));
     block = std::min(block, std::max(n_users, 1));
-    RC(ensure_fused_buffers(c, block, K));
+    RC(ensure_fused_buffers(c, block, K, 2));
     RC(ensure_eval_buffers(c, 1, K, n_cut));           // metric tables (usums, icounts, cut_dev)
   } else {
     if (block <= 0) block = (int)std::min<long long>(8192, std::max<long long>(1, (1LL << 28) / rup(n_items, 32)));
@@ -1876,20 +1953,52 @@ int ganmf_evaluate_values(ganmf_ctx* c, const int32_t* users, int n_users, const
   CU(cudaMemcpyAsync(c->eval_users, users, (size_t)n_users * 4, cudaMemcpyHostToDevice, c->st));
   CU(cudaMemcpyAsync(c->cut_dev, cutoffs, (size_t)n_cut * 4, cudaMemcpyHostToDevice, c->st));
   CU(cudaMemsetAsync(c->icounts, 0, (size_t)n_cut * n_items * 4, c->st));
-  if (fused) RC(prepare_fused(c));
-  else RC(prepare_item_factors(c));
-  for (int s = 0; s < n_users; s += block) {
-    const int n = std::min(block, n_users - s);
-    const int* ud = c->eval_users + s;
-    if (fused) {
-      RC(fused_topk_block(c, n, ud, remove_seen, K));
-    } else {
+  if (inline_sums) CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
+  if (fused) {
+    RC(prepare_fused(c));
+    // setup (ids, tables, norms) is ordered before everything the side streams do
+    CU(cudaEventRecord(c->ev_setup, c->st));
+    CU(cudaStreamWaitEvent(c->st_res, c->ev_setup, 0));
+    CU(cudaStreamWaitEvent(c->st_fin, c->ev_setup, 0));
+    const int nb = (n_users + block - 1) / block;
+    for (int i = 0; i <= nb; ++i) {
+      if (i < nb) {                                    // tensor-core pass of block i, re-scoring right behind it
+        ganmf_ctx::FusedBuf& b = c->fbuf[i & 1];
+        const int s0 = i * block, n = std::min(block, n_users - s0);
+        if (i >= 2) CU(cudaStreamWaitEvent(c->st, b.ev_fin, 0));          // the set is free again
+        RC(fused_select(c, b, n, c->eval_users + s0, remove_seen, K, c->st));
+        CU(cudaEventRecord(b.ev_sel, c->st));
+        CU(cudaStreamWaitEvent(c->st_res, b.ev_sel, 0));
+        RC(fused_rescore(c, b, n, K, c->st_res));
+        CU(cudaEventRecord(b.ev_res, c->st_res));
+      }
+      if (i >= 1) {                                    // block i-1: fallback rows, metric values, running sums
+        ganmf_ctx::FusedBuf& b = c->fbuf[(i - 1) & 1];
+        const int s0 = (i - 1) * block, n = std::min(block, n_users - s0);
+        const int* ud = c->eval_users + s0;
+        CU(cudaEventSynchronize(b.ev_res));            // (the host needs the count of uncertified rows)
+        RC(fused_fallback(c, b, n, ud, remove_seen, K, *b.h_count, c->st_fin));
+        RC(metrics_block(c, n, K, n_cut, n_items, true, ud, c->uvals + (size_t)s0 * n_cut * MC_NCOL, &b, remove_seen,
+                         c->st_fin));
+        if (inline_sums) RC(accumulate_users(c, n, n_cut, (size_t)s0, c->st_fin));
+        CU(cudaEventRecord(b.ev_fin, c->st_fin));
+      }
+    }
+    CU(cudaEventRecord(c->ev_pipe_done, c->st_fin));
+    CU(cudaStreamWaitEvent(c->st, c->ev_pipe_done, 0));
+  } else {
+    RC(prepare_item_factors(c));
+    for (int s = 0; s < n_users; s += block) {
+      const int n = std::min(block, n_users - s);
+      const int* ud = c->eval_users + s;
       RC(score_block(c, n, ud));
       RC(mask_and_topk(c, n, n_items, remove_seen, K, ud));
+      RC(metrics_block(c, n, K, n_cut, n_items, true, ud, c->uvals + (size_t)s * n_cut * MC_NCOL));
     }
-    RC(metrics_block(c, n, K, n_cut, n_items, true, ud, c->uvals + (size_t)s * n_cut * MC_NCOL, fused, remove_seen));
+    if (inline_sums && n_users > 0) RC(accumulate_users(c, n_users, n_cut));
   }
   c->ev_pending_users = n_users; c->ev_pending_ncut = n_cut;
+  c->ev_sums_done = inline_sums;
   return 0;
 }
 
@@ -1898,9 +2007,13 @@ int ganmf_evaluate_sums(ganmf_ctx* c, const double* carry_in, double* sums_host,
   if (c->ev_pending_users < 0) return fail("ganmf_evaluate_values first");
   const int n_users = c->ev_pending_users, n_cut = c->ev_pending_ncut;
   const int n_items = n_items_of(c);
-  if (carry_in) CU(cudaMemcpyAsync(c->usums, carry_in, (size_t)n_cut * MC_NCOL * 8, cudaMemcpyHostToDevice, c->st));
-  else CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
-  if (n_users > 0) RC(accumulate_users(c, n_users, n_cut));
+  if (c->ev_sums_done) {
+    if (carry_in) return fail("the running sums of this evaluation were already formed from zero");
+  } else {
+    if (carry_in) CU(cudaMemcpyAsync(c->usums, carry_in, (size_t)n_cut * MC_NCOL * 8, cudaMemcpyHostToDevice, c->st));
+    else CU(cudaMemsetAsync(c->usums, 0, (size_t)n_cut * MC_NCOL * 8, c->st));
+    if (n_users > 0) RC(accumulate_users(c, n_users, n_cut));
+  }
   CU(cudaMemcpyAsync(sums_host, c->usums, (size_t)n_cut * MC_NCOL * 8, cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));
   if (counts_host) {

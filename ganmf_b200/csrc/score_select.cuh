@@ -418,22 +418,38 @@ __device__ __forceinline__ void exact_dot4_warp(const double (&qd)[8], const flo
   for (int u = 0; u < 4; ++u) out[u] = (float)acc[u];
 }
 
-// max_j ||V[j, :]||_2 -> *out (float bits, atomicMax on the non-negative pattern); one warp per 4 rows, 16-byte loads
+// max_j ||V[j, :]||_2 -> *out (float bits, atomicMax on the non-negative pattern); one warp per 4 rows, all four rows'
+// 16-byte loads in flight together
 __global__ void row_norm_max_kernel(const float* __restrict__ V, int rows, int k, int ld, unsigned int* out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int r0 = warp * 4;
+  if (r0 >= rows) return;
   const int k4 = k >> 2;
-  for (int r = warp * 4; r < min(warp * 4 + 4, rows); ++r) {
-    const float4* v4 = reinterpret_cast<const float4*>(V + (size_t)r * ld);       // ld is a multiple of 32
-    float s = 0.f;
-    for (int i = lane; i < k4; i += 32) {
-      const float4 x = __ldg(v4 + i);
-      s = fmaf(x.x, x.x, s); s = fmaf(x.y, x.y, s); s = fmaf(x.z, x.z, s); s = fmaf(x.w, x.w, s);
-    }
-    for (int i = (k4 << 2) + lane; i < k; i += 32) { const float x = V[(size_t)r * ld + i]; s = fmaf(x, x, s); }
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = lane; i < k4; i += 32) {
+    float4 x[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) atomicMax(out, __float_as_uint(sqrtf(s) * 1.0001f));
+    for (int j = 0; j < 4; ++j)
+      x[j] = r0 + j < rows ? __ldg(reinterpret_cast<const float4*>(V + (size_t)(r0 + j) * ld) + i)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s[j] = fmaf(x[j].x, x[j].x, s[j]); s[j] = fmaf(x[j].y, x[j].y, s[j]);
+      s[j] = fmaf(x[j].z, x[j].z, s[j]); s[j] = fmaf(x[j].w, x[j].w, s[j]);
+    }
   }
+  for (int i = (k4 << 2) + lane; i < k; i += 32)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (r0 + j < rows) { const float x = V[(size_t)(r0 + j) * ld + i]; s[j] = fmaf(x, x, s[j]); }
+  float m = fmaxf(fmaxf(0.f, 0.f), 0.f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    m = fmaxf(m, s[j]);
+  }
+  if (lane == 0) atomicMax(out, __float_as_uint(sqrtf(m) * 1.0001f));
 }
 
 // Total order of the evaluator: higher score first, then lower item index (== topk_key's order for finite scores)
