@@ -67,7 +67,8 @@ struct SelSmem {
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = SS_MAX_KB * A_KB_BYTES;
   static constexpr int BAR_OFF = B_OFF + SS_STAGES * B_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * SS_STAGES + 6) * 8 + 16 + 1024;
+  static constexpr int VAL_OFF = BAR_OFF + (2 * SS_STAGES + 6) * 8 + 16;       // slow-path staging: 32 scores x 256 threads
+  static constexpr int TOTAL = VAL_OFF + 32 * 256 * 4 + 1024;
 };
 
 // sorted (descending) insertion of (v, idx) into the KP-entry register list; v > sv[KP-1] on entry
@@ -81,6 +82,23 @@ __device__ __forceinline__ void sel_insert(float (&sv)[KP], int (&si)[KP], float
     si[j] = here ? (above ? si[j - 1] : idx) : si[j];
   }
   if (v > sv[0]) { sv[0] = v; si[0] = idx; }
+}
+
+// 32 lanes x 32 consecutive fp32 columns into r[OFF .. OFF+32) of a larger register array
+template <int OFF, int N>
+__device__ __forceinline__ void tmem_ld_32x32_at(uint32_t taddr, uint32_t (&r)[N]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[OFF + 0]), "=r"(r[OFF + 1]), "=r"(r[OFF + 2]), "=r"(r[OFF + 3]), "=r"(r[OFF + 4]), "=r"(r[OFF + 5]),
+        "=r"(r[OFF + 6]), "=r"(r[OFF + 7]), "=r"(r[OFF + 8]), "=r"(r[OFF + 9]), "=r"(r[OFF + 10]), "=r"(r[OFF + 11]),
+        "=r"(r[OFF + 12]), "=r"(r[OFF + 13]), "=r"(r[OFF + 14]), "=r"(r[OFF + 15]), "=r"(r[OFF + 16]), "=r"(r[OFF + 17]),
+        "=r"(r[OFF + 18]), "=r"(r[OFF + 19]), "=r"(r[OFF + 20]), "=r"(r[OFF + 21]), "=r"(r[OFF + 22]), "=r"(r[OFF + 23]),
+        "=r"(r[OFF + 24]), "=r"(r[OFF + 25]), "=r"(r[OFF + 26]), "=r"(r[OFF + 27]), "=r"(r[OFF + 28]), "=r"(r[OFF + 29]),
+        "=r"(r[OFF + 30]), "=r"(r[OFF + 31])
+      : "r"(taddr)
+      : "memory");
 }
 
 template <int KP>
@@ -225,44 +243,75 @@ score_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (sp < se) ns0 = __ldg(args.seen_indices + sp);
         if (sp + 1 < se) ns1 = __ldg(args.seen_indices + sp + 1);
       }
+      // GROUP chunks (32 columns each) are pulled out of TMEM at a time; with GROUP = 4 the whole 128-column share of
+      // this warp sits in registers and the accumulator stage is handed back to the MMA warp BEFORE any selection
+      // work: the tensor cores never wait for a warp that happens to have insertions to do (ncu: with the release
+      // after the last chunk's load only, the MMA warp spent most of its time on tmem_empty -- the slowest of the
+      // pair's 16 epilogue warps sets the pace -- and the tensor pipe idled half the time).
+      constexpr int GROUP = KP <= 16 ? 4 : 2;
+      float* sval = reinterpret_cast<float*>(smem + S::VAL_OFF) + (threadIdx.x - 64);   // [32][256]: slow-path staging
       for (int t = t0; t < t1; ++t, ++ti) {
         const uint32_t acc = ti & 1;
         // what the other lists of this row have published meanwhile (the load is consumed a tile later)
         const unsigned int thr_seen = live ? __ldcg(thr_slot) : 0u;
         ptx::mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
         ptx::tc_fence_after();
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          const int c = half * (SS_BN / 2) + j * 32;
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(tmem_base + acc * SS_BN + (uint32_t)c + ((uint32_t)(q * 32) << 16), r);
+#pragma unroll
+        for (int g = 0; g < 4 / GROUP; ++g) {
+          uint32_t r[32 * GROUP];
+          const uint32_t tbase = tmem_base + acc * SS_BN + (uint32_t)(half * (SS_BN / 2) + g * GROUP * 32) +
+                                 ((uint32_t)(q * 32) << 16);
+          tmem_ld_32x32_at<0>(tbase, r);
+          tmem_ld_32x32_at<32>(tbase + 32, r);
+          if (GROUP == 4) {
+            tmem_ld_32x32_at<(GROUP == 4 ? 64 : 0)>(tbase + 64, r);
+            tmem_ld_32x32_at<(GROUP == 4 ? 96 : 0)>(tbase + 96, r);
+          }
           ptx::tmem_ld_wait();
-          if (j == 3) {                                 // last TMEM read of this warp for this tile
+          if (g == 4 / GROUP - 1) {                     // last TMEM read of this warp for this tile
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty_bar[acc]), 0u));
           }
-          const int n0 = t * SS_BN + c;
-          // columns to skip: beyond the matrix (TMA zero-filled them) and the row's seen items
-          uint32_t skip = n0 + 32 <= args.n_items ? 0u : (n0 >= args.n_items ? 0xFFFFFFFFu : (0xFFFFFFFFu << (args.n_items - n0)));
-          while (ns0 < n0 + 32) {
-            if (ns0 >= n0) skip |= 1u << (ns0 - n0);
-            ++sp;
-            ns0 = ns1;
-            ns1 = sp + 1 < se ? __ldg(args.seen_indices + sp + 1) : 0x7fffffff;
-          }
-          if (!live) skip = 0xFFFFFFFFu;
-          const float thr0 = fmaxf(sv[KP - 1], thr_ext);
-          // quick reject: nothing of this chunk beats the row's KP-th best (the common case once the list has
-          // warmed up); masked columns may only cause a false alarm here, they are excluded again below
-          float mx = __uint_as_float(r[0]);
 #pragma unroll
-          for (int e = 1; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
-          if (!__any_sync(0xffffffffu, mx > thr0 && skip != 0xFFFFFFFFu)) continue;
+          for (int jj = 0; jj < GROUP; ++jj) {
+            const int n0 = t * SS_BN + half * (SS_BN / 2) + (g * GROUP + jj) * 32;
+            // columns to skip: beyond the matrix (TMA zero-filled them) and the row's seen items
+            uint32_t skip = n0 + 32 <= args.n_items ? 0u : (n0 >= args.n_items ? 0xFFFFFFFFu : (0xFFFFFFFFu << (args.n_items - n0)));
+            while (ns0 < n0 + 32) {
+              if (ns0 >= n0) skip |= 1u << (ns0 - n0);
+              ++sp;
+              ns0 = ns1;
+              ns1 = sp + 1 < se ? __ldg(args.seen_indices + sp + 1) : 0x7fffffff;
+            }
+            if (!live) skip = 0xFFFFFFFFu;
+            const float thr0 = fmaxf(sv[KP - 1], thr_ext);
+            // quick reject: nothing of this chunk beats the row's threshold (the common case once the lists have
+            // warmed up); masked columns may only cause a false alarm here, they are excluded below
+            float mx = __uint_as_float(r[32 * jj]);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float v = __uint_as_float(r[e]);
-            if (v > fmaxf(sv[KP - 1], thr_ext) && !((skip >> e) & 1u)) sel_insert<KP>(sv, si, v, n0 + e);
+            for (int e = 1; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[32 * jj + e]));
+            if (!__any_sync(0xffffffffu, mx > thr0 && skip != 0xFFFFFFFFu)) continue;
+            // slow path: bit e of pm = column e of the chunk beats the threshold and may be ranked
+            uint32_t pm = 0u;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) pm |= (__uint_as_float(r[32 * jj + e]) > thr0 ? 1u : 0u) << e;
+            pm &= ~skip;
+            if (!__any_sync(0xffffffffu, pm != 0u)) continue;
+            // the chunk goes to shared memory so the survivors can be addressed dynamically; ONE copy of the insertion
+            // code serves all lanes and all survivors (iterations = the largest survivor count of a lane, usually 1)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) sval[e * 256] = __uint_as_float(r[32 * jj + e]);
+            __syncwarp();
+            while (__any_sync(0xffffffffu, pm != 0u)) {
+              if (pm) {
+                const int e = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const float v = sval[e * 256];
+                if (v > fmaxf(sv[KP - 1], thr_ext)) sel_insert<KP>(sv, si, v, n0 + e);
+              }
+            }
+            __syncwarp();
           }
         }
         if (live && sv[KP - 1] > thr_pub) {             // publish (fire and forget)
@@ -308,6 +357,9 @@ struct ScoreSelectCall {
 
 inline int score_select_segments(int n_rows, int n_items, int num_sms) {
   // enough units to fill the CTA pairs evenly; every segment keeps >= 8 item tiles
+  static int forced = -1;                  // GANMF_EVAL_SEGS=n: A/B switch
+  if (forced < 0) { const char* e = getenv("GANMF_EVAL_SEGS"); forced = e ? atoi(e) : 0; }
+  if (forced > 0) return forced > SS_MAX_LISTS / 2 ? SS_MAX_LISTS / 2 : forced;
   const int pairs = num_sms / 2, rb = (n_rows + SS_ROWS - 1) / SS_ROWS;
   const int tiles = (n_items + SS_BN - 1) / SS_BN;
   int best = 1;

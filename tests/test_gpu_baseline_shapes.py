@@ -106,14 +106,14 @@ def test_cfg3_disganmf_item_hetrec2011_steps_parity():
     """DisGANMF --item, hetrec2011 split: 10 109 rows, 4 hidden layers of 1024 units, B = 256 -- the wide case.
 
     With these committed hyper-parameters the trajectory is CHAOTIC: the raw row id (up to 10 108) is a discriminator
-    input (DisGANMF.py:110), the logits are O(100..1000), the D loss is O(100), and Adam's first updates are
-    sign-like (m / sqrt(v) = +-1), so gradient elements at rounding-noise level move their weight by +-lr in a
-    rounding-dependent direction.  From identical weights the FIRST step agrees with the oracle to ~1e-6; a free
-    run then separates by ~1e-2 within two steps for ANY change of summation order (measured below on the
-    split-TF32 path, which has fp32-accurate products; TF's own CPU and GPU kernels would separate the same way).
-    The contract is therefore checked per step: before every step the device gets the oracle's current weights
-    (teacher forcing, zero Adam moments on both sides), the losses must agree within 1e-3, the updated weights
-    within 1e-3 * sqrt(2) of each other relative to the SIZE OF THE UPDATE being ~lr per element."""
+    input (DisGANMF.py:110), the logits are O(100..1000), the D loss is O(100), and Adam's first updates are sign-like
+    (m / sqrt(v) = +-1), so gradient elements at rounding-noise level move their weight by +-lr in a rounding-dependent
+    direction, which the id feature amplifies by 1e4.  From identical weights the D loss agrees with the fp32 oracle to
+    ~1e-6, but the G loss evaluated right after that ONE D update already differs by ~1e-2 -- for any change of summation
+    order (measured below on the split-TF32 path, whose products are fp32-accurate; the fp32 oracle itself is that far
+    from the fp64 oracle).  The contract is therefore checked per UPDATE: before every D step and before every G step the
+    device gets the oracle's current weights (zero Adam moments on both sides), each loss must agree within 1e-3, and the
+    device must be as close to the float64 oracle as the float32 oracle is (factor 3)."""
     from ganmf_b200 import _lib as L
     from ganmf_b200.engine import Engine
     bp = load_quality_targets()["DisGANMF_item_hetrec2011"]["best_params"]
@@ -122,38 +122,63 @@ def test_cfg3_disganmf_item_hetrec2011_steps_parity():
     k, B, layers, nodes = int(bp["num_factors"]), int(bp["batch_size"]), int(bp["d_layers"]), int(bp["d_nodes"])
     assert (n_rows, width, k, B, layers, nodes) == (10109, 2113, 25, 256, 4, 1024)
     act = bp["d_hidden_act"]
-    p = to.init_disganmf_params(n_rows, width, k, layers, nodes, seed=3)
-    eng = Engine(L.KIND_DISGANMF, n_rows, width, k, d_layers=layers, d_nodes=nodes, d_act=act, max_batch=B, item_mode=True)
-    eng.set_csr(L.CSR_TRAIN, urm)
-    batches = pick_batches(n_rows, B, 5)
-    worst_loss, worst_upd = 0.0, 0.0
-    for b in batches:
-        eng.set_params(p)
-        eng.reset_optimizers()
-        orc = to.DisGanmfOracle(p, layers, act, bp["d_lr"], bp["g_lr"], dtype=np.float32)
-        eng.upload_ids(b.astype(np.int32))
-        eng.d_step(0, len(b), bp["d_lr"], bp["d_reg"], 1.0, loss_slot=0)
-        eng.g_step(0, len(b), bp["g_lr"], 0.0, bp["recon_coefficient"], loss_slot=1)
-        got_l = eng.read_losses(2)
-        R = to.csr_rows_to_dense(urm, b)
-        want_l = [orc.d_step(b, R, d_reg=bp["d_reg"]), orc.g_step(b, R, g_reg=0.0, recon_coefficient=bp["recon_coefficient"])]
-        np.testing.assert_allclose(got_l, want_l, rtol=REL)
-        worst_loss = max(worst_loss, float(np.max(np.abs(got_l - np.array(want_l)) / np.abs(want_l))))
-        got = eng.get_params()
-        for n in orc.p:
-            # the first Adam step moves every element by ~lr: compare the UPDATES (theta_new - theta_old)
-            du, dw = got[n].astype(np.float64) - p[n], orc.p[n].astype(np.float64) - p[n]
-            if np.linalg.norm(dw) > 0:
-                worst_upd = max(worst_upd, float(np.linalg.norm(du - dw) / np.linalg.norm(dw)))
-        p = {n: v.copy() for n, v in orc.p.items()}                # the next step starts from the oracle's weights
-    print("cfg3-item teacher-forced: worst loss rel err %.2e, worst update rel err %.2e" % (worst_loss, worst_upd))
-    assert worst_upd < 0.05          # sign-like first Adam steps: elements with |g| at rounding level flip (+-lr)
-    eng.close()
+    d_names = to.disganmf_d_names(layers)
+    for path, tol in (("GEMM_SIMT", 1e-3), ("GEMM_AUTO", 0.15)):
+        _cfg3_item_teacher_forced(path, tol, bp, urm, k, B, layers, nodes, act, d_names)
     # free-running trajectories, for the record (not asserted at 1e-3: see the docstring)
     for path in ("GEMM_AUTO", "GEMM_TC"):
         _, losses, want, got, ref = disganmf_case("DisGANMF_item_hetrec2011", "Movielenshetrec2011", True, 5, path)
         print("free run, %s: loss rel err per step %s" % (path, np.array2string(np.abs(losses - want) / np.abs(want), precision=1)))
         assert abs(losses[0] - want[0]) <= REL * abs(want[0])      # the very first step (identical weights) agrees
+
+
+def _cfg3_item_teacher_forced(path, tol, bp, urm, k, B, layers, nodes, act, d_names):
+    """path GEMM_SIMT: exact fp32 FMA GEMMs -- the update must be as close to the float64 oracle as the float32 oracle
+    is (factor 3, floor 1e-3).  path GEMM_AUTO (split-TF32 on the tensor cores, the shipping path): products are
+    fp32-accurate but the tensor core accumulates K in its own order and rounding, and here the weight gradients are
+    sums of a real and a fake half that cancel to ~1e-3 of their terms: a fraction ~1e-3 of the elements change sign,
+    which a sign-like first Adam step turns into an update error of a few percent.  Recorded, bounded at `tol`."""
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    n_rows, width = urm.shape
+    p = to.init_disganmf_params(n_rows, width, k, layers, nodes, seed=3)
+    eng = Engine(L.KIND_DISGANMF, n_rows, width, k, d_layers=layers, d_nodes=nodes, d_act=act, max_batch=B, item_mode=True,
+                 gemm_path=getattr(L, path))
+    eng.set_csr(L.CSR_TRAIN, urm)
+
+    def upd_err(got, ref64, names, p_old):
+        num = sum(float(np.sum((got[n].astype(np.float64) - ref64[n]) ** 2)) for n in names)
+        den = sum(float(np.sum((ref64[n] - p_old[n].astype(np.float64)) ** 2)) for n in names)
+        return np.sqrt(num / max(den, 1e-300))
+
+    report = []
+    for b in pick_batches(n_rows, B, 4):
+        R = to.csr_rows_to_dense(urm, b)
+        for which in ("d", "g"):
+            eng.set_params(p)
+            eng.reset_optimizers()
+            o32 = to.DisGanmfOracle(p, layers, act, bp["d_lr"], bp["g_lr"], dtype=np.float32)
+            o64 = to.DisGanmfOracle(p, layers, act, bp["d_lr"], bp["g_lr"], dtype=np.float64)
+            eng.upload_ids(b.astype(np.int32))
+            if which == "d":
+                eng.d_step(0, len(b), bp["d_lr"], bp["d_reg"], 1.0, loss_slot=0)
+                l32, l64 = (o.d_step(b, R, d_reg=bp["d_reg"]) for o in (o32, o64))
+                names = d_names
+            else:
+                eng.g_step(0, len(b), bp["g_lr"], 0.0, bp["recon_coefficient"], loss_slot=0)
+                l32, l64 = (o.g_step(b, R, g_reg=0.0, recon_coefficient=bp["recon_coefficient"]) for o in (o32, o64))
+                names = to.GANMF_G
+            got_l = float(eng.read_losses(1)[0])
+            assert abs(got_l - l64) <= REL * abs(l64), (which, got_l, l32, l64)
+            got = eng.get_params()
+            e_dev, e_o32 = upd_err(got, o64.p, names, p), upd_err(o32.p, o64.p, names, p)
+            report.append((which, abs(got_l - l64) / abs(l64), e_dev, e_o32))
+            # the update of the device is as close to the float64 update as the float32 oracle's is
+            assert e_dev <= max(3.0 * e_o32, tol), (path, which, e_dev, e_o32)
+        p = {n: v.astype(np.float32) for n, v in o64.p.items()}   # next batch starts from the float64 oracle's weights
+    for r in report:
+        print("cfg3-item %s, %s step: loss rel err %.1e, update error vs fp64: device %.2e, fp32 oracle %.2e" % ((path,) + r))
+    eng.close()
 
 
 def test_cfg4_synthetic_shape_five_steps_parity():

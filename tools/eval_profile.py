@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--density", type=float, default=0.001)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cutoff", type=int, default=10)
+    ap.add_argument("--block", type=int, default=0)
     a = ap.parse_args()
     import torch
     from ganmf_b200 import _lib as L
@@ -40,20 +41,21 @@ def main():
     test = bench.csr_to_host(tip, tix, (U, I))
     e.set_test(test, item_popularity=pop)
     users = np.flatnonzero(np.diff(test.indptr) > 0).astype(np.int32)
-    e.evaluate(users, [a.cutoff], remove_seen=True, want_counts=False)
+    e.evaluate(users, [a.cutoff], remove_seen=True, want_counts=False, block_size=a.block)
     torch.cuda.synchronize()
     best = 1e9
     for _ in range(a.reps):
         t0 = time.perf_counter()
         if os.environ.get("EVAL_PROFILE_RANGE") == "1":
             torch.cuda.profiler.start()
-        e.evaluate(users, [a.cutoff], remove_seen=True, want_counts=False)
+        e.evaluate(users, [a.cutoff], remove_seen=True, want_counts=False, block_size=a.block)
         torch.cuda.synchronize()
         if os.environ.get("EVAL_PROFILE_RANGE") == "1":
             torch.cuda.profiler.stop()
         best = min(best, time.perf_counter() - t0)
     fused, fb = e.eval_stats()
     pk = bench.peaks()
+    print("block=%d segs=%s " % (a.block, os.environ.get("GANMF_EVAL_SEGS", "auto")), end="")
     print("items=%d users=%d k=%d: %.3f ms, %.3g users/s, frac of 4*I HBM roofline %.3f, fused rows %d, fallback %d" %
           (I, len(users), a.k, best * 1e3, len(users) / best, len(users) / best * 4 * I / 1e9 / pk["hbm"], fused, fb))
 
