@@ -552,7 +552,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-kernels", action="store_true")
     ap.add_argument("--no-second-record", action="store_true")
-    ap.add_argument("--eval-users", type=int, default=32768, help="users evaluated per rank")
+    ap.add_argument("--eval-users", type=int, default=131072, help="users evaluated per rank")
     ap.add_argument("--quick", action="store_true", help="A/B runs: training throughput + GEMM roofline only")
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS),
                     help="cfg5 = 2M x 200k (default, BASELINE.json configs[4]); cfg4 = 138k x 27k (configs[3])")

@@ -70,6 +70,8 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
             self._scorer.close()
         self._trainer, self._scorer, self._scorer_dirty = None, None, True
         dist, world, rank = _dist_state()
+        if os.environ.get("GANMF_GEMM_PATH"):             # A/B switch: 1 = exact fp32 FMA, 2 = TF32, 3 = split-TF32
+            gemm_path = int(os.environ["GANMF_GEMM_PATH"])
         if device is None:
             device = 0
             if dist is not None:
