@@ -727,21 +727,25 @@ static int forward_generator(ganmf_ctx* c, int ids_offset, int B) {
 }
 
 static int adam_group(ganmf_ctx* c, int first, int count, float alpha, float reg, int slot_param) {
-  AdamArgs a;
-  memset(&a, 0, sizeof a);
-  a.nseg = count;
-  for (int i = 0; i < count; ++i) {
-    Param& p = c->params[first + i];
-    AdamSeg& s = a.seg[i];
-    s.theta = p.w.p; s.m = p.m; s.v = p.v; s.g = p.g; s.slot = nullptr; s.ld = p.w.ld;
-    s.n4 = p.w.elems() / 4;
-    if (first + i == slot_param) { s.g = c->dPb.p; s.slot = c->slot; }
+  // one launch per ADAM_MAX_SEG tensors (a 4-layer DisGANMF discriminator has 10)
+  for (int f0 = 0; f0 < count; f0 += ADAM_MAX_SEG) {
+    const int n = std::min(ADAM_MAX_SEG, count - f0);
+    AdamArgs a;
+    memset(&a, 0, sizeof a);
+    a.nseg = n;
+    for (int i = 0; i < n; ++i) {
+      Param& p = c->params[first + f0 + i];
+      AdamSeg& s = a.seg[i];
+      s.theta = p.w.p; s.m = p.m; s.v = p.v; s.g = p.g; s.slot = nullptr; s.ld = p.w.ld;
+      s.n4 = p.w.elems() / 4;
+      if (first + f0 + i == slot_param) { s.g = c->dPb.p; s.slot = c->slot; }
+    }
+    a.alpha = alpha; a.reg = reg;
+    a.l2_out = &c->sc->l2;
+    a.l2_shard_out = &c->sc->l2_shard;
+    c->launches++;
+    CU(fused_adam(a, c->st));
   }
-  a.alpha = alpha; a.reg = reg;
-  a.l2_out = &c->sc->l2;
-  a.l2_shard_out = &c->sc->l2_shard;
-  c->launches++;
-  CU(fused_adam(a, c->st));
   return 0;
 }
 

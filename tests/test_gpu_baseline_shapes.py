@@ -103,41 +103,34 @@ def test_cfg3_disganmf_user_hetrec2011_steps_parity():
 
 
 def test_cfg3_disganmf_item_hetrec2011_steps_parity():
-    """DisGANMF --item, hetrec2011 split: 10 109 rows, 4 hidden layers of 1024 units, B = 256 -- the wide case.
+    """DisGANMF --item, hetrec2011 split: 10 109 rows, 4 hidden layers of 1024 units, B = 256 -- the wide case, and the
+    only committed configuration with more than 8 discriminator tensors (this test found an overflow of the fused-Adam
+    segment table that left layer_3/bias and the output layer without updates).  The raw row id (up to 10 108) is a
+    discriminator input (DisGANMF.py:110): logits are O(100..1000), the D loss O(100).
 
-    With these committed hyper-parameters the trajectory is CHAOTIC: the raw row id (up to 10 108) is a discriminator
-    input (DisGANMF.py:110), the logits are O(100..1000), the D loss is O(100), and Adam's first updates are sign-like
-    (m / sqrt(v) = +-1), so gradient elements at rounding-noise level move their weight by +-lr in a rounding-dependent
-    direction, which the id feature amplifies by 1e4.  From identical weights the D loss agrees with the fp32 oracle to
-    ~1e-6, but the G loss evaluated right after that ONE D update already differs by ~1e-2 -- for any change of summation
-    order (measured below on the split-TF32 path, whose products are fp32-accurate; the fp32 oracle itself is that far
-    from the fp64 oracle).  The contract is therefore checked per UPDATE: before every D step and before every G step the
-    device gets the oracle's current weights (zero Adam moments on both sides), each loss must agree within 1e-3, and the
-    device must be as close to the float64 oracle as the float32 oracle is (factor 3)."""
-    from ganmf_b200 import _lib as L
-    from ganmf_b200.engine import Engine
+    (1) free run on the shipping path (split-TF32 tensor-core GEMMs): losses and weights within 1e-3 of the fp32 oracle;
+    (2) the same on plain TF32 for the record: the BCE gradients of the real and the fake half cancel in the
+        weight-gradient sums, TF32 rounding drifts to ~1e-1 within ten steps -- which is why DisGANMF defaults to
+        GANMF_GEMM_TC3;
+    (3) per update (teacher forcing from the float64 oracle's weights, zero Adam moments): the device is as close to the
+        float64 oracle as the float32 oracle is, on the exact-FMA path and on the tensor-core path."""
+    shape, losses, want, got, ref = disganmf_case("DisGANMF_item_hetrec2011", "Movielenshetrec2011", True, 5, "GEMM_AUTO")
+    assert shape == (10109, 2113, 25, 256, 4, 1024)
+    check(losses, want, got, ref)
+    _, l32, _, g32, _ = disganmf_case("DisGANMF_item_hetrec2011", "Movielenshetrec2011", True, 5, "GEMM_TC")
+    print("plain TF32 on the 4x1024 net: loss rel err per step %s, worst tensor rel err %.1e" %
+          (np.array2string(np.abs(l32 - want) / np.abs(want), precision=1), max(rel_err(g32[n], ref[n]) for n in ref)))
     bp = load_quality_targets()["DisGANMF_item_hetrec2011"]["best_params"]
     urm = load_split("Movielenshetrec2011")["train"].T.tocsr()
-    n_rows, width = urm.shape
     k, B, layers, nodes = int(bp["num_factors"]), int(bp["batch_size"]), int(bp["d_layers"]), int(bp["d_nodes"])
-    assert (n_rows, width, k, B, layers, nodes) == (10109, 2113, 25, 256, 4, 1024)
-    act = bp["d_hidden_act"]
-    d_names = to.disganmf_d_names(layers)
-    for path, tol in (("GEMM_SIMT", 1e-3), ("GEMM_AUTO", 0.15)):
-        _cfg3_item_teacher_forced(path, tol, bp, urm, k, B, layers, nodes, act, d_names)
-    # free-running trajectories, for the record (not asserted at 1e-3: see the docstring)
-    for path in ("GEMM_AUTO", "GEMM_TC"):
-        _, losses, want, got, ref = disganmf_case("DisGANMF_item_hetrec2011", "Movielenshetrec2011", True, 5, path)
-        print("free run, %s: loss rel err per step %s" % (path, np.array2string(np.abs(losses - want) / np.abs(want), precision=1)))
-        assert abs(losses[0] - want[0]) <= REL * abs(want[0])      # the very first step (identical weights) agrees
+    for path in ("GEMM_SIMT", "GEMM_AUTO"):
+        _cfg3_item_teacher_forced(path, 1e-3, bp, urm, k, B, layers, nodes, bp["d_hidden_act"], to.disganmf_d_names(layers))
 
 
 def _cfg3_item_teacher_forced(path, tol, bp, urm, k, B, layers, nodes, act, d_names):
-    """path GEMM_SIMT: exact fp32 FMA GEMMs -- the update must be as close to the float64 oracle as the float32 oracle
-    is (factor 3, floor 1e-3).  path GEMM_AUTO (split-TF32 on the tensor cores, the shipping path): products are
-    fp32-accurate but the tensor core accumulates K in its own order and rounding, and here the weight gradients are
-    sums of a real and a fake half that cancel to ~1e-3 of their terms: a fraction ~1e-3 of the elements change sign,
-    which a sign-like first Adam step turns into an update error of a few percent.  Recorded, bounded at `tol`."""
+    """One D update and one G update per batch, each from the float64 oracle's current weights with zero Adam moments:
+    loss within 1e-3, update (theta_new - theta_old) as close to the float64 oracle's as the float32 oracle's is
+    (factor 3, floor `tol`)."""
     from ganmf_b200 import _lib as L
     from ganmf_b200.engine import Engine
     n_rows, width = urm.shape

@@ -158,7 +158,10 @@ def test_disganmf_cta_pairs_equal_single_ctas(monkeypatch, act):
         assert rel_err(outs[0][1][n], outs[1][1][n]) < 2e-5, n
 
 
-@pytest.mark.parametrize("act,layers,nodes", [("linear", 1, 4), ("tanh", 2, 48), ("relu", 3, 33), ("sigmoid", 2, 130)])
+# (4 and 5 layers: 10 / 12 discriminator tensors, more than one fused-Adam launch holds -- regression for an overflow of
+#  the optimiser's segment table that left the last tensors of a 4-layer net without updates)
+@pytest.mark.parametrize("act,layers,nodes", [("linear", 1, 4), ("tanh", 2, 48), ("relu", 3, 33), ("sigmoid", 2, 130),
+                                              ("tanh", 4, 24), ("linear", 5, 16)])
 def test_disganmf_steps_parity(act, layers, nodes):
     from ganmf_b200 import _lib as L
     from ganmf_b200.engine import Engine
