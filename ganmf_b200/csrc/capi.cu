@@ -78,7 +78,7 @@ struct ganmf_ctx {
   int B = 0, W = 0, Wp = 0, k = 0, kp = 0, E = 0, Ep = 0;
   int Wg = 0;                          // columns of the WHOLE training matrix (= W unless item-sharded)
   int tp_rank = 0, tp_world = 1;       // item-sharded group
-  float tp_g_alpha = 0.f;
+  float tp_g_alpha = 0.f, tp_d_alpha = 0.f;
   Mat X2, H2, H2s, Res2, dH2, dF, Pb, dPb;
   // DisGANMF: per layer activations h[l] [2B, Hp], dz [2B, Hp], out2/dout2 [2B]
   std::vector<Mat> hs, dzs;
@@ -1151,13 +1151,16 @@ int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
       e5.out = c->dH2.p; e5.ldo = c->dH2.ld; e5.row_scale2 = rs; e5.row_split = B;
       return gemm(c, c->Res2.p, c->Res2.ld, 0, Wd->w.p, Wd->w.ld, 0, 2 * B, c->E, c->W, e5);
     }
-    case 4: {                                                                      // local weight gradients + Adam
-      CU(cudaMemcpyAsync(be->g, c->dH2.row(2 * B), (size_t)be->w.ld * 4, cudaMemcpyDeviceToDevice, c->st));
-      const float alpha = adam_alpha(c, 0, lr);
+    case 4: {                          // dWd needs no summed quantity: it runs while the code gradients are all-reduced
+      const float alpha = c->tp_d_alpha = adam_alpha(c, 0, lr);
       Epilogue e4;                                                                 // G4: dWd[:, slice] -> Adam
       e4.out = Wd->w.p; e4.ldo = Wd->w.ld;
       e4.adam_m = Wd->m; e4.adam_v = Wd->v; e4.adam_alpha = alpha; e4.adam_reg = reg; e4.adam_l2 = &c->sc->l2;
-      RC(gemm(c, c->H2s.p, c->H2s.ld, 1, c->Res2.p, c->Res2.ld, 1, c->E, c->W, 2 * B, e4));
+      return gemm(c, c->H2s.p, c->H2s.ld, 1, c->Res2.p, c->Res2.ld, 1, c->E, c->W, 2 * B, e4);
+    }
+    case 5: {                                                                      // summed dH2 | dbe -> dWe, biases
+      const float alpha = c->tp_d_alpha;
+      CU(cudaMemcpyAsync(be->g, c->dH2.row(2 * B), (size_t)be->w.ld * 4, cudaMemcpyDeviceToDevice, c->st));
       Epilogue e6;                                                                 // G6: dWe[slice, :] -> Adam
       e6.out = We->w.p; e6.ldo = We->w.ld;
       e6.adam_m = We->m; e6.adam_v = We->v; e6.adam_alpha = alpha; e6.adam_reg = reg; e6.adam_l2 = &c->sc->l2;
@@ -1181,7 +1184,7 @@ int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
       return 0;
     }
     default:
-      return fail("ganmf_tp_d_phase: phase must be 1..4");
+      return fail("ganmf_tp_d_phase: phase must be 1..5");
   }
 }
 
@@ -1541,7 +1544,8 @@ int ganmf_encode(ganmf_ctx* c, const int32_t* rows, int n, float* codes_host) {
     c->launches++;
     Epilogue e;
     e.out = c->H2.p; e.ldo = c->H2.ld; e.bias = be->w.p;
-    RC(gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, b, c->E, c->W, e));
+    // API edge, not a training step: fp32-accurate products (split-TF32), like the scorer
+    RC(gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, b, c->E, c->W, e, GANMF_GEMM_TC3));
     CU(cudaMemcpy2DAsync(codes_host + (size_t)s * c->E, (size_t)c->E * 4, c->H2.p, (size_t)c->H2.ld * 4,
                          (size_t)c->E * 4, b, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));

@@ -269,8 +269,11 @@ class ItemShardedTrainer(object):
         self._phase("tp_d_phase", 2, *a)
         self._sum("step_scalars", 0, 2)
         self._phase("tp_d_phase", 3, *a)
-        self._sum("tp_dh2", 0, (2 * B + 1) * self.ld_h)
+        w = self._sum("tp_dh2", 0, (2 * B + 1) * self.ld_h, async_op=True)    # travels while dWd (+ Adam) is computed
         self._phase("tp_d_phase", 4, *a)
+        if w is not None:
+            w.wait()
+        self._phase("tp_d_phase", 5, *a)
 
     def g_step(self, ids_offset, B, lr, reg, recon_coefficient, loss_slot):
         a = (ids_offset, B, lr, reg, recon_coefficient, loss_slot)

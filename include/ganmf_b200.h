@@ -148,8 +148,9 @@ int ganmf_finalize_loss(ganmf_ctx* ctx, float reg, int loss_slot);
  * where partial sums over the item slices must be added up by the caller (NCCL all-reduce, SUM):
  *   D: phase 1 (profiles, F = Pb.V^T, partial codes)      -> sum "tp_h2"[0 : 2B*ld]
  *      phase 2 (residuals, energy sums)                    -> sum "step_scalars"[0:2]   (the hinge gate is global)
- *      phase 3 (hinge gate, dbd, partial dH and dbe)       -> sum "tp_dh2"[0 : (2B+1)*ld]  (row 2B = dbe)
- *      phase 4 (dWd, dWe with Adam in the epilogue, biases, loss log)
+ *      phase 3 (hinge gate, dbd, partial dH and dbe)       -> sum "tp_dh2"[0 : (2B+1)*ld]  (row 2B = dbe; may overlap phase 4)
+ *      phase 4 (dWd with Adam in the epilogue: needs no summed quantity)
+ *      phase 5 (dWe with Adam in the epilogue, biases, loss log)
  *   G: phase 1 (as D)                                      -> sum "tp_h2"[0 : 2B*ld]
  *      phase 2 (fake residual, feature matching, partial dHf) -> sum "tp_dh2"[B*ld : 2B*ld]
  *      phase 3 (dF, partial dPb)                           -> sum "tp_dpb"[0 : B*ld]  (may overlap phase 4)

@@ -135,9 +135,9 @@ def test_autoencoder_codes_and_factors():
     rec.fit(num_factors=8, emb_dim=24, epochs=1, batch_size=50)
     w = rec.get_weights()
     codes = rec.autoencoder_codes()                          # GANMF.py:304-307
-    want = train.toarray() @ w["autoencoder/encoding/kernel"] + w["autoencoder/encoding/bias"]
+    want = train.toarray().astype(np.float64) @ w["autoencoder/encoding/kernel"] + w["autoencoder/encoding/bias"]
     assert codes.shape == want.shape
-    assert np.max(np.abs(codes - want)) < 2e-3 * np.sqrt(np.maximum(train.getnnz(1).max(), 1))
+    assert np.max(np.abs(codes - want)) <= 1e-5 * np.max(np.abs(want))          # split-TF32: fp32-accurate
     assert np.array_equal(rec.user_factors(), w["generator/user_embeddings"])
     assert np.array_equal(rec.item_factors(), w["generator/item_embeddings"])
 

@@ -197,3 +197,29 @@ def test_cfg4_synthetic_shape_five_steps_parity():
              for b in batches]
     check(losses, want, eng.get_params(), orc.p)
     eng.close()
+
+
+def test_cfg5_item_width_two_steps_parity():
+    """BASELINE.json configs[4] width: I = 200 000, k = 250, E = 1024 (K = 200 000 split-K accumulations, 782 pair tiles
+    per row block); two D and two G steps at B = 128 against the oracle (the full B = 1024 step takes a minute per step
+    on the host; the shapes that depend on I are the same)."""
+    import bench
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    c = bench.workload("cfg5")
+    n_rows, I, k, E, B = 1024, c["items"], c["k"], c["E"], 128
+    urm = bench.synthetic_urm(n_rows, I, c["density"], 13)
+    p0 = to.init_ganmf_params(n_rows, I, k, E, seed=6)
+    hp = bench.HP
+    eng = Engine(L.KIND_GANMF, n_rows, I, k, emb_dim=E, max_batch=B)
+    eng.set_csr(L.CSR_TRAIN, urm)
+    eng.set_params(p0)
+    eng.reset_optimizers()
+    batches = pick_batches(n_rows, B, 2)[:2]
+    losses = run_engine(eng, batches, (hp["d_lr"], hp["d_reg"], hp["m"]), (hp["g_lr"], hp["g_reg"], hp["alpha"]))
+    orc = to.GanmfOracle(p0, hp["d_lr"], hp["g_lr"], dtype=np.float32)
+    want = [orc.d_step(b, to.csr_rows_to_dense(urm, b), d_reg=hp["d_reg"], m=hp["m"]) for b in batches]
+    want += [orc.g_step(b, to.csr_rows_to_dense(urm, b), g_reg=hp["g_reg"], recon_coefficient=hp["alpha"])
+             for b in batches]
+    check(losses, want, eng.get_params(), orc.p)
+    eng.close()

@@ -75,12 +75,14 @@ class NumpyTPEngine(object):
             dh = self._view("tp_dh2", 2 * B + 1, E)
             dh[:2 * B] = G @ self.p[WD].T                       # partial over items
             dh[2 * B] = self.p[WD] @ self.dbd                   # partial dbe
-        elif phase == 4:
+        elif phase == 4:                                        # (on the device: dWd + Adam(Wd), no summed input)
+            self.dWd = (self.rs * H2).T @ self.Res
+        elif phase == 5:
             dh = self._view("tp_dh2", 2 * B + 1, E)
             l2 = (self.p[WE] ** 2).sum() + (self.p[WD] ** 2).sum() + (self.p[BD] ** 2).sum()
             if self.rank == 0:
                 l2 += (self.p[BE] ** 2).sum()
-            grads = {WD: (self.rs * H2).T @ self.Res + reg * self.p[WD], WE: self.X2.T @ dh[:2 * B] + reg * self.p[WE],
+            grads = {WD: self.dWd + reg * self.p[WD], WE: self.X2.T @ dh[:2 * B] + reg * self.p[WE],
                      BE: dh[2 * B] + reg * self.p[BE], BD: self.dbd + reg * self.p[BD]}
             self.opt_d.apply(self.p, grads)
             self.losses[slot] = (self.loss_main if self.rank == 0 else 0.0) + reg * 0.5 * l2
