@@ -177,16 +177,18 @@ class ClockSampler(object):
                 "reasons": reasons, "samples": len(self.sm), "source": self.src}
 
 
-def gemm_algorithmic_bytes(c, world=1):
+def gemm_algorithmic_bytes(c, world=1, sparse_real=False):
     """Operand + output bytes (each read/written once) of the 13 tensor-core GEMMs of one D+G step pair on ONE
     rank (item-sharded: B rows of the whole minibatch, I / world items).  The dWd / dWe epilogues do not write
-    the gradient but read and write theta, m, v in place (24 B per parameter instead of 4)."""
+    the gradient but read and write theta, m, v in place (24 B per parameter instead of 4).  sparse_real: the two
+    encode GEMMs only carry the fake rows (the real codes are a CSR gather-sum)."""
     B, I, k, E = c["B"] * world, c["items"] // world, c["k"], c["E"]
     f = 4.0
     g = lambda M, N, K, extra=0: f * (M * K + N * K + M * N * (1 + extra))
     wg = 5                                        # 6 tensors moved instead of 1
-    d = g(B, I, k) + g(2 * B, E, I) + g(2 * B, I, E, 1) + g(E, I, 2 * B, wg) + g(2 * B, E, I) + g(I, E, 2 * B, wg)
-    gs = g(B, I, k) + g(2 * B, E, I) + g(B, I, E, 1) + g(B, E, I, 2) + g(B, I, E, 1) + g(I, k, B) + g(B, k, I)
+    enc = g(B, E, I) if sparse_real else g(2 * B, E, I)
+    d = g(B, I, k) + enc + g(2 * B, I, E, 1) + g(E, I, 2 * B, wg) + g(2 * B, E, I) + g(I, E, 2 * B, wg)
+    gs = g(B, I, k) + enc + g(B, I, E, 1) + g(B, E, I, 2) + g(B, I, E, 1) + g(I, k, B) + g(B, k, I)
     return d + gs
 
 
@@ -424,7 +426,9 @@ class Bench(object):
         roofline = {"kernel": "tc_gemm_kernel (tcgen05 kind::tf32, TMA, TMEM; CTA pairs cta_group::2 on the many-tile GEMMs)",
                     "bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                     "frac": achieved / pk["tf_sust"], "traffic": traffic, "traffic_source": traffic_src,
-                    "algorithmic_bytes_per_launch_mean": gemm_algorithmic_bytes(c, world) / 13.0,
+                    "algorithmic_bytes_per_launch_mean":
+                        gemm_algorithmic_bytes(c, world, eng.step_routes()["sparse_real"]) / 13.0,
+                    "routes": eng.step_routes(),
                     "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json); kind::tf32 issues at half the "
                     "bf16 rate, so frac <= 0.5 by construction", "frac_of_tf32_rate": 2 * achieved / pk["tf_sust"],
                     "achieved_excl_fused_adam_gemms": pure_flops / (pure_ms * 1e-3) / 1e12 if pure_ms > 0 else None,
@@ -436,7 +440,10 @@ class Bench(object):
                                   "(output / optimiser traffic), see profiles/r02_ncu_full_tc_gemm_cfg5.txt: 65-89 % of the "
                                   "copy peak; the others run the tensor pipe at 77-92 %",
                     "gemm_launches_per_step": gemm_launches / K, "gemm_share_of_step": gemm_ms / max(ms, 1e-9),
-                    "step_algorithmic_tflops_per_gpu": flops_per_row(c) * c["B"] * K / (ms * 1e-3) / 1e12}
+                    "step_algorithmic_tflops_per_gpu": flops_per_row(c) * c["B"] * K / (ms * 1e-3) / 1e12,
+                    "step_algorithmic_note": "SURVEY 8(d) dense count I*(8k+30E) per row; on the sparse route "
+                                             "(routes.sparse_real) 4*I*E of it per row are not executed as MMAs: the "
+                                             "real rows' codes are a CSR gather-sum (HBM-bound, see hbm_kernels)"}
         out = {"value": value, "ms": ms, "launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
                "gemm_tflops": achieved, "loss_last": [float(losses[K - 1]), float(losses[2 * K - 1])]}
         if self.args.quick:
@@ -549,7 +556,7 @@ def run_workload(c, args, torch, dist, world, rank, local_rank, with_cpu):
     line["e2e"] = tr["e2e"]
     line["eval"] = b.measure_eval(local_rank)
     if rank == 0 and not args.no_hbm_kernels:
-        line["hbm_kernels"] = hbm_kernel_rooflines(b.eng, torch, b.L, c, peaks(), b.hi - b.lo)
+        line["hbm_kernels"] = hbm_kernel_rooflines(b.eng, torch, b.L, c, peaks(), b.hi - b.lo, b.nnz / float(c["users"]))
     b.close()
     if with_cpu:
         line["cpu_baseline"] = cpu_baseline(c)
@@ -639,7 +646,7 @@ def real_config_records(epochs=4):
     return out
 
 
-def hbm_kernel_rooflines(eng, torch, L, c, pk, width_local):
+def hbm_kernel_rooflines(eng, torch, L, c, pk, width_local, nnz_per_row):
     """top-k (4*I bytes/user), fused Adam (28 B/param) and CSR gather (4*B*ld written) on their own."""
     out = {}
 
@@ -681,6 +688,17 @@ def hbm_kernel_rooflines(eng, torch, L, c, pk, width_local):
     gbs = 4.0 * B * ldw / t / 1e9
     out["csr_gather_dense_kernel"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
                                       "frac": gbs / pk["hbm"], "output_bytes": 4 * B * ldw}
+    # real-profile encode as a gather-sum: 4*E bytes of We per interaction of the batch + the codes
+    Ep = (c["E"] + 31) // 32 * 32
+    codes = torch.empty((B, Ep), device="cuda", dtype=torch.float32)
+    t = timed(lambda: L.check(eng.lib.ganmf_k_csr_encode_rows(eng.ctx, 0, B, codes.data_ptr(), Ep)), reps=20)
+    nnz_b = float(nnz_per_row) * B
+    gbs = (4.0 * Ep * nnz_b + 4.0 * B * Ep) / t / 1e9
+    out["csr_encode_rows_kernel"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                                     "frac": gbs / pk["hbm"], "ms": t * 1e3, "interactions": nnz_b,
+                                     "bytes": 4.0 * Ep * nnz_b + 4.0 * B * Ep,
+                                     "note": "mean interactions per row x B rows; weight rows that repeat inside the "
+                                             "batch or stay in L2 make the achieved figure exceed the DRAM rate"}
     return out
 
 

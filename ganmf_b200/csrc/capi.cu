@@ -137,6 +137,14 @@ struct ganmf_ctx {
   int gemm_sm_cap = 0;        // > 0: persistent GEMM grids leave SMs free (ganmf_set_gemm_sms)
   int pair_mode = 1;          // CTA-pair (cta_group::2) GEMM tiles: 0 = never, 1 = GEMMs with >= 148 tiles, 2 = whenever legal
   bool fuse_adam = true;      // ganmf_d_step / ganmf_g_step: optimiser inside the weight-gradient GEMMs
+  // sparse real-profile encode: codes of the real rows as a gather-sum over their CSR entries instead
+  // of the real half of the dense G2 product.  sparse_mode: -1 = by density (GANMF_SPARSE_REAL unset), 0 / 1 = forced
+  int sparse_mode = -1;
+  bool sparse_real = false;
+  // decoder-bias gradient from the residual GEMM's per-32-row column sums (Epilogue::colpart)
+  float* colpart = nullptr; int colpart_rows = 0;
+  bool colpart_on = true;     // GANMF_COLPART=0: always the colsum pass over the residual (A/B switch)
+  bool colpart_ok = false;    // the last GEMM that was asked for partial column sums produced them
   // lazy user-factor optimiser (kernels.cuh K6b): p_last[row] = G step the row is current at, alpha_log[t -
   // log_base] = step size of G step t+1, g_T = G steps taken, p_stale = some row may lag behind g_T
   bool lazy_p = true;
@@ -212,6 +220,7 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   }
   if (path == GANMF_GEMM_SIMT) {
     c->launches += 1;
+    if (ep.colpart) c->colpart_ok = false;              // (tensor-core epilogue only: the caller falls back to colsum)
     CU(simt_gemm(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, c->st));
     return 0;
   }
@@ -253,6 +262,10 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   // loading half of B) need 1.5x fewer bytes per flop and keep the accumulator double-buffered.
   if (c->pair_mode && g.bn == 256 && g.mt == 1 && splits == 1 && M > TC_BM && (c->pair_mode == 2 || tiles >= 148))
     g.cg = 2;
+  if (ep.colpart) {                                     // partial column sums: unsplit launches only
+    c->colpart_ok = splits == 1 && tc_lean_epilogue(ep);
+    if (!c->colpart_ok) g.ep.colpart = nullptr;
+  }
   g.splits = splits;
   g.ws = c->ws;
   g.cache = &c->tmaps;
@@ -313,6 +326,8 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   if (const char* nl = getenv("GANMF_NO_LAZY_ADAM")) c->lazy_p = !(nl[0] == '1');       // A/B switch
   if (const char* lc = getenv("GANMF_LAZY_LOG_CAP")) c->log_cap = std::max(1, atoi(lc)); // tests: force log wrap
   if (const char* ef = getenv("GANMF_EVAL_FUSED")) c->eval_fused = !(ef[0] == '0');     // A/B switch / tests
+  if (const char* sr = getenv("GANMF_SPARSE_REAL")) c->sparse_mode = atoi(sr);          // A/B switch / tests
+  if (const char* cp = getenv("GANMF_COLPART")) c->colpart_on = !(cp[0] == '0');        // A/B switch / tests
   c->B = cfg->max_batch; c->W = cfg->width; c->Wp = rup(cfg->width, 32);
   c->k = cfg->num_factors; c->kp = rup(c->k, 32);
   c->Wg = cfg->global_width > 0 ? cfg->global_width : cfg->width;
@@ -399,6 +414,8 @@ static int create_buffers(ganmf_ctx* c) {
     RC(mat_alloc(&c->H2s, 2 * B, c->E));
     RC(mat_alloc(&c->dH2, 2 * B + 1, c->E));      // + one row: partial encoder-bias gradient of an item-sharded step
     RC(mat_alloc(&c->Res2, 2 * B, c->W));
+    c->colpart_rows = (2 * B + 31) / 32;
+    RC(dalloc(&c->colpart, (size_t)c->colpart_rows * c->Wp));
   } else if (cfg->kind == GANMF_KIND_DISGANMF) {
     c->hs.resize(cfg->d_layers);
     c->dzs.resize(cfg->d_layers);
@@ -437,7 +454,7 @@ void ganmf_destroy(ganmf_ctx* c) {
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
   cudaFree(c->d_slab); cudaFree(c->p_slab); cudaFree(c->v_slab);
-  cudaFree(c->p_last); cudaFree(c->alpha_log);
+  cudaFree(c->p_last); cudaFree(c->alpha_log); cudaFree(c->colpart);
   for (Mat* m : {&c->X2, &c->H2, &c->H2s, &c->Res2, &c->dH2, &c->dF, &c->Pb, &c->dPb, &c->dhtmp, &c->Fb, &c->Ob})
     cudaFree(m->p);
   for (auto& m : c->hs) cudaFree(m.p);
@@ -517,6 +534,18 @@ int ganmf_profile_read(ganmf_ctx* c, double* ms, double* flops, int64_t* launche
 }
 
 // ------------------------------------------------------------------------------ data
+// Route of the real rows' codes.  The gather-sum reads 4*E bytes of We per interaction from HBM, the
+// dense product spends 2*E flops per matrix cell: on a B200 (~6.5 TB/s against ~650 TFLOP/s of tf32 MMAs inside the
+// step) the two meet near 0.5 % density; the sparse route is taken below half of that (cfg5: 0.1 %; cfg4 at 0.5 %
+// and the committed MovieLens / LastFM splits stay dense).
+static void note_train_csr(ganmf_ctx* c) {
+  const Csr& m = c->csr[GANMF_CSR_TRAIN];
+  const double cells = (double)m.n_rows * (double)m.n_cols;
+  const double density = cells > 0 ? (double)m.nnz / cells : 1.0;
+  c->sparse_real = c->cfg.kind == GANMF_KIND_GANMF &&
+                   (c->sparse_mode == 1 || (c->sparse_mode < 0 && density <= 0.0025));
+}
+
 int ganmf_set_csr(ganmf_ctx* c, int which, int n_rows, int n_cols, const int32_t* indptr,
                   const int32_t* indices, const float* data) {
   if (!c || which < 0 || which > 2 || !indptr) return fail("bad argument");
@@ -534,6 +563,7 @@ int ganmf_set_csr(ganmf_ctx* c, int which, int n_rows, int n_cols, const int32_t
     if (m.nnz) CU(cudaMemcpy(m.data, data, (size_t)m.nnz * 4, cudaMemcpyHostToDevice));
   }
   if (which == GANMF_CSR_TEST) c->have_tables = false;
+  if (which == GANMF_CSR_TRAIN) note_train_csr(c);
   return 0;
 }
 
@@ -557,6 +587,7 @@ int ganmf_set_csr_device(ganmf_ctx* c, int which, int n_rows, int n_cols, const 
     if (nnz) CU(cudaMemcpy(m.data, data_dev, (size_t)nnz * 4, cudaMemcpyDeviceToDevice));
   }
   if (which == GANMF_CSR_TEST) c->have_tables = false;
+  if (which == GANMF_CSR_TRAIN) note_train_csr(c);
   return 0;
 }
 
@@ -749,6 +780,42 @@ static int adam_group(ganmf_ctx* c, int first, int count, float alpha, float reg
   return 0;
 }
 
+// Codes of the stacked [real ; fake] rows, H2 = X2 . We (+ bias).  On the sparse route (note_train_csr) the real
+// rows are a gather-sum over their CSR entries -- exact fp32, 4*E bytes per interaction -- and only the fake rows go
+// through the tensor cores: the real half of G2 (2*B*I*E flops, twice per step pair) is gone.
+static int forward_codes(ganmf_ctx* c, int ids_offset, int B, const float* bias) {
+  Param* We = &c->params[0];
+  Epilogue e2;                                                                     // G2
+  e2.bias = bias;
+  if (c->sparse_real) {
+    const Csr& tr = c->csr[GANMF_CSR_TRAIN];
+    CU(csr_encode_rows(tr.indptr, tr.indices, tr.data, c->ids + ids_offset, B, We->w.p, We->w.ld, c->H2.ld, bias,
+                       c->H2.p, c->H2.ld, c->st));
+    c->launches++;
+    e2.out = c->H2.row(B); e2.ldo = c->H2.ld;
+    return gemm(c, c->X2.row(B), c->X2.ld, 0, We->w.p, We->w.ld, 1, B, c->E, c->W, e2);
+  }
+  e2.out = c->H2.p; e2.ldo = c->H2.ld;
+  return gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, 2 * B, c->E, c->W, e2);
+}
+
+// G3 asks for the per-32-row column sums of the residual when the real / fake boundary falls on a row group
+static void want_colpart(ganmf_ctx* c, Epilogue& e3, int B) {
+  c->colpart_ok = false;
+  if (c->colpart_on && c->colpart && (B & 31) == 0 && (2 * B + 31) / 32 <= c->colpart_rows) {
+    e3.colpart = c->colpart; e3.ldcp = c->Wp;
+  }
+}
+// dbd = colsum(rs (.) Res2): from G3's partial sums when they exist, else one pass over the residual
+static int decoder_bias_grad(ganmf_ctx* c, int B, const float* rs, float* out) {
+  if (c->colpart_ok)
+    colsum_parts_kernel<<<(c->W + 255) / 256, 256, 0, c->st>>>(c->colpart, 2 * B / 32, B / 32, c->W, c->Wp, rs, out);
+  else
+    colsum_kernel<<<(c->W + 31) / 32, dim3(32, 8), 0, c->st>>>(c->Res2.p, 2 * B, c->W, c->Res2.ld, rs, B, nullptr, out);
+  CU(cudaGetLastError());
+  return 0;
+}
+
 // ---- GANMF ---------------------------------------------------------------------------------
 // phase 1: profiles + generator (independent of the discriminator weights); phase 2: discriminator
 // forward on [R ; F]; phase 0: both.  A data-parallel caller runs phase 1 of the NEXT step while the
@@ -756,15 +823,14 @@ static int adam_group(ganmf_ctx* c, int first, int count, float alpha, float reg
 static int ganmf_d_forward_impl(ganmf_ctx* c, int ids_offset, int B, int phase = 0) {
   if (phase != 2) RC(forward_generator(c, ids_offset, B));
   if (phase == 1) return 0;
-  Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
+  Param *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
   CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
-  Epilogue e2;                                                                     // G2
-  e2.out = c->H2.p; e2.ldo = c->H2.ld; e2.bias = be->w.p;
-  RC(gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, 2 * B, c->E, c->W, e2));
+  RC(forward_codes(c, ids_offset, B, be->w.p));                                    // G2
   Epilogue e3;                                                                     // G3
   e3.out = c->Res2.p; e3.ldo = c->Res2.ld; e3.bias = bd->w.p;
   e3.c1 = c->X2.p; e3.ldc1 = c->X2.ld; e3.beta1 = -1.f;
   e3.sumsq2 = c->sc->sumsq; e3.row_split = B;
+  want_colpart(c, e3, B);
   return gemm(c, c->H2.p, c->H2.ld, 0, Wd->w.p, Wd->w.ld, 1, 2 * B, c->W, c->E, e3);
 }
 
@@ -785,9 +851,7 @@ static int ganmf_d_backward_impl(ganmf_ctx* c, int B, int n_global, float m_hing
   Epilogue e4;                                                                     // G4: dWd
   e4.out = Wd->g; e4.ldo = Wd->w.ld;
   RC(gemm(c, c->H2s.p, c->H2s.ld, 1, c->Res2.p, c->Res2.ld, 1, c->E, c->W, 2 * B, e4));
-  colsum_kernel<<<(c->W + 31) / 32, dim3(32, 8), 0, c->st>>>(c->Res2.p, 2 * B, c->W, c->Res2.ld, rs, B,
-                                                            nullptr, bd->g);   // dbd
-  CU(cudaGetLastError());
+  RC(decoder_bias_grad(c, B, rs, bd->g));                                          // dbd
   // dbe = colsum(dH2) = dbd . Wd^T, evaluated in fp32 from the LOCAL fp32 column sums (no tensor-core
   // rounding); it belongs to phase 1 because a data-parallel caller sums dbd in place right after it
   rowdot_kernel<<<c->E, 256, 0, c->st>>>(Wd->w.p, c->E, c->W, Wd->w.ld, bd->g, be->g);
@@ -823,9 +887,7 @@ static int ganmf_d_backward_apply_fused(ganmf_ctx* c, int B, int n_global, float
   scale_rows_kernel<<<dim3(std::max(1, c->H2.ld / 4 / 128), 2 * B), 128, 0, c->st>>>(
       c->H2.p, c->H2s.p, c->H2.ld / 4, rs, B);
   CU(cudaGetLastError());
-  colsum_kernel<<<(c->W + 31) / 32, dim3(32, 8), 0, c->st>>>(c->Res2.p, 2 * B, c->W, c->Res2.ld, rs, B,
-                                                            nullptr, bd->g);   // dbd
-  CU(cudaGetLastError());
+  RC(decoder_bias_grad(c, B, rs, bd->g));                                          // dbd
   rowdot_kernel<<<c->E, 256, 0, c->st>>>(Wd->w.p, c->E, c->W, Wd->w.ld, bd->g, be->g);   // dbe = dbd . Wd^T
   CU(cudaGetLastError());
   c->launches += 4;
@@ -883,9 +945,7 @@ static int ganmf_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, fl
   Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
   Param& V = c->params[c->n_d + 1];
   CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
-  Epilogue e2;                                                                     // G2 (real + fake codes)
-  e2.out = c->H2.p; e2.ldo = c->H2.ld; e2.bias = be->w.p;
-  RC(gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, 2 * B, c->E, c->W, e2));
+  RC(forward_codes(c, ids_offset, B, be->w.p));                                    // G2 (real + fake codes)
   Epilogue e3;                                                                     // G3': fake residual
   e3.out = c->Res2.row(B); e3.ldo = c->Res2.ld; e3.bias = bd->w.p;
   e3.c1 = c->X2.row(B); e3.ldc1 = c->X2.ld; e3.beta1 = -1.f;
@@ -1112,11 +1172,9 @@ static int tp_check(ganmf_ctx* c, int ids_offset, int B) {
 // profiles + generator + partial codes (the bias joins the sum once: on rank 0)
 static int tp_forward_codes(ganmf_ctx* c, int ids_offset, int B) {
   RC(forward_generator(c, ids_offset, B));
-  Param *We = &c->params[0], *be = &c->params[1];
+  Param* be = &c->params[1];
   CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
-  Epilogue e2;                                                                     // G2 (partial over items)
-  e2.out = c->H2.p; e2.ldo = c->H2.ld; e2.bias = c->tp_rank == 0 ? be->w.p : nullptr;
-  return gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, 2 * B, c->E, c->W, e2);
+  return forward_codes(c, ids_offset, B, c->tp_rank == 0 ? be->w.p : nullptr);     // G2 (partial over items)
 }
 
 int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, float reg, float m_hinge,
@@ -1133,6 +1191,7 @@ int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
       e3.out = c->Res2.p; e3.ldo = c->Res2.ld; e3.bias = bd->w.p;
       e3.c1 = c->X2.p; e3.ldc1 = c->X2.ld; e3.beta1 = -1.f;
       e3.sumsq2 = c->sc->sumsq; e3.row_split = B;
+      want_colpart(c, e3, B);
       return gemm(c, c->H2.p, c->H2.ld, 0, Wd->w.p, Wd->w.ld, 1, 2 * B, c->W, c->E, e3);
     }
     case 3: {                                                                      // gate (global sums), dbd, partial dH | dbe
@@ -1141,9 +1200,7 @@ int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
       scale_rows_kernel<<<dim3(std::max(1, c->H2.ld / 4 / 128), 2 * B), 128, 0, c->st>>>(
           c->H2.p, c->H2s.p, c->H2.ld / 4, rs, B);
       CU(cudaGetLastError());
-      colsum_kernel<<<(c->W + 31) / 32, dim3(32, 8), 0, c->st>>>(c->Res2.p, 2 * B, c->W, c->Res2.ld, rs, B,
-                                                                nullptr, bd->g);
-      CU(cudaGetLastError());
+      RC(decoder_bias_grad(c, B, rs, bd->g));
       rowdot_kernel<<<c->E, 256, 0, c->st>>>(Wd->w.p, c->E, c->W, Wd->w.ld, bd->g, c->dH2.row(2 * B));
       CU(cudaGetLastError());
       c->launches += 4;
@@ -1540,12 +1597,10 @@ int ganmf_encode(ganmf_ctx* c, const int32_t* rows, int n, float* codes_host) {
   for (int s = 0; s < n; s += c->B) {
     const int b = std::min(c->B, n - s);
     CU(cudaMemcpyAsync(c->ids, rows + s, (size_t)b * 4, cudaMemcpyHostToDevice, c->st));
-    CU(csr_gather_dense(tr.indptr, tr.indices, tr.data, c->ids, b, c->X2.p, c->X2.ld, 0, c->st));
+    // API edge: exact fp32 gather-sum over the rows' interactions (no dense profile tile, no tensor-core rounding)
+    CU(csr_encode_rows(tr.indptr, tr.indices, tr.data, c->ids, b, We->w.p, We->w.ld, c->H2.ld, be->w.p, c->H2.p,
+                       c->H2.ld, c->st));
     c->launches++;
-    Epilogue e;
-    e.out = c->H2.p; e.ldo = c->H2.ld; e.bias = be->w.p;
-    // API edge, not a training step: fp32-accurate products (split-TF32), like the scorer
-    RC(gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, b, c->E, c->W, e, GANMF_GEMM_TC3));
     CU(cudaMemcpy2DAsync(codes_host + (size_t)s * c->E, (size_t)c->E * 4, c->H2.p, (size_t)c->H2.ld * 4,
                          (size_t)c->E * 4, b, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
@@ -2189,6 +2244,25 @@ int ganmf_k_csr_gather_dense(ganmf_ctx* c, int ids_offset, int B, float* out, in
   if (ld < c->W || (ld & 3)) return fail("ld must be >= width and a multiple of 4");
   c->launches++;
   CU(csr_gather_dense(tr.indptr, tr.indices, tr.data, c->ids + ids_offset, B, out, ld, 0, c->st));
+  return 0;
+}
+int ganmf_k_csr_encode_rows(ganmf_ctx* c, int ids_offset, int B, float* out, int ldo) {
+  if (!c) return fail("null ctx");
+  if (c->cfg.kind != GANMF_KIND_GANMF) return fail("csr_encode_rows: GANMF only");
+  const Csr& tr = c->csr[GANMF_CSR_TRAIN];
+  if (!tr.indptr) return fail("train CSR not set");
+  if (ldo < c->Ep || (ldo & 3)) return fail("ldo must be >= roundup(emb_dim, 32) and a multiple of 4");
+  if (B <= 0 || ids_offset < 0 || ids_offset + B > c->ids_cap) return fail("ids range out of bounds");
+  const Param *We = &c->params[0], *be = &c->params[1];
+  c->launches++;
+  CU(csr_encode_rows(tr.indptr, tr.indices, tr.data, c->ids + ids_offset, B, We->w.p, We->w.ld, c->Ep, be->w.p, out,
+                     ldo, c->st));
+  return 0;
+}
+int ganmf_step_routes(ganmf_ctx* c, int32_t* sparse_real, int32_t* bias_grad_from_gemm) {
+  if (!c) return fail("null ctx");
+  if (sparse_real) *sparse_real = c->sparse_real ? 1 : 0;
+  if (bias_grad_from_gemm) *bias_grad_from_gemm = (c->colpart_on && c->colpart) ? 1 : 0;
   return 0;
 }
 int ganmf_k_adam(ganmf_ctx* c, float* theta, float* m, float* v, const float* g, int64_t n, float alpha,

@@ -63,6 +63,73 @@ inline cudaError_t csr_gather_dense(const int* indptr, const int* indices, const
   return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------- K1b
+// Sparse real-profile encode: out[b, :] = bias + sum_{j in CSR row ids[b]} data[j] * W[indices[j], :], i.e. the real
+// half of H = X . We + be (GANMF.py:64) as a gather-sum over the row's interactions instead of a dense
+// [B, I] x [I, E] product: at 0.1 % density a row touches 200 of the 200 000 rows of We (800 KB read against
+// 0.41 GFLOP of dense MMA work).  Exact fp32 FMAs in CSR order (deterministic).  grid = (column chunks, B); one
+// thread owns 4 consecutive columns; the row's (index, value) pairs are staged through shared memory and the
+// weight rows are fetched eight at a time (independent 16-byte loads in flight).  HBM-bound:
+// algorithmic bytes = 4 * E * nnz(batch) read + 4 * B * E written.
+constexpr int ENC_THREADS = 256, ENC_UNROLL = 8;
+__global__ void __launch_bounds__(ENC_THREADS)
+csr_encode_rows_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ data,
+                       const int* __restrict__ row_ids, const float* __restrict__ W, int ldw, int E4,
+                       const float* __restrict__ bias, float* __restrict__ out, int ldo) {
+  __shared__ int s_idx[ENC_THREADS];
+  __shared__ float s_val[ENC_THREADS];
+  const int b = blockIdx.y;
+  const int c4 = blockIdx.x * ENC_THREADS + threadIdx.x;
+  const bool live = c4 < E4;
+  const int r = row_ids ? row_ids[b] : b;
+  const int s = indptr[r], e = indptr[r + 1];
+  const float4* w4 = reinterpret_cast<const float4*>(W) + (live ? c4 : 0);
+  const size_t ldw4 = (size_t)(ldw >> 2);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias && live) acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+  for (int base = s; base < e; base += ENC_THREADS) {
+    const int cnt = min(ENC_THREADS, e - base);
+    __syncthreads();                                   // the previous batch of pairs has been consumed
+    if ((int)threadIdx.x < cnt) {
+      s_idx[threadIdx.x] = indices[base + threadIdx.x];
+      s_val[threadIdx.x] = data ? data[base + threadIdx.x] : 1.0f;
+    }
+    __syncthreads();
+    if (!live) continue;
+    int j = 0;
+    for (; j + ENC_UNROLL <= cnt; j += ENC_UNROLL) {
+      float4 w[ENC_UNROLL];
+#pragma unroll
+      for (int u = 0; u < ENC_UNROLL; ++u) w[u] = __ldg(w4 + (size_t)s_idx[j + u] * ldw4);
+#pragma unroll
+      for (int u = 0; u < ENC_UNROLL; ++u) {
+        const float v = s_val[j + u];
+        acc.x = fmaf(v, w[u].x, acc.x); acc.y = fmaf(v, w[u].y, acc.y);
+        acc.z = fmaf(v, w[u].z, acc.z); acc.w = fmaf(v, w[u].w, acc.w);
+      }
+    }
+    for (; j < cnt; ++j) {
+      const float4 w = __ldg(w4 + (size_t)s_idx[j] * ldw4);
+      const float v = s_val[j];
+      acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y);
+      acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
+    }
+  }
+  if (live) *(reinterpret_cast<float4*>(out + (size_t)b * ldo) + c4) = acc;
+}
+
+// W: [items][ldw] (ldw and ldo multiples of 4, 16-byte aligned bases); E_pad = columns to produce (multiple of 4;
+// padding columns of W and bias are zero, so the padding of out stays zero)
+inline cudaError_t csr_encode_rows(const int* indptr, const int* indices, const float* data, const int* row_ids,
+                                   int B, const float* W, int ldw, int E_pad, const float* bias, float* out, int ldo,
+                                   cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  const int E4 = E_pad >> 2;
+  csr_encode_rows_kernel<<<dim3((E4 + ENC_THREADS - 1) / ENC_THREADS, B), ENC_THREADS, 0, st>>>(
+      indptr, indices, data, row_ids, W, ldw, E4, bias, out, ldo);
+  return cudaGetLastError();
+}
+
 // out[b, :] = src[ids[b], :]   (ld multiple of 4)
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ ids,
                                    float* __restrict__ out, int ld) {
@@ -333,6 +400,21 @@ __global__ void colsum_kernel(const float* __restrict__ X, int M, int N, int ld,
     for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
     out[n] = t;
   }
+}
+
+// The same weighted column sums from the per-32-row partial sums a GEMM epilogue left behind
+// (Epilogue::colpart: part[p][n] = sum of out[32p .. 32p+31][n]): out[n] = rs[0] * sum_{p < split_part} part[p][n] +
+// rs[1] * sum_{p >= split_part} part[p][n].  Reads M/32 rows instead of M (the decoder-bias gradient no longer
+// costs a pass over the [2B, I] residual); fixed summation order.
+__global__ void __launch_bounds__(256)
+colsum_parts_kernel(const float* __restrict__ part, int nparts, int split_part, int N, int ld,
+                    const float* __restrict__ row_scale2, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (int p = 0; p < split_part && p < nparts; ++p) s0 += part[(size_t)p * ld + n];
+  for (int p = split_part; p < nparts; ++p) s1 += part[(size_t)p * ld + n];
+  out[n] = row_scale2[0] * s0 + row_scale2[1] * s1;
 }
 
 // out[e] = sum_i W[e, i] * x[i]   (fp32; ld multiple of 4).

@@ -50,6 +50,7 @@ __device__ __forceinline__ float act_fwd(int act, float z) {
 //           the hinge-gate coefficients are only known on the device)
 //   out[m,n] = round_out ? rna_tf32(v) : v
 //   sumsq2[m >= row_split] += v*v                            (energy loss, fp64)
+//   colpart[m / 32][n]     = sum of v over the 32-row group   (bias gradients without another pass)
 struct Epilogue {
   float* out = nullptr;
   int ldo = 0;
@@ -65,6 +66,12 @@ struct Epilogue {
   float beta2 = 0.f;
   int round_out = 0;
   double* sumsq2 = nullptr;
+  // per-32-row column sums of the stored values: colpart[(m >> 5) * ldcp + n] = sum of out[m & ~31 .. +31][n]
+  // (rows >= M count as zero).  Only unsplit launches of the lean tensor-core kernel honour it (the caller checks,
+  // tc_lean_epilogue()); the decoder-bias
+  // gradient is then a weighted sum of M/32 partial rows instead of a pass over the whole residual.
+  float* colpart = nullptr;
+  int ldcp = 0;
   const float* r1_row = nullptr;
   const float* r1_col = nullptr;
   int act = ACT_LINEAR;
@@ -521,6 +528,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               continue;
             }
             const bool more = j + 1 < NCH;
+            float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int itr = 0; itr < 8; ++itr) {
               const int row = itr * 4 + sub_r;
@@ -545,10 +553,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (use_c1 && more) load_c1(j + 1, itr);         // next chunk's row group, a whole chunk ahead
               const float sq = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
               if (lower) sq1 += sq; else sq0 += sq;
+              if (LEAN) { cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w; }
+            }
+            if (LEAN && ep.colpart) {
+              // this lane summed rows sub_r, sub_r + 4, ...; the four row phases meet through two shuffles
+#pragma unroll
+              for (int sh = 8; sh <= 16; sh <<= 1) {
+                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, sh); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, sh);
+                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, sh); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, sh);
+              }
+              if (sub_r == 0) *reinterpret_cast<float4*>(ep.colpart + (size_t)(mw >> 5) * ep.ldcp + n) = cs;
             }
           }
         } else {
           // ---- generic path: boundary tiles / unaligned views / rank-1 term
+          float cs[4] = {0.f, 0.f, 0.f, 0.f};
           for (int itr = 0; itr < 8; ++itr) {
             const int row = itr * 4 + sub_r;
             const int m = mw + row;
@@ -562,9 +581,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             const float rs = m >= ep.row_split ? rs1 : rs0;
             float sq = 0.f;
-            for (int e = 0; e < 4 && n + e < args.N; ++e)
-              sq += finish_element(ep, apply_epilogue(ep, v[e], m, n + e, rs), m, n + e);
+            for (int e = 0; e < 4 && n + e < args.N; ++e) {
+              const float x = apply_epilogue(ep, v[e], m, n + e, rs);
+              if (LEAN) cs[e] += x;
+              sq += finish_element(ep, x, m, n + e);
+            }
             if (ep.adam_m || m < ep.row_split) sq0 += sq; else sq1 += sq;
+          }
+          if (LEAN && !partial && ep.colpart) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+            }
+            if (sub_r == 0)
+              for (int e = 0; e < 4 && n + e < args.N; ++e) ep.colpart[(size_t)(mw >> 5) * ep.ldcp + n + e] = cs[e];
           }
         }
         __syncwarp();                               // slab is reused by the next chunk
@@ -811,6 +842,9 @@ inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const
   return cudaGetLastError();
 }
 
+// EPI = 1 kernels serve every epilogue without the fused optimiser, an activation or tf32 rounding of the output
+inline bool tc_lean_epilogue(const Epilogue& ep) { return !ep.adam_m && ep.act == ACT_LINEAR && !ep.round_out; }
+
 // Returns cudaSuccess or an error; never falls back to another implementation.
 inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   if (c.M <= 0 || c.N <= 0 || c.K <= 0) return cudaErrorInvalidValue;
@@ -867,7 +901,7 @@ inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   args.ep = c.ep;
 
   cudaError_t e;
-  const bool lean = !c.ep.adam_m && c.ep.act == ACT_LINEAR && !c.ep.round_out;
+  const bool lean = tc_lean_epilogue(c.ep);
 #define TC_LAUNCH(BN_, ST_, MT_, CG_)                                                            \
   (lean ? tc_gemm_launch_t<BN_, ST_, MT_, CG_, 1>(c, args, ma, mb, splits, stream)               \
         : tc_gemm_launch_t<BN_, ST_, MT_, CG_, 0>(c, args, ma, mb, splits, stream))

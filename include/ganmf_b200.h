@@ -238,11 +238,21 @@ int ganmf_metrics_from_topk(ganmf_ctx* ctx, const int32_t* topk_idx_host, int K,
                             int n_cutoffs, double* per_user_host /* [n][n_cut][NCOL] nullable */,
                             double* sums_host, int64_t* item_counts_host);
 
+/* Which routes the training step of this context takes (decided when the train CSR is set; GANRec/GANMF.py:62-70,
+ * 184-187 is one dense graph): *sparse_real = 1 when the codes of the real rows are the CSR gather-sum instead of
+ * the real half of the dense encode GEMM (density <= 0.25 %, or GANMF_SPARSE_REAL=1); *bias_grad_from_gemm = 1 when
+ * the decoder-bias gradient is formed from the residual GEMM's per-32-row column sums (GANMF_COLPART != 0). */
+int ganmf_step_routes(ganmf_ctx* ctx, int32_t* sparse_real, int32_t* bias_grad_from_gemm);
+
 /* ---- primitive kernels (unit tests, ncu) ------------------------------------------------- */
 /* All pointers are DEVICE pointers here. */
 int ganmf_k_gemm(ganmf_ctx* ctx, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn,
                  int M, int N, int K, float* out, int ldo, int path);
 int ganmf_k_csr_gather_dense(ganmf_ctx* ctx, int ids_offset, int B, float* out, int ld);
+/* Sparse real-profile encode on its own: out[b, :] = be + sum over the interactions j of training row
+ * ids[ids_offset + b] of data[j] * We[indices[j], :] -- `real_histories . W_enc + b_enc` of GANRec/GANMF.py:64 without
+ * the dense tile of GANMF.py:184.  out: [B][ldo] device floats, ldo >= roundup(emb_dim, 32). */
+int ganmf_k_csr_encode_rows(ganmf_ctx* ctx, int ids_offset, int B, float* out, int ldo);
 int ganmf_k_adam(ganmf_ctx* ctx, float* theta, float* m, float* v, const float* g, int64_t n,
                  float alpha, float reg);
 int ganmf_k_topk(ganmf_ctx* ctx, const float* scores, int ld, int n, int n_items, int K,

@@ -24,10 +24,12 @@ def rel_err(a, b):
                  max(np.linalg.norm(b.astype(np.float64)), 1e-30))
 
 
-def run_ganmf(n_rows, width, k, E, B, epochs, hp, gemm_path, density=0.05, seed=0):
+def run_ganmf(n_rows, width, k, E, B, epochs, hp, gemm_path, density=0.05, seed=0, explicit=False):
     from ganmf_b200 import _lib as L
     from ganmf_b200.engine import Engine
     urm = make_urm(n_rows, width, density, seed)
+    if explicit:                                        # ratings 1..5 instead of implicit ones
+        urm.data[:] = np.random.RandomState(seed + 3).randint(1, 6, size=urm.nnz).astype(np.float32)
     p0 = to.init_ganmf_params(n_rows, width, k, E, seed=seed + 1)
     rs = np.random.RandomState(seed + 2)
     p0["autoencoder/encoding/bias"] = (rs.standard_normal(E) * 0.01).astype(np.float32)
@@ -80,6 +82,57 @@ def test_ganmf_steps_parity_on_cta_pairs(monkeypatch, hp):
     monkeypatch.setenv("GANMF_PAIR", "2")
     dl, gl, odl, ogl, got, want = run_ganmf(600, 517, 24, 300, 160, 8, hp, L.GEMM_TC)
     assert len(dl) == 32 and len(gl) == 32
+    np.testing.assert_allclose(dl, odl, rtol=REL)
+    np.testing.assert_allclose(gl, ogl, rtol=REL)
+    for n in want:
+        assert rel_err(got[n], want[n]) <= REL, (n, rel_err(got[n], want[n]))
+
+
+@pytest.mark.parametrize("pair", ["1", "2"])
+@pytest.mark.parametrize("hp,explicit", [(HP, False), (dict(HP, m=0.05, alpha=0.3), True)])   # gate open / closed
+def test_ganmf_steps_parity_sparse_real_route(monkeypatch, pair, hp, explicit):
+    """GANMF_SPARSE_REAL=1 forces the codes of the real rows through the CSR gather-sum
+    (csr_encode_rows_kernel, exact fp32) and only the fake rows through the tensor cores -- the route the engine
+    takes by itself below 0.25 % density (cfg5).  Same contract as the dense route; ratings other than 1 exercise
+    the value column of the CSR; 44-row last batch = ragged fake-half GEMM."""
+    from ganmf_b200 import _lib as L
+    monkeypatch.setenv("GANMF_SPARSE_REAL", "1")
+    monkeypatch.setenv("GANMF_PAIR", pair)
+    dl, gl, odl, ogl, got, want = run_ganmf(600, 517, 24, 300, 160, 8, hp, L.GEMM_TC, explicit=explicit)
+    assert len(dl) == 32 and len(gl) == 32
+    np.testing.assert_allclose(dl, odl, rtol=REL)
+    np.testing.assert_allclose(gl, ogl, rtol=REL)
+    for n in want:
+        assert rel_err(got[n], want[n]) <= REL, (n, rel_err(got[n], want[n]))
+
+
+def test_ganmf_sparse_route_is_chosen_by_density_and_matches_dense(monkeypatch):
+    """At 0.2 % density the engine takes the sparse route by itself: fewer tensor-core flops are launched than with
+    GANMF_SPARSE_REAL=0, and both runs stay within the oracle tolerance of each other."""
+    from ganmf_b200 import _lib as L
+    res = {}
+    for mode in ("auto", "0"):
+        if mode == "auto":
+            monkeypatch.delenv("GANMF_SPARSE_REAL", raising=False)
+        else:
+            monkeypatch.setenv("GANMF_SPARSE_REAL", mode)
+        res[mode] = run_ganmf(512, 4096, 24, 64, 128, 2, HP, L.GEMM_TC, density=0.002)
+    for mode in res:
+        dl, gl, odl, ogl, got, want = res[mode]
+        np.testing.assert_allclose(dl, odl, rtol=REL)
+        np.testing.assert_allclose(gl, ogl, rtol=REL)
+        for n in want:
+            assert rel_err(got[n], want[n]) <= REL, (mode, n, rel_err(got[n], want[n]))
+    # the two routes differ in rounding (exact fp32 vs TF32 on the real codes), so they are not bit-identical
+    assert any(not np.array_equal(res["auto"][4][n], res["0"][4][n]) for n in res["0"][4])
+
+
+def test_ganmf_decoder_bias_grad_from_the_colsum_pass(monkeypatch):
+    """GANMF_COLPART=0: dbd from the pass over the residual instead of the residual GEMM's per-32-row column sums
+    (the default whenever the real / fake boundary falls on a 32-row group, i.e. in every other test here)."""
+    from ganmf_b200 import _lib as L
+    monkeypatch.setenv("GANMF_COLPART", "0")
+    dl, gl, odl, ogl, got, want = run_ganmf(600, 517, 24, 300, 160, 4, HP, L.GEMM_TC)
     np.testing.assert_allclose(dl, odl, rtol=REL)
     np.testing.assert_allclose(gl, ogl, rtol=REL)
     for n in want:
