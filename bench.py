@@ -177,19 +177,28 @@ class ClockSampler(object):
                 "reasons": reasons, "samples": len(self.sm), "source": self.src}
 
 
-def gemm_algorithmic_bytes(c, world=1, sparse_real=False):
-    """Operand + output bytes (each read/written once) of the 13 tensor-core GEMMs of one D+G step pair on ONE
-    rank (item-sharded: B rows of the whole minibatch, I / world items).  The dWd / dWe epilogues do not write
-    the gradient but read and write theta, m, v in place (24 B per parameter instead of 4).  sparse_real: the two
-    encode GEMMs only carry the fake rows (the real codes are a CSR gather-sum)."""
+def gemm_algorithmic_bytes(c, world=1, routes=None):
+    """(bytes, launches): operand + output bytes (each read/written once) of the tensor-core GEMMs of one D+G step
+    pair on ONE rank (item-sharded: B rows of the whole minibatch, I / world items).  The dWd / dWe epilogues do not
+    write the gradient but read and write theta, m, v in place (24 B per parameter instead of 4).  routes
+    (Engine.step_routes): sparse_real -- the real rows' codes are a CSR gather-sum, not a GEMM; lowrank_fake -- the fake
+    rows' codes and the generator gradients go through the [k, E] matrices V^T.We / Pb^T.dHf (csrc/capi.cu)."""
+    routes = routes or {}
     B, I, k, E = c["B"] * world, c["items"] // world, c["k"], c["E"]
     f = 4.0
     g = lambda M, N, K, extra=0: f * (M * K + N * K + M * N * (1 + extra))
     wg = 5                                        # 6 tensors moved instead of 1
-    enc = g(B, E, I) if sparse_real else g(2 * B, E, I)
-    d = g(B, I, k) + enc + g(2 * B, I, E, 1) + g(E, I, 2 * B, wg) + g(2 * B, E, I) + g(I, E, 2 * B, wg)
-    gs = g(B, I, k) + enc + g(B, I, E, 1) + g(B, E, I, 2) + g(B, I, E, 1) + g(I, k, B) + g(B, k, I)
-    return d + gs
+    enc_rows = (0 if routes.get("sparse_real") else B) + (0 if routes.get("lowrank_fake") else B)
+    enc = [g(enc_rows, E, I)] if enc_rows else []
+    if routes.get("lowrank_fake"):
+        enc += [g(k, E, I), g(B, E, k)]           # M1 = V^T.We, Hf = Pb.M1
+    d = [g(B, I, k)] + enc + [g(2 * B, I, E, 1), g(E, I, 2 * B, wg), g(2 * B, E, I), g(I, E, 2 * B, wg)]
+    gs = [g(B, I, k)] + enc + [g(B, I, E, 1), g(B, E, I, 2)]
+    if routes.get("lowrank_fake"):
+        gs += [g(B, k, I), g(B, k, E, 1), g(k, E, B), g(I, k, B), g(I, k, E, 1)]
+    else:
+        gs += [g(B, I, E, 1), g(I, k, B), g(B, k, I)]
+    return sum(d) + sum(gs), len(d) + len(gs)
 
 
 def use_all_host_threads():
@@ -423,17 +432,17 @@ class Bench(object):
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["dram_bytes_per_launch_mean"], os.path.relpath(tpath, ROOT) + ": " + tj["note"]
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        alg_bytes, alg_launches = gemm_algorithmic_bytes(c, world, eng.step_routes())
         roofline = {"kernel": "tc_gemm_kernel (tcgen05 kind::tf32, TMA, TMEM; CTA pairs cta_group::2 on the many-tile GEMMs)",
                     "bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                     "frac": achieved / pk["tf_sust"], "traffic": traffic, "traffic_source": traffic_src,
-                    "algorithmic_bytes_per_launch_mean":
-                        gemm_algorithmic_bytes(c, world, eng.step_routes()["sparse_real"]) / 13.0,
+                    "algorithmic_bytes_per_launch_mean": alg_bytes / alg_launches,
                     "routes": eng.step_routes(),
                     "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json); kind::tf32 issues at half the "
                     "bf16 rate, so frac <= 0.5 by construction", "frac_of_tf32_rate": 2 * achieved / pk["tf_sust"],
                     "achieved_excl_fused_adam_gemms": pure_flops / (pure_ms * 1e-3) / 1e12 if pure_ms > 0 else None,
                     "note": "the dWd/dWe GEMM epilogues also run TF-Adam on Wd/We in place (24 B/param of HBM "
-                            "traffic inside those 2 of the 13 launches), which lowers their FLOP rate but removes the "
+                            "traffic inside those 2 launches), which lowers their FLOP rate but removes the "
                             "separate optimiser pass", "rank": 0,
                     "gemms": gemm_table,
                     "gemms_note": "k = 250 GEMMs (N or K = 250) and the two Adam-fused weight-gradient GEMMs are HBM-bound "
@@ -441,9 +450,11 @@ class Bench(object):
                                   "copy peak; the others run the tensor pipe at 77-92 %",
                     "gemm_launches_per_step": gemm_launches / K, "gemm_share_of_step": gemm_ms / max(ms, 1e-9),
                     "step_algorithmic_tflops_per_gpu": flops_per_row(c) * c["B"] * K / (ms * 1e-3) / 1e12,
-                    "step_algorithmic_note": "SURVEY 8(d) dense count I*(8k+30E) per row; on the sparse route "
-                                             "(routes.sparse_real) 4*I*E of it per row are not executed as MMAs: the "
-                                             "real rows' codes are a CSR gather-sum (HBM-bound, see hbm_kernels)"}
+                    "step_algorithmic_note": "SURVEY 8(d) dense count I*(8k+30E) per row, i.e. the reference graph's "
+                                             "flops; the step executes fewer: routes.sparse_real replaces 4*I*E per row "
+                                             "by a CSR gather-sum (HBM-bound, see hbm_kernels), routes.lowrank_fake "
+                                             "contracts the rank-k fake profiles through [k, E] matrices (the "
+                                             "roofline's `achieved` counts executed MMA flops only)"}
         out = {"value": value, "ms": ms, "launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
                "gemm_tflops": achieved, "loss_last": [float(losses[K - 1]), float(losses[2 * K - 1])]}
         if self.args.quick:

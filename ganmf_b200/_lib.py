@@ -90,7 +90,7 @@ SIGNATURES = {
                                C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "ganmf_k_csr_gather_dense": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "ganmf_k_csr_encode_rows": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int]),
-    "ganmf_step_routes": (C.c_int, [_ctx, _i32p, _i32p]),
+    "ganmf_step_routes": (C.c_int, [_ctx, _i32p, _i32p, _i32p]),
     "ganmf_k_adam": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
                                C.c_float]),
     "ganmf_k_topk": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

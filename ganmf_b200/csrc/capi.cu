@@ -141,6 +141,18 @@ struct ganmf_ctx {
   // of the real half of the dense G2 product.  sparse_mode: -1 = by density (GANMF_SPARSE_REAL unset), 0 / 1 = forced
   int sparse_mode = -1;
   bool sparse_real = false;
+  // low-rank generator route: the fake profiles F = Pb . V^T have rank k, so every product that contracts F (or a
+  // gradient flowing back into it) over the items can go through a [k, E] matrix instead of a [B, I] one:
+  //   codes      Hf  = F . We            = Pb . (V^T . We)                        = Pb . M1
+  //   dPb        = dF . V                = dHf . M1^T - c1 * (Res_f . V)
+  //   dV         = dF^T . Pb             = We . (dHf^T . Pb) - c1 * (Res_f^T . Pb)
+  // (dF = dHf . We^T - c1 * Res_f is never formed).  2*k*I*E flops for M1 replace 2*B*I*E for the fake codes, and the
+  // [B, I] x [I, E] product behind dF disappears: worth it when k is well below the minibatch rows (always for the
+  // item-sharded step, whose minibatch is N * 1024 rows).  lowrank_mode: -1 = by shape (2k <= max_batch), 0 / 1 forced
+  // (GANMF_LOWRANK).
+  int lowrank_mode = -1;
+  bool lowrank = false;
+  Mat M1, T1t;                // V^T . We  [k, E];  Pb^T . dHf  [k, E]
   // decoder-bias gradient from the residual GEMM's per-32-row column sums (Epilogue::colpart)
   float* colpart = nullptr; int colpart_rows = 0;
   bool colpart_on = true;     // GANMF_COLPART=0: always the colsum pass over the residual (A/B switch)
@@ -328,6 +340,7 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   if (const char* ef = getenv("GANMF_EVAL_FUSED")) c->eval_fused = !(ef[0] == '0');     // A/B switch / tests
   if (const char* sr = getenv("GANMF_SPARSE_REAL")) c->sparse_mode = atoi(sr);          // A/B switch / tests
   if (const char* cp = getenv("GANMF_COLPART")) c->colpart_on = !(cp[0] == '0');        // A/B switch / tests
+  if (const char* lr = getenv("GANMF_LOWRANK")) c->lowrank_mode = atoi(lr);             // A/B switch / tests
   c->B = cfg->max_batch; c->W = cfg->width; c->Wp = rup(cfg->width, 32);
   c->k = cfg->num_factors; c->kp = rup(c->k, 32);
   c->Wg = cfg->global_width > 0 ? cfg->global_width : cfg->width;
@@ -416,6 +429,9 @@ static int create_buffers(ganmf_ctx* c) {
     RC(mat_alloc(&c->Res2, 2 * B, c->W));
     c->colpart_rows = (2 * B + 31) / 32;
     RC(dalloc(&c->colpart, (size_t)c->colpart_rows * c->Wp));
+    c->lowrank = c->lowrank_mode == 1 || (c->lowrank_mode < 0 && 2 * c->k <= B);
+    RC(mat_alloc(&c->M1, c->k, c->E));
+    RC(mat_alloc(&c->T1t, c->k, c->E));
   } else if (cfg->kind == GANMF_KIND_DISGANMF) {
     c->hs.resize(cfg->d_layers);
     c->dzs.resize(cfg->d_layers);
@@ -455,7 +471,8 @@ void ganmf_destroy(ganmf_ctx* c) {
   cudaDeviceSynchronize();
   cudaFree(c->d_slab); cudaFree(c->p_slab); cudaFree(c->v_slab);
   cudaFree(c->p_last); cudaFree(c->alpha_log); cudaFree(c->colpart);
-  for (Mat* m : {&c->X2, &c->H2, &c->H2s, &c->Res2, &c->dH2, &c->dF, &c->Pb, &c->dPb, &c->dhtmp, &c->Fb, &c->Ob})
+  for (Mat* m : {&c->X2, &c->H2, &c->H2s, &c->Res2, &c->dH2, &c->dF, &c->Pb, &c->dPb, &c->dhtmp, &c->Fb, &c->Ob, &c->M1,
+                 &c->T1t})
     cudaFree(m->p);
   for (auto& m : c->hs) cudaFree(m.p);
   for (auto& m : c->dzs) cudaFree(m.p);
@@ -741,20 +758,28 @@ static int check_batch(ganmf_ctx* c, int ids_offset, int B, bool tp_call = false
   return 0;
 }
 
-// real profiles -> X2[0:B], P[ids] -> Pb, fake profiles F = Pb . V^T -> X2[B:2B]
-static int forward_generator(ganmf_ctx* c, int ids_offset, int B) {
+// real profiles -> X2[0:B], P[ids] -> Pb
+static int forward_profiles(ganmf_ctx* c, int ids_offset, int B) {
   const Csr& tr = c->csr[GANMF_CSR_TRAIN];
   const int* ids = c->ids + ids_offset;
   CU(csr_gather_dense(tr.indptr, tr.indices, tr.data, ids, B, c->X2.p, c->X2.ld, 0, c->st));
   const Param& P = c->params[c->n_d];
-  const Param& V = c->params[c->n_d + 1];
   RC(p_catchup(c, ids, B));                // deferred optimiser steps of exactly these rows
   gather_rows_kernel<<<B, 64, 0, c->st>>>(P.w.p, ids, c->Pb.p, c->Pb.ld);
   CU(cudaGetLastError());
   c->launches += 2;
+  return 0;
+}
+// fake profiles F = Pb . V^T -> X2[B:2B]
+static int forward_fake(ganmf_ctx* c, int B) {
+  const Param& V = c->params[c->n_d + 1];
   Epilogue ep;
   ep.out = c->X2.row(B); ep.ldo = c->X2.ld;
   return gemm(c, c->Pb.p, c->Pb.ld, 0, V.w.p, V.w.ld, 0, B, c->W, c->k, ep);      // G1
+}
+static int forward_generator(ganmf_ctx* c, int ids_offset, int B) {
+  RC(forward_profiles(c, ids_offset, B));
+  return forward_fake(c, B);
 }
 
 static int adam_group(ganmf_ctx* c, int first, int count, float alpha, float reg, int slot_param) {
@@ -783,8 +808,33 @@ static int adam_group(ganmf_ctx* c, int first, int count, float alpha, float reg
 // Codes of the stacked [real ; fake] rows, H2 = X2 . We (+ bias).  On the sparse route (note_train_csr) the real
 // rows are a gather-sum over their CSR entries -- exact fp32, 4*E bytes per interaction -- and only the fake rows go
 // through the tensor cores: the real half of G2 (2*B*I*E flops, twice per step pair) is gone.
-static int forward_codes(ganmf_ctx* c, int ids_offset, int B, const float* bias) {
+// On the low-rank route (ganmf_ctx::lowrank) the fake rows' codes are Pb . M1 with M1 = V^T . We [k, E]:
+// forward_codes_partial leaves M1 (a partial sum over the items of an item-sharded context, like the real codes),
+// forward_codes_finish forms Hf = Pb . M1 + be from the complete M1.
+static int forward_m1(ganmf_ctx* c) {
   Param* We = &c->params[0];
+  const Param& V = c->params[c->n_d + 1];
+  Epilogue em;                                                                     // M1 = V^T . We
+  em.out = c->M1.p; em.ldo = c->M1.ld;
+  return gemm(c, V.w.p, V.w.ld, 1, We->w.p, We->w.ld, 1, c->k, c->E, c->W, em);
+}
+// the real rows' codes alone (low-rank route: the only rows that are encoded at all)
+static int forward_codes_real(ganmf_ctx* c, int ids_offset, int B, const float* bias) {
+  Param* We = &c->params[0];
+  if (c->sparse_real) {
+    const Csr& tr = c->csr[GANMF_CSR_TRAIN];
+    CU(csr_encode_rows(tr.indptr, tr.indices, tr.data, c->ids + ids_offset, B, We->w.p, We->w.ld, c->H2.ld, bias,
+                       c->H2.p, c->H2.ld, c->st));
+    c->launches++;
+    return 0;
+  }
+  Epilogue e2;
+  e2.out = c->H2.p; e2.ldo = c->H2.ld; e2.bias = bias;
+  return gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, B, c->E, c->W, e2);
+}
+static int forward_codes_partial(ganmf_ctx* c, int ids_offset, int B, const float* bias) {
+  Param* We = &c->params[0];
+  const int fake_rows = c->lowrank ? 0 : B;            // rows of X2 that still go through the dense encode GEMM
   Epilogue e2;                                                                     // G2
   e2.bias = bias;
   if (c->sparse_real) {
@@ -792,11 +842,25 @@ static int forward_codes(ganmf_ctx* c, int ids_offset, int B, const float* bias)
     CU(csr_encode_rows(tr.indptr, tr.indices, tr.data, c->ids + ids_offset, B, We->w.p, We->w.ld, c->H2.ld, bias,
                        c->H2.p, c->H2.ld, c->st));
     c->launches++;
-    e2.out = c->H2.row(B); e2.ldo = c->H2.ld;
-    return gemm(c, c->X2.row(B), c->X2.ld, 0, We->w.p, We->w.ld, 1, B, c->E, c->W, e2);
+    if (fake_rows) {
+      e2.out = c->H2.row(B); e2.ldo = c->H2.ld;
+      RC(gemm(c, c->X2.row(B), c->X2.ld, 0, We->w.p, We->w.ld, 1, fake_rows, c->E, c->W, e2));
+    }
+  } else {
+    e2.out = c->H2.p; e2.ldo = c->H2.ld;
+    RC(gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, B + fake_rows, c->E, c->W, e2));
   }
-  e2.out = c->H2.p; e2.ldo = c->H2.ld;
-  return gemm(c, c->X2.p, c->X2.ld, 0, We->w.p, We->w.ld, 1, 2 * B, c->E, c->W, e2);
+  return c->lowrank ? forward_m1(c) : 0;
+}
+static int forward_codes_finish(ganmf_ctx* c, int B, const float* bias) {
+  if (!c->lowrank) return 0;
+  Epilogue ef;                                                                     // Hf = Pb . M1 + be
+  ef.out = c->H2.row(B); ef.ldo = c->H2.ld; ef.bias = bias;
+  return gemm(c, c->Pb.p, c->Pb.ld, 0, c->M1.p, c->M1.ld, 1, B, c->E, c->k, ef);
+}
+static int forward_codes(ganmf_ctx* c, int ids_offset, int B, const float* bias) {
+  RC(forward_codes_partial(c, ids_offset, B, bias));
+  return forward_codes_finish(c, B, bias);
 }
 
 // G3 asks for the per-32-row column sums of the residual when the real / fake boundary falls on a row group
@@ -933,8 +997,55 @@ static int d_apply_impl(ganmf_ctx* c, float lr, float reg, int loss_slot) {
   return 0;
 }
 
+// Low-rank generator backward (ganmf_ctx::lowrank), from Res_f = Res2[B:2B], dHf = dH2[B:2B], Pb, M1:
+//   dPb = [dHf . M1^T] - c1 * (Res_f . V)      (the bracket is complete on every rank of an item-sharded group:
+//                                               `with_codes_term` is true on one of them only)
+//   dV  = We . (dHf^T . Pb) - c1 * (Res_f^T . Pb)   -> V.g
+// (the *_a halves need no code gradient: an item-sharded caller runs them while dHf is being summed over the ranks)
+static int lowrank_dpb_a(ganmf_ctx* c, int B, float c1) {
+  const Param& V = c->params[c->n_d + 1];
+  Epilogue ea;                                                                     // -c1 * Res_f . V
+  ea.out = c->dPb.p; ea.ldo = c->dPb.ld; ea.alpha = -c1;
+  return gemm(c, c->Res2.row(B), c->Res2.ld, 0, V.w.p, V.w.ld, 1, B, c->k, c->W, ea);
+}
+static int lowrank_dpb_b(ganmf_ctx* c, int B) {
+  Epilogue eb;                                                                     // + dHf . M1^T
+  eb.out = c->dPb.p; eb.ldo = c->dPb.ld;
+  eb.c1 = c->dPb.p; eb.ldc1 = c->dPb.ld; eb.beta1 = 1.f;
+  return gemm(c, c->dH2.row(B), c->dH2.ld, 0, c->M1.p, c->M1.ld, 0, B, c->k, c->E, eb);
+}
+static int lowrank_dpb(ganmf_ctx* c, int B, float c1, bool with_codes_term) {
+  RC(lowrank_dpb_a(c, B, c1));
+  return with_codes_term ? lowrank_dpb_b(c, B) : 0;
+}
+static int lowrank_dv_a(ganmf_ctx* c, int B, float c1) {
+  const Param& V = c->params[c->n_d + 1];
+  Epilogue ea;                                                                     // -c1 * Res_f^T . Pb
+  ea.out = V.g; ea.ldo = V.w.ld; ea.alpha = -c1;
+  return gemm(c, c->Res2.row(B), c->Res2.ld, 1, c->Pb.p, c->Pb.ld, 1, c->W, c->k, B, ea);
+}
+static int lowrank_dv_b(ganmf_ctx* c, int B) {
+  Param* We = &c->params[0];
+  const Param& V = c->params[c->n_d + 1];
+  Epilogue et;                                                                     // T1t = Pb^T . dHf  [k, E]
+  et.out = c->T1t.p; et.ldo = c->T1t.ld;
+  RC(gemm(c, c->Pb.p, c->Pb.ld, 1, c->dH2.row(B), c->dH2.ld, 1, c->k, c->E, B, et));
+  Epilogue eb;                                                                     // + We . T1t^T
+  eb.out = V.g; eb.ldo = V.w.ld;
+  eb.c1 = V.g; eb.ldc1 = V.w.ld; eb.beta1 = 1.f;
+  return gemm(c, We->w.p, We->w.ld, 0, c->T1t.p, c->T1t.ld, 0, c->W, c->k, c->E, eb);
+}
+static int lowrank_dv(ganmf_ctx* c, int B, float c1) {
+  RC(lowrank_dv_a(c, B, c1));
+  return lowrank_dv_b(c, B);
+}
+
 static int ganmf_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, float alpha,
                            bool fuse_adam = false, float adam_step = 0.f, float adam_reg = 0.f, int part = 0) {
+  if (part == 2 && c->lowrank) {
+    const double Ng = (double)n_global * c->Wg;
+    return lowrank_dpb(c, B, (float)((1.0 - alpha) * 2.0 / Ng), true);
+  }
   if (part == 2) {                                                                 // dPb only (after part 1)
     Param& V2 = c->params[c->n_d + 1];
     Epilogue e9;
@@ -960,6 +1071,11 @@ static int ganmf_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, fl
   e5.c1 = c->H2.row(B); e5.ldc1 = c->H2.ld; e5.beta1 = c2;
   e5.c2 = c->H2.p; e5.ldc2 = c->H2.ld; e5.beta2 = -c2;
   RC(gemm(c, c->Res2.row(B), c->Res2.ld, 0, Wd->w.p, Wd->w.ld, 0, B, c->E, c->W, e5));
+  if (c->lowrank) {
+    if (part != 1) RC(lowrank_dpb(c, B, c1, true));
+    if (part == 0 || part == 1) RC(lowrank_dv(c, B, c1));
+    return 0;
+  }
   Epilogue e7;                                                                     // G7: dF
   e7.out = c->dF.p; e7.ldo = c->dF.ld;
   e7.c1 = c->Res2.row(B); e7.ldc1 = c->Res2.ld; e7.beta1 = -c1;
@@ -1169,12 +1285,25 @@ static int tp_check(ganmf_ctx* c, int ids_offset, int B) {
   if (c->tp_world <= 1) return fail("not an item-sharded context (config.tp_world <= 1)");
   return check_batch(c, ids_offset, B, true);
 }
+// Low-rank route, phase 1 in two parts so the all-reduce of the real rows' codes travels while the generator GEMM and
+// V^T . We are computed: part 6 = profiles + the real rows' partial codes, part 7 = F = Pb . V^T + the partial M1.
+static int tp_forward_split(ganmf_ctx* c, int phase, int ids_offset, int B) {
+  if (!c->lowrank) return fail("phases 6 / 7 belong to the low-rank route (ganmf_step_routes)");
+  if (phase == 6) {
+    RC(forward_profiles(c, ids_offset, B));
+    CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
+    return forward_codes_real(c, ids_offset, B, c->tp_rank == 0 ? c->params[1].w.p : nullptr);
+  }
+  RC(forward_fake(c, B));
+  return forward_m1(c);
+}
 // profiles + generator + partial codes (the bias joins the sum once: on rank 0)
 static int tp_forward_codes(ganmf_ctx* c, int ids_offset, int B) {
   RC(forward_generator(c, ids_offset, B));
   Param* be = &c->params[1];
   CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
-  return forward_codes(c, ids_offset, B, c->tp_rank == 0 ? be->w.p : nullptr);     // G2 (partial over items)
+  // G2 (partial over items; on the low-rank route the fake rows' codes are formed from the summed M1 in phase 2)
+  return forward_codes_partial(c, ids_offset, B, c->tp_rank == 0 ? be->w.p : nullptr);
 }
 
 int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, float reg, float m_hinge,
@@ -1186,7 +1315,11 @@ int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
   switch (phase) {
     case 1:
       return tp_forward_codes(c, ids_offset, B);
+    case 6:
+    case 7:
+      return tp_forward_split(c, phase, ids_offset, B);
     case 2: {                                                                      // G3 on the summed codes
+      RC(forward_codes_finish(c, B, be->w.p));
       Epilogue e3;
       e3.out = c->Res2.p; e3.ldo = c->Res2.ld; e3.bias = bd->w.p;
       e3.c1 = c->X2.p; e3.ldc1 = c->X2.ld; e3.beta1 = -1.f;
@@ -1241,7 +1374,7 @@ int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
       return 0;
     }
     default:
-      return fail("ganmf_tp_d_phase: phase must be 1..5");
+      return fail("ganmf_tp_d_phase: phase must be 1..7");
   }
 }
 
@@ -1256,7 +1389,21 @@ int ganmf_tp_g_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
   switch (phase) {
     case 1:
       return tp_forward_codes(c, ids_offset, B);
+    case 6:
+    case 7:
+      return tp_forward_split(c, phase, ids_offset, B);
+    case 8:                            // low-rank route: the halves of dV and dPb that need no summed code gradient
+      if (!c->lowrank) return fail("phases 8..10 belong to the low-rank route (ganmf_step_routes)");
+      RC(lowrank_dv_a(c, B, c1));
+      return lowrank_dpb_a(c, B, c1);
+    case 9:                            // ... the code-gradient term of dPb joins the sum once
+      if (!c->lowrank) return fail("phases 8..10 belong to the low-rank route (ganmf_step_routes)");
+      return c->tp_rank == 0 ? lowrank_dpb_b(c, B) : 0;
+    case 10:                           // ... and the code-gradient term of dV (runs while dPb is summed)
+      if (!c->lowrank) return fail("phases 8..10 belong to the low-rank route (ganmf_step_routes)");
+      return lowrank_dv_b(c, B);
     case 2: {
+      RC(forward_codes_finish(c, B, c->params[1].w.p));
       Epilogue e3;                                                                 // G3': fake residual (slice)
       e3.out = c->Res2.row(B); e3.ldo = c->Res2.ld; e3.bias = bd->w.p;
       e3.c1 = c->X2.row(B); e3.ldc1 = c->X2.ld; e3.beta1 = -1.f;
@@ -1275,6 +1422,7 @@ int ganmf_tp_g_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
       return gemm(c, c->Res2.row(B), c->Res2.ld, 0, Wd->w.p, Wd->w.ld, 0, B, c->E, c->W, e5);
     }
     case 3: {
+      if (c->lowrank) return lowrank_dpb(c, B, c1, c->tp_rank == 0);             // dPb (partial over items)
       Epilogue e7;                                                                 // G7: dF (slice)
       e7.out = c->dF.p; e7.ldo = c->dF.ld;
       e7.c1 = c->Res2.row(B); e7.ldc1 = c->Res2.ld; e7.beta1 = -c1;
@@ -1284,6 +1432,7 @@ int ganmf_tp_g_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
       return gemm(c, c->dF.p, c->dF.ld, 0, V.w.p, V.w.ld, 1, B, c->k, c->W, e9);
     }
     case 4: {                                                                      // (runs while dPb is summed)
+      if (c->lowrank) return lowrank_dv(c, B, c1);
       Epilogue e8;                                                                 // G8: dV (slice)
       e8.out = V.g; e8.ldo = V.w.ld;
       return gemm(c, c->dF.p, c->dF.ld, 1, c->Pb.p, c->Pb.ld, 1, c->W, c->k, B, e8);
@@ -1298,7 +1447,7 @@ int ganmf_tp_g_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
       c->launches++;
       return 0;
     default:
-      return fail("ganmf_tp_g_phase: phase must be 1..5");
+      return fail("ganmf_tp_g_phase: phase must be 1..10");
   }
 }
 
@@ -1472,6 +1621,7 @@ int ganmf_device_buffer(ganmf_ctx* c, const char* name, void** ptr, int64_t* n) 
   if (!strcmp(name, "tp_h2")) { *ptr = c->H2.p; *n = (int64_t)c->H2.elems(); return 0; }
   if (!strcmp(name, "tp_dh2")) { *ptr = c->dH2.p; *n = (int64_t)c->dH2.elems(); return 0; }
   if (!strcmp(name, "tp_dpb")) { *ptr = c->dPb.p; *n = (int64_t)c->dPb.elems(); return 0; }
+  if (!strcmp(name, "tp_m1")) { *ptr = c->M1.p; *n = (int64_t)c->M1.elems(); return 0; }
   if (!strcmp(name, "user_factors")) {
     RC(p_flush(c));                          // deferred optimiser steps first: the caller reads the matrix
     *ptr = c->params[c->n_d].w.p; *n = (int64_t)c->params[c->n_d].w.elems(); return 0;
@@ -1486,6 +1636,7 @@ int ganmf_device_buffer_ld(ganmf_ctx* c, const char* name, int* ld) {
   if (!strcmp(name, "tp_h2")) { *ld = c->H2.ld; return 0; }
   if (!strcmp(name, "tp_dh2")) { *ld = c->dH2.ld; return 0; }
   if (!strcmp(name, "tp_dpb")) { *ld = c->dPb.ld; return 0; }
+  if (!strcmp(name, "tp_m1")) { *ld = c->M1.ld; return 0; }
   if (!strcmp(name, "user_factors")) { *ld = c->params[c->n_d].w.ld; return 0; }
   if (!strcmp(name, "item_factors")) { *ld = c->params[c->n_d + 1].w.ld; return 0; }
   return fail("no leading dimension for buffer %s", name);
@@ -2259,10 +2410,11 @@ int ganmf_k_csr_encode_rows(ganmf_ctx* c, int ids_offset, int B, float* out, int
                      ldo, c->st));
   return 0;
 }
-int ganmf_step_routes(ganmf_ctx* c, int32_t* sparse_real, int32_t* bias_grad_from_gemm) {
+int ganmf_step_routes(ganmf_ctx* c, int32_t* sparse_real, int32_t* bias_grad_from_gemm, int32_t* lowrank_fake) {
   if (!c) return fail("null ctx");
   if (sparse_real) *sparse_real = c->sparse_real ? 1 : 0;
   if (bias_grad_from_gemm) *bias_grad_from_gemm = (c->colpart_on && c->colpart) ? 1 : 0;
+  if (lowrank_fake) *lowrank_fake = c->lowrank ? 1 : 0;
   return 0;
 }
 int ganmf_k_adam(ganmf_ctx* c, float* theta, float* m, float* v, const float* g, int64_t n, float alpha,

@@ -422,7 +422,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (u < 0) break;
       const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN, BM);
       const uint32_t acc = ui % ACC;
-      const bool interior = vec_all && (un.m0 + row_off + MT * TC_BM <= args.M) && (un.n0 + BN <= args.N);
+      // A ragged last column tile still takes the vector path when the layout convention (ld = roundup(cols, 32),
+      // zero padding) covers the tile: the accumulator columns >= N are exactly zero (TMA zero-fills the operand
+      // beyond its true extent), so are the padding columns of addends and biases, and zeros land in padding that is
+      // zero anyway (N = k = 250 -> 256: the item-factor gradient GEMMs, whose every tile is ragged).
+      const bool n_pad_ok = !partial && ep.ldo == ((args.N + 31) & ~31) && un.n0 + BN <= ep.ldo &&
+                            (!ep.c1 || un.n0 + BN <= ep.ldc1) && ep.act != ACT_SIGMOID;
+      const bool interior = vec_all && (un.m0 + row_off + MT * TC_BM <= args.M) && (un.n0 + BN <= args.N || n_pad_ok);
       // this warp's chunks of the unit: 32 rows x 32 columns each, NCH = MT * BN / 64 of them
       constexpr int CH = BN / 64, NCH = MT * CH;
       auto chunk_mw = [&](int j) { return un.m0 + row_off + (j / CH) * TC_BM + q * 32; };

@@ -59,10 +59,11 @@ class Engine(object):
         L.check(self.lib.ganmf_synchronize(self.ctx))
 
     def step_routes(self):
-        """{'sparse_real': codes of the real rows by CSR gather-sum, 'bias_grad_from_gemm': dbd from G3's column sums}"""
-        a, b = C.c_int32(), C.c_int32()
-        L.check(self.lib.ganmf_step_routes(self.ctx, C.byref(a), C.byref(b)))
-        return {"sparse_real": bool(a.value), "bias_grad_from_gemm": bool(b.value)}
+        """{'sparse_real': codes of the real rows by CSR gather-sum, 'bias_grad_from_gemm': dbd from G3's column sums,
+        'lowrank_fake': products over the generated profiles through V^T . We (ganmf_step_routes)}"""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        L.check(self.lib.ganmf_step_routes(self.ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return {"sparse_real": bool(a.value), "bias_grad_from_gemm": bool(b.value), "lowrank_fake": bool(c.value)}
 
     def launch_count(self):
         return int(self.lib.ganmf_launch_count(self.ctx))

@@ -225,7 +225,7 @@ class ItemShardedTrainer(object):
     one device -- the sums are then formed in place with torch instead of NCCL.  `buffers`: per-engine dicts of
     host tensors for a stand-in engine (CPU/gloo tests)."""
 
-    NAMES = ("tp_h2", "tp_dh2", "tp_dpb", "step_scalars")
+    NAMES = ("tp_h2", "tp_dh2", "tp_dpb", "tp_m1", "step_scalars")
 
     def __init__(self, engines, group=None, buffers=None):
         import torch
@@ -245,6 +245,10 @@ class ItemShardedTrainer(object):
         e0 = self.engines[0]
         self.ld_h, self.ld_p = e0.device_buffer_ld("tp_h2"), e0.device_buffer_ld("tp_dpb")
         self.world = len(self.engines) if self.local else dist.get_world_size(group)
+        # low-rank generator route (ganmf_step_routes): the fake rows' codes are Pb . (V^T . We), so after phase 1 only
+        # the real rows' partial codes and the [k, E] partial of V^T . We are summed (B + k rows instead of 2B)
+        self.lowrank = bool(e0.step_routes()["lowrank_fake"])
+        self.k = e0.cfg.num_factors
 
     def _sum(self, name, lo, hi, async_op=False):
         if self.local:
@@ -258,14 +262,27 @@ class ItemShardedTrainer(object):
         return self.dist.all_reduce(self.buf[0][name][lo:hi], op=self.dist.ReduceOp.SUM, group=self.group,
                                     async_op=async_op)
 
+    def _forward_codes(self, fn, a, B):
+        """Phase 1 and the sums behind it.  Low-rank route: the real rows' codes travel while the generator GEMM and
+        V^T.We are computed (phases 6 / 7), then the [k, E] partial of V^T.We (1 MB) is summed."""
+        if not self.lowrank:
+            self._phase(fn, 1, *a)
+            self._sum("tp_h2", 0, 2 * B * self.ld_h)
+            return
+        self._phase(fn, 6, *a)
+        w = self._sum("tp_h2", 0, B * self.ld_h, async_op=True)
+        self._phase(fn, 7, *a)
+        self._sum("tp_m1", 0, self.k * self.ld_h)
+        if w is not None:
+            w.wait()
+
     def _phase(self, fn, *a):
         for e in self.engines:
             getattr(e, fn)(*a)
 
     def d_step(self, ids_offset, B, lr, reg, m_hinge, loss_slot):
         a = (ids_offset, B, lr, reg, m_hinge, loss_slot)
-        self._phase("tp_d_phase", 1, *a)
-        self._sum("tp_h2", 0, 2 * B * self.ld_h)
+        self._forward_codes("tp_d_phase", a, B)
         self._phase("tp_d_phase", 2, *a)
         self._sum("step_scalars", 0, 2)
         self._phase("tp_d_phase", 3, *a)
@@ -277,13 +294,22 @@ class ItemShardedTrainer(object):
 
     def g_step(self, ids_offset, B, lr, reg, recon_coefficient, loss_slot):
         a = (ids_offset, B, lr, reg, recon_coefficient, loss_slot)
-        self._phase("tp_g_phase", 1, *a)
-        self._sum("tp_h2", 0, 2 * B * self.ld_h)
+        self._forward_codes("tp_g_phase", a, B)
         self._phase("tp_g_phase", 2, *a)
-        self._sum("tp_dh2", B * self.ld_h, 2 * B * self.ld_h)
-        self._phase("tp_g_phase", 3, *a)
-        w = self._sum("tp_dpb", 0, B * self.ld_p, async_op=True)      # travels while the item-factor gradient is computed
-        self._phase("tp_g_phase", 4, *a)
+        if self.lowrank:
+            # the fake code gradients travel while the halves of dV / dPb that do not need them are computed
+            w = self._sum("tp_dh2", B * self.ld_h, 2 * B * self.ld_h, async_op=True)
+            self._phase("tp_g_phase", 8, *a)
+            if w is not None:
+                w.wait()
+            self._phase("tp_g_phase", 9, *a)
+            w = self._sum("tp_dpb", 0, B * self.ld_p, async_op=True)  # travels while dV is completed
+            self._phase("tp_g_phase", 10, *a)
+        else:
+            self._sum("tp_dh2", B * self.ld_h, 2 * B * self.ld_h)
+            self._phase("tp_g_phase", 3, *a)
+            w = self._sum("tp_dpb", 0, B * self.ld_p, async_op=True)  # travels while the item-factor gradient is computed
+            self._phase("tp_g_phase", 4, *a)
         if w is not None:
             w.wait()
         self._phase("tp_g_phase", 5, *a)
@@ -333,8 +359,8 @@ class ItemShardedTrainer(object):
             ids = rows[s:s + B]
             for e in self.engines:
                 e.upload_ids(ids)
-            self._phase("tp_d_phase", 1, 0, ids.size, 0.0, 0.0, 1.0, 0)
-            self._sum("tp_h2", 0, 2 * ids.size * self.ld_h)
+            self._phase("tp_d_phase", 6 if self.lowrank else 1, 0, ids.size, 0.0, 0.0, 1.0, 0)
+            self._sum("tp_h2", 0, ids.size * self.ld_h)
             h = self.buf[0]["tp_h2"][:ids.size * self.ld_h].reshape(ids.size, self.ld_h)[:, :E]
             out[s:s + ids.size] = h.cpu().numpy()
         return out

@@ -156,6 +156,15 @@ int ganmf_finalize_loss(ganmf_ctx* ctx, float reg, int loss_slot);
  *      phase 3 (dF, partial dPb)                           -> sum "tp_dpb"[0 : B*ld]  (may overlap phase 4)
  *      phase 4 (dV)
  *      phase 5 (Adam on the batch rows of P and on the V slice, loss log)
+ * Low-rank generator route (ganmf_step_routes reports lowrank_fake = 1): after phase 1 only the real rows of the codes
+ * and the [k, E] partial of V^T.We are summed -- "tp_h2"[0 : B*ld] and "tp_m1"[0 : k*ld] -- and phase 2 forms the fake
+ * rows' codes from the summed M1.  Finer cuts of the same step, for overlapping the sums with work that does not need
+ * them (both steps: 6 then 7 instead of 1; G step: 8, 9, 10 instead of 3, 4):
+ *      phase 6  (profiles, real rows' partial codes)          -> sum "tp_h2"[0 : B*ld]   (may overlap phase 7)
+ *      phase 7  (F = Pb.V^T, partial V^T.We)                  -> sum "tp_m1"[0 : k*ld]
+ *      phase 8  (after G phase 2; -c1 Res_f^T.Pb -> dV, -c1 Res_f.V -> partial dPb: overlaps the sum of "tp_dh2")
+ *      phase 9  (rank 0 adds dHf.M1^T to its partial dPb)      -> sum "tp_dpb"[0 : B*ld]  (may overlap phase 10)
+ *      phase 10 (dV += We.(dHf^T.Pb))
  * ld = leading dimension reported by ganmf_device_buffer_ld.  Every rank passes the same ids.  The loss log holds
  * per-rank PARTIAL losses (rank 0: the data term + its l2 share; others: their l2 / reconstruction share): the
  * step's loss is their SUM over ranks, formed by the caller once per epoch. */
@@ -241,8 +250,12 @@ int ganmf_metrics_from_topk(ganmf_ctx* ctx, const int32_t* topk_idx_host, int K,
 /* Which routes the training step of this context takes (decided when the train CSR is set; GANRec/GANMF.py:62-70,
  * 184-187 is one dense graph): *sparse_real = 1 when the codes of the real rows are the CSR gather-sum instead of
  * the real half of the dense encode GEMM (density <= 0.25 %, or GANMF_SPARSE_REAL=1); *bias_grad_from_gemm = 1 when
- * the decoder-bias gradient is formed from the residual GEMM's per-32-row column sums (GANMF_COLPART != 0). */
-int ganmf_step_routes(ganmf_ctx* ctx, int32_t* sparse_real, int32_t* bias_grad_from_gemm);
+ * the decoder-bias gradient is formed from the residual GEMM's per-32-row column sums (GANMF_COLPART != 0);
+ * *lowrank_fake = 1 when the products that contract the generated profiles `fake_profile = P[u] . V^T`
+ * (GANRec/GANMF.py:82-84) over the items go through the [k, emb_dim] matrix V^T . W_enc (2 * num_factors <=
+ * max_batch, or GANMF_LOWRANK=1): an item-sharded caller then all-reduces the buffer "tp_m1" and only the real rows
+ * of "tp_h2" after phase 1 of ganmf_tp_d_phase / ganmf_tp_g_phase. */
+int ganmf_step_routes(ganmf_ctx* ctx, int32_t* sparse_real, int32_t* bias_grad_from_gemm, int32_t* lowrank_fake);
 
 /* ---- primitive kernels (unit tests, ncu) ------------------------------------------------- */
 /* All pointers are DEVICE pointers here. */

@@ -58,10 +58,13 @@ def run_ganmf(n_rows, width, k, E, B, epochs, hp, gemm_path, density=0.05, seed=
 HP = dict(d_lr=1e-4, g_lr=2e-4, d_reg=1e-4, g_reg=0.0, m=10.0, alpha=0.01)
 
 
-@pytest.mark.parametrize("path_name", ["simt", "tc"])
+@pytest.mark.parametrize("path_name", ["simt", "tc", "tc-dense"])
 @pytest.mark.parametrize("hp", [HP, dict(HP, m=0.05, g_reg=1e-3, alpha=0.3)])     # gate open / closed
-def test_ganmf_100_steps_parity(path_name, hp):
+def test_ganmf_100_steps_parity(monkeypatch, path_name, hp):
     from ganmf_b200 import _lib as L
+    if path_name == "tc-dense":            # the reference graph's own GEMM list (no low-rank generator route)
+        monkeypatch.setenv("GANMF_LOWRANK", "0")
+        path_name = "tc"
     path = {"simt": L.GEMM_SIMT, "tc": L.GEMM_TC}[path_name]
     # 300 rows, B=64 -> 5 batches/epoch (last one short: 44 rows); 10 epochs = 50 D + 50 G steps
     dl, gl, odl, ogl, got, want = run_ganmf(300, 517, 24, 40, 64, 10, hp, path)
@@ -73,13 +76,15 @@ def test_ganmf_100_steps_parity(path_name, hp):
 
 
 @pytest.mark.parametrize("hp", [HP, dict(HP, m=0.05, alpha=0.3)])                  # gate open / closed
-def test_ganmf_steps_parity_on_cta_pairs(monkeypatch, hp):
+@pytest.mark.parametrize("lowrank", ["0", "1"])       # fake profiles through the dense GEMMs / through V^T.We (capi.cu)
+def test_ganmf_steps_parity_on_cta_pairs(monkeypatch, hp, lowrank):
     """GANMF_PAIR=2 forces every legal tcgen05 GEMM onto CTA pairs (cta_group::2), which the benchmark shapes
     use for all many-tile GEMMs: residual epilogue with prefetched addend + bias + energy sums (2B=320 rows: the
     second CTA of the last pair tile is partly out of range; 517 columns: ragged last tile), the fused-Adam
     epilogues of dWd / dWe, the plain generator GEMMs.  Same tolerance as the single-CTA paths."""
     from ganmf_b200 import _lib as L
     monkeypatch.setenv("GANMF_PAIR", "2")
+    monkeypatch.setenv("GANMF_LOWRANK", lowrank)
     dl, gl, odl, ogl, got, want = run_ganmf(600, 517, 24, 300, 160, 8, hp, L.GEMM_TC)
     assert len(dl) == 32 and len(gl) == 32
     np.testing.assert_allclose(dl, odl, rtol=REL)

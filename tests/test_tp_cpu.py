@@ -21,19 +21,28 @@ P_, V_ = to.GANMF_G
 class NumpyTPEngine(object):
     """The arithmetic of one rank of an item-sharded GANMF context (csrc/capi.cu, ganmf_tp_*_phase), float64."""
 
-    def __init__(self, rank, world, urm_slice, width_global, p0_slice, hp, B):
+    def __init__(self, rank, world, urm_slice, width_global, p0_slice, hp, B, lowrank=False):
         self.rank, self.world, self.urm, self.Wg, self.hp = rank, world, urm_slice, width_global, hp
+        self.lowrank = lowrank              # ganmf_ctx::lowrank: products over the fake profiles through V^T . We
         self.p = {k: np.array(v, dtype=np.float64) for k, v in p0_slice.items()}
         E, k = self.p[BE].shape[0], self.p[P_].shape[1]
         self.ld_h, self.ld_p = E, k
         self.b = {"tp_h2": torch.zeros(2 * B * E, dtype=torch.float64),
                   "tp_dh2": torch.zeros((2 * B + 1) * E, dtype=torch.float64),
                   "tp_dpb": torch.zeros(B * k, dtype=torch.float64),
+                  "tp_m1": torch.zeros(k * E, dtype=torch.float64),
                   "step_scalars": torch.zeros(7, dtype=torch.float64)}
         self.opt_d = to.TFAdam(self.p, to.GANMF_D, hp["d_lr"], np.float64)
         self.opt_g = to.TFAdam(self.p, to.GANMF_G, hp["g_lr"], np.float64)
         self.losses = {}
         self.ids = None
+
+        class _Cfg(object):
+            num_factors = k
+        self.cfg = _Cfg()
+
+    def step_routes(self):
+        return {"sparse_real": False, "bias_grad_from_gemm": False, "lowrank_fake": self.lowrank}
 
     def device_buffer_ld(self, name):
         return self.ld_p if name == "tp_dpb" else self.ld_h
@@ -44,22 +53,37 @@ class NumpyTPEngine(object):
     def _view(self, name, rows, ld):
         return self.b[name].numpy()[:rows * ld].reshape(rows, ld)
 
-    def _forward_codes(self, off, B):
-        ids = self.ids[off:off + B]
-        self.R = np.asarray(self.urm[ids].toarray(), dtype=np.float64)
-        self.Pb = self.p[P_][ids]
+    def _forward_codes(self, off, B, part=0):
+        bias = self.p[BE] if self.rank == 0 else 0.0                             # bias joins the sum once
+        if part in (0, 6):
+            ids = self.ids[off:off + B]
+            self.R = np.asarray(self.urm[ids].toarray(), dtype=np.float64)
+            self.Pb = self.p[P_][ids]
+            self.b["step_scalars"].zero_()
+        if part == 6:                      # low-rank route: the real rows' partial codes ...
+            self._view("tp_h2", 2 * B, self.ld_h)[:B] = self.R @ self.p[WE] + bias
+            return
         self.F = self.Pb @ self.p[V_].T
         self.X2 = np.concatenate([self.R, self.F], 0)
-        self.b["step_scalars"].zero_()
-        H = self.X2 @ self.p[WE] + (self.p[BE] if self.rank == 0 else 0.0)      # bias joins the sum once
-        self._view("tp_h2", 2 * B, self.ld_h)[:] = H
+        if part == 7:                      # ... and the [k, E] partial of V^T . We; the fake codes follow in phase 2
+            assert self.lowrank
+            self._view("tp_m1", self.ld_p, self.ld_h)[:] = self.p[V_].T @ self.p[WE]
+            return
+        assert not self.lowrank            # (the trainer drives the low-rank route through phases 6 / 7)
+        self._view("tp_h2", 2 * B, self.ld_h)[:] = self.X2 @ self.p[WE] + bias
+
+    def _finish_codes(self, B):
+        if self.lowrank:                   # Hf = Pb . M1 + be from the summed M1 (the same on every rank)
+            M1 = self._view("tp_m1", self.ld_p, self.ld_h)
+            self._view("tp_h2", 2 * B, self.ld_h)[B:] = self.Pb @ M1 + self.p[BE]
 
     def tp_d_phase(self, phase, off, B, lr, reg, m, slot):
         E = self.ld_h
         H2 = self._view("tp_h2", 2 * B, E)
-        if phase == 1:
-            self._forward_codes(off, B)
+        if phase in (1, 6, 7):
+            self._forward_codes(off, B, 0 if phase == 1 else phase)
         elif phase == 2:
+            self._finish_codes(B)
             self.Res = H2 @ self.p[WD] + self.p[BD] - self.X2
             sc = self.b["step_scalars"].numpy()
             sc[0], sc[1] = (self.Res[:B] ** 2).sum(), (self.Res[B:] ** 2).sum()
@@ -92,9 +116,10 @@ class NumpyTPEngine(object):
         H2 = self._view("tp_h2", 2 * B, E)
         N, M = float(B) * self.Wg, float(B) * E
         c1, c2 = (1 - a) * 2 / N, a * 2 / M
-        if phase == 1:
-            self._forward_codes(off, B)
+        if phase in (1, 6, 7):
+            self._forward_codes(off, B, 0 if phase == 1 else phase)
         elif phase == 2:
+            self._finish_codes(B)
             self.Resf = H2[B:] @ self.p[WD] + self.p[BD] - self.F
             self.sumsq = (self.Resf ** 2).sum()
             self.fm = ((H2[:B] - H2[B:]) ** 2).sum()
@@ -108,6 +133,18 @@ class NumpyTPEngine(object):
             self._view("tp_dpb", B, k)[:] = self.dF @ self.p[V_]
         elif phase == 4:
             self.dV = self.dF.T @ self.Pb
+        # low-rank route (dF is never formed): dPb = [dHf . M1^T on one rank] - c1 * Res_f . V,
+        # dV = We . (dHf^T . Pb) - c1 * Res_f^T . Pb; phase 8 runs BEFORE the code gradients are summed
+        elif phase == 8:
+            self.dV = -c1 * (self.Resf.T @ self.Pb)
+            self._view("tp_dpb", B, k)[:] = -c1 * (self.Resf @ self.p[V_])
+        elif phase == 9:
+            if self.rank == 0:
+                dhf = self._view("tp_dh2", 2 * B + 1, E)[B:2 * B]
+                self._view("tp_dpb", B, k)[:] += dhf @ self._view("tp_m1", self.ld_p, self.ld_h).T
+        elif phase == 10:
+            dhf = self._view("tp_dh2", 2 * B + 1, E)[B:2 * B]
+            self.dV = self.dV + self.p[WE] @ (dhf.T @ self.Pb)
         elif phase == 5:
             ids = self.ids[off:off + B]
             dP = reg * self.p[P_]
@@ -133,14 +170,14 @@ def _problem():
     return urm, p0, hp, B
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, lowrank=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     urm, p0, hp, B = _problem()
     lo, hi = item_slices(urm.shape[1], world)[rank]
     sl = {WE: p0[WE][lo:hi], BE: p0[BE], WD: p0[WD][:, lo:hi], BD: p0[BD][lo:hi], P_: p0[P_], V_: p0[V_][lo:hi]}
-    eng = NumpyTPEngine(rank, world, urm[:, lo:hi].tocsr(), urm.shape[1], sl, hp, B)
+    eng = NumpyTPEngine(rank, world, urm[:, lo:hi].tocsr(), urm.shape[1], sl, hp, B, lowrank)
     tr = ItemShardedTrainer(eng, buffers=eng.b)
     dl, gl = [], []
     for _, batches in to.epoch_index_stream(urm.shape[0], B, 3, seed=5):
@@ -151,14 +188,15 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_item_sharded_trainer_gloo_equals_oracle():
+@pytest.mark.parametrize("lowrank", [False, True])
+def test_item_sharded_trainer_gloo_equals_oracle(lowrank):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, lowrank)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted((q.get(timeout=180) for _ in procs), key=lambda t: t[0])
