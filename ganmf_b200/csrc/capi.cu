@@ -141,6 +141,14 @@ struct ganmf_ctx {
   // of the real half of the dense G2 product.  sparse_mode: -1 = by density (GANMF_SPARSE_REAL unset), 0 / 1 = forced
   int sparse_mode = -1;
   bool sparse_real = false;
+  // Side stream: small-footprint kernels that are independent of the main chain run beside it -- the deferred
+  // user-factor steps (compute-bound, 64-thread CTAs) next to the profile gather and the real rows' encode
+  // (HBM-bound).
+  // Fork = event on st, join = event on st_aux; every entry point leaves with the side stream joined or joins it at
+  // the first consumer (aux_pending).  GANMF_AUX_STREAM=0: everything on st (A/B switch).
+  cudaStream_t st_aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool aux_on = true, aux_pending = false;
   // low-rank generator route: the fake profiles F = Pb . V^T have rank k, so every product that contracts F (or a
   // gradient flowing back into it) over the items can go through a [k, E] matrix instead of a [B, I] one:
   //   codes      Hf  = F . We            = Pb . (V^T . We)                        = Pb . M1
@@ -175,6 +183,7 @@ struct ganmf_ctx {
 };
 
 const char* ganmf_last_error(void) { return g_err; }
+static int aux_join(ganmf_ctx* c);
 
 template <typename T>
 static int dalloc(T** p, size_t n) {
@@ -341,6 +350,7 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   if (const char* sr = getenv("GANMF_SPARSE_REAL")) c->sparse_mode = atoi(sr);          // A/B switch / tests
   if (const char* cp = getenv("GANMF_COLPART")) c->colpart_on = !(cp[0] == '0');        // A/B switch / tests
   if (const char* lr = getenv("GANMF_LOWRANK")) c->lowrank_mode = atoi(lr);             // A/B switch / tests
+  if (const char* ax = getenv("GANMF_AUX_STREAM")) c->aux_on = !(ax[0] == '0');         // A/B switch / tests
   c->B = cfg->max_batch; c->W = cfg->width; c->Wp = rup(cfg->width, 32);
   c->k = cfg->num_factors; c->kp = rup(c->k, 32);
   c->Wg = cfg->global_width > 0 ? cfg->global_width : cfg->width;
@@ -444,6 +454,11 @@ static int create_buffers(ganmf_ctx* c) {
     RC(dalloc(&c->dout2, (size_t)rup(2 * B, 32)));
     RC(dalloc(&c->idf, (size_t)rup(2 * B, 32)));
   }
+  if (c->aux_on) {
+    CU(cudaStreamCreateWithFlags(&c->st_aux, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
   c->ws_floats = (size_t)48 << 20;     // 192 MB of split-K partials
   RC(dalloc(&c->ws, c->ws_floats));
   RC(dalloc(&c->sc, 1));
@@ -490,6 +505,9 @@ void ganmf_destroy(ganmf_ctx* c) {
     if (b.h_count) cudaFreeHost(b.h_count);
     for (cudaEvent_t ev : {b.ev_sel, b.ev_res, b.ev_fin}) if (ev) cudaEventDestroy(ev);
   }
+  if (c->st_aux) cudaStreamDestroy(c->st_aux);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->st_res) cudaStreamDestroy(c->st_res);
   if (c->st_fin) cudaStreamDestroy(c->st_fin);
   if (c->ev_setup) cudaEventDestroy(c->ev_setup);
@@ -510,6 +528,7 @@ int ganmf_set_gemm_sms(ganmf_ctx* c, int n_sms) {
   return 0;
 }
 int ganmf_synchronize(ganmf_ctx* c) {
+  RC(aux_join(c));
   CU(cudaStreamSynchronize(c->st));
   return 0;
 }
@@ -608,13 +627,34 @@ int ganmf_set_csr_device(ganmf_ctx* c, int which, int n_rows, int n_cols, const 
   return 0;
 }
 
+// ------------------------------------------------------------------------------ side stream
+// work enqueued on the returned stream starts after everything enqueued on c->st so far
+static int aux_fork(ganmf_ctx* c, cudaStream_t* s) {
+  *s = c->st;
+  if (!c->aux_on) return 0;
+  CU(cudaEventRecord(c->ev_fork, c->st));
+  CU(cudaStreamWaitEvent(c->st_aux, c->ev_fork, 0));
+  c->aux_pending = true;
+  *s = c->st_aux;
+  return 0;
+}
+// everything enqueued on c->st from here on waits for the side stream
+static int aux_join(ganmf_ctx* c) {
+  if (!c->aux_pending) return 0;
+  CU(cudaEventRecord(c->ev_join, c->st_aux));
+  CU(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+  c->aux_pending = false;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ lazy user factors
 // Replay the deferred zero-gradient Adam steps: for the rows in ids (device), or for every row.
-static int p_catchup(ganmf_ctx* c, const int* ids_dev, int n) {
+static int p_catchup(ganmf_ctx* c, const int* ids_dev, int n, cudaStream_t st = nullptr) {
   if (!c->p_stale || n <= 0) return 0;
+  if (!st) st = c->st;
   const Param& P = c->params[c->n_d];
   const int grid = ids_dev ? n : std::min(n, 148 * 16);
-  p_catchup_kernel<<<grid, 64, 0, c->st>>>(P.w.p, P.m, P.v, P.w.ld, ids_dev, n, c->p_last, c->alpha_log, c->g_T,
+  p_catchup_kernel<<<grid, 64, 0, st>>>(P.w.p, P.m, P.v, P.w.ld, ids_dev, n, c->p_last, c->alpha_log, c->g_T,
                                           c->log_base);
   CU(cudaGetLastError());
   c->launches++;
@@ -622,6 +662,7 @@ static int p_catchup(ganmf_ctx* c, const int* ids_dev, int n) {
 }
 // Every reader of the whole matrix (export, snapshot, scoring, a dense optimiser step) calls this first.
 static int p_flush(ganmf_ctx* c) {
+  RC(aux_join(c));
   if (!c->p_stale) return 0;
   RC(p_catchup(c, nullptr, c->cfg.n_rows));
   c->p_stale = false;
@@ -758,20 +799,27 @@ static int check_batch(ganmf_ctx* c, int ids_offset, int B, bool tp_call = false
   return 0;
 }
 
-// real profiles -> X2[0:B], P[ids] -> Pb
-static int forward_profiles(ganmf_ctx* c, int ids_offset, int B) {
+// real profiles -> X2[0:B] (when some GEMM of the step reads the dense tile), P[ids] -> Pb.  The replay of the deferred
+// user-factor steps and the row gather go to the side stream: the first consumer of Pb joins it (forward_fake).
+static int forward_profiles(ganmf_ctx* c, int ids_offset, int B, bool dense_real = true) {
   const Csr& tr = c->csr[GANMF_CSR_TRAIN];
   const int* ids = c->ids + ids_offset;
-  CU(csr_gather_dense(tr.indptr, tr.indices, tr.data, ids, B, c->X2.p, c->X2.ld, 0, c->st));
+  cudaStream_t s2;
+  RC(aux_fork(c, &s2));
   const Param& P = c->params[c->n_d];
-  RC(p_catchup(c, ids, B));                // deferred optimiser steps of exactly these rows
-  gather_rows_kernel<<<B, 64, 0, c->st>>>(P.w.p, ids, c->Pb.p, c->Pb.ld);
+  RC(p_catchup(c, ids, B, s2));            // deferred optimiser steps of exactly these rows
+  gather_rows_kernel<<<B, 64, 0, s2>>>(P.w.p, ids, c->Pb.p, c->Pb.ld);
   CU(cudaGetLastError());
-  c->launches += 2;
+  c->launches += 1;
+  if (dense_real) {
+    CU(csr_gather_dense(tr.indptr, tr.indices, tr.data, ids, B, c->X2.p, c->X2.ld, 0, c->st));
+    c->launches += 1;
+  }
   return 0;
 }
 // fake profiles F = Pb . V^T -> X2[B:2B]
 static int forward_fake(ganmf_ctx* c, int B) {
+  RC(aux_join(c));
   const Param& V = c->params[c->n_d + 1];
   Epilogue ep;
   ep.out = c->X2.row(B); ep.ldo = c->X2.ld;
@@ -854,6 +902,7 @@ static int forward_codes_partial(ganmf_ctx* c, int ids_offset, int B, const floa
 }
 static int forward_codes_finish(ganmf_ctx* c, int B, const float* bias) {
   if (!c->lowrank) return 0;
+  RC(aux_join(c));
   Epilogue ef;                                                                     // Hf = Pb . M1 + be
   ef.out = c->H2.row(B); ef.ldo = c->H2.ld; ef.bias = bias;
   return gemm(c, c->Pb.p, c->Pb.ld, 0, c->M1.p, c->M1.ld, 1, B, c->E, c->k, ef);
@@ -861,6 +910,22 @@ static int forward_codes_finish(ganmf_ctx* c, int B, const float* bias) {
 static int forward_codes(ganmf_ctx* c, int ids_offset, int B, const float* bias) {
   RC(forward_codes_partial(c, ids_offset, B, bias));
   return forward_codes_finish(c, B, bias);
+}
+
+// Profiles, generator and codes of one step, ordered so that the side stream has company: on the low-rank route the
+// real rows' codes (HBM-bound gather-sum or GEMM) are formed before the generator GEMM, which is the first kernel that
+// needs the (caught-up) user-factor rows.  dense_real: some later GEMM of the step reads the dense real tile X2[0:B].
+static int forward_all(ganmf_ctx* c, int ids_offset, int B, const float* bias, bool dense_real) {
+  RC(forward_profiles(c, ids_offset, B, dense_real || !c->sparse_real));
+  CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
+  if (c->lowrank) {
+    RC(forward_codes_real(c, ids_offset, B, bias));
+    RC(forward_fake(c, B));
+    RC(forward_m1(c));
+    return forward_codes_finish(c, B, bias);
+  }
+  RC(forward_fake(c, B));
+  return forward_codes_partial(c, ids_offset, B, bias);
 }
 
 // G3 asks for the per-32-row column sums of the residual when the real / fake boundary falls on a row group
@@ -885,11 +950,15 @@ static int decoder_bias_grad(ganmf_ctx* c, int B, const float* rs, float* out) {
 // forward on [R ; F]; phase 0: both.  A data-parallel caller runs phase 1 of the NEXT step while the
 // all-gather of the freshly updated discriminator weights is still in flight.
 static int ganmf_d_forward_impl(ganmf_ctx* c, int ids_offset, int B, int phase = 0) {
-  if (phase != 2) RC(forward_generator(c, ids_offset, B));
-  if (phase == 1) return 0;
   Param *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
-  CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
-  RC(forward_codes(c, ids_offset, B, be->w.p));                                    // G2
+  if (phase == 0) {
+    RC(forward_all(c, ids_offset, B, be->w.p, true));                              // G1, G2
+  } else {
+    if (phase != 2) RC(forward_generator(c, ids_offset, B));
+    if (phase == 1) return 0;
+    CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
+    RC(forward_codes(c, ids_offset, B, be->w.p));                                  // G2
+  }
   Epilogue e3;                                                                     // G3
   e3.out = c->Res2.p; e3.ldo = c->Res2.ld; e3.bias = bd->w.p;
   e3.c1 = c->X2.p; e3.ldc1 = c->X2.ld; e3.beta1 = -1.f;
@@ -952,7 +1021,9 @@ static int ganmf_d_backward_apply_fused(ganmf_ctx* c, int B, int n_global, float
       c->H2.p, c->H2s.p, c->H2.ld / 4, rs, B);
   CU(cudaGetLastError());
   RC(decoder_bias_grad(c, B, rs, bd->g));                                          // dbd
-  rowdot_kernel<<<c->E, 256, 0, c->st>>>(Wd->w.p, c->E, c->W, Wd->w.ld, bd->g, be->g);   // dbe = dbd . Wd^T
+  // dbe = dbd . Wd^T.  (Running these row dots on the side stream under G5 -- both stream the old Wd -- was measured:
+  // G5 slows down by 0.23 ms to hide a 0.18 ms kernel, profiles/r02b_ab_aux_stream.txt.)
+  rowdot_kernel<<<c->E, 256, 0, c->st>>>(Wd->w.p, c->E, c->W, Wd->w.ld, bd->g, be->g);
   CU(cudaGetLastError());
   c->launches += 4;
   Epilogue e5;                                                                     // G5: dH2 (old Wd)
@@ -1052,11 +1123,9 @@ static int ganmf_g_fb_impl(ganmf_ctx* c, int ids_offset, int B, int n_global, fl
     e9.out = c->dPb.p; e9.ldo = c->dPb.ld;
     return gemm(c, c->dF.p, c->dF.ld, 0, V2.w.p, V2.w.ld, 1, B, c->k, c->W, e9);
   }
-  RC(forward_generator(c, ids_offset, B));
   Param *We = &c->params[0], *be = &c->params[1], *Wd = &c->params[2], *bd = &c->params[3];
   Param& V = c->params[c->n_d + 1];
-  CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
-  RC(forward_codes(c, ids_offset, B, be->w.p));                                    // G2 (real + fake codes)
+  RC(forward_all(c, ids_offset, B, be->w.p, false));                               // G1, G2 (real + fake codes)
   Epilogue e3;                                                                     // G3': fake residual
   e3.out = c->Res2.row(B); e3.ldo = c->Res2.ld; e3.bias = bd->w.p;
   e3.c1 = c->X2.row(B); e3.ldc1 = c->X2.ld; e3.beta1 = -1.f;
@@ -1287,10 +1356,10 @@ static int tp_check(ganmf_ctx* c, int ids_offset, int B) {
 }
 // Low-rank route, phase 1 in two parts so the all-reduce of the real rows' codes travels while the generator GEMM and
 // V^T . We are computed: part 6 = profiles + the real rows' partial codes, part 7 = F = Pb . V^T + the partial M1.
-static int tp_forward_split(ganmf_ctx* c, int phase, int ids_offset, int B) {
+static int tp_forward_split(ganmf_ctx* c, int phase, int ids_offset, int B, bool dense_real) {
   if (!c->lowrank) return fail("phases 6 / 7 belong to the low-rank route (ganmf_step_routes)");
   if (phase == 6) {
-    RC(forward_profiles(c, ids_offset, B));
+    RC(forward_profiles(c, ids_offset, B, dense_real || !c->sparse_real));
     CU(cudaMemsetAsync(c->sc, 0, sizeof(StepScalars), c->st));
     return forward_codes_real(c, ids_offset, B, c->tp_rank == 0 ? c->params[1].w.p : nullptr);
   }
@@ -1317,7 +1386,7 @@ int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
       return tp_forward_codes(c, ids_offset, B);
     case 6:
     case 7:
-      return tp_forward_split(c, phase, ids_offset, B);
+      return tp_forward_split(c, phase, ids_offset, B, true);
     case 2: {                                                                      // G3 on the summed codes
       RC(forward_codes_finish(c, B, be->w.p));
       Epilogue e3;
@@ -1391,7 +1460,7 @@ int ganmf_tp_g_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
       return tp_forward_codes(c, ids_offset, B);
     case 6:
     case 7:
-      return tp_forward_split(c, phase, ids_offset, B);
+      return tp_forward_split(c, phase, ids_offset, B, false);   // (no GEMM of the G step reads the dense real tile)
     case 8:                            // low-rank route: the halves of dV and dPb that need no summed code gradient
       if (!c->lowrank) return fail("phases 8..10 belong to the low-rank route (ganmf_step_routes)");
       RC(lowrank_dv_a(c, B, c1));
