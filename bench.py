@@ -427,7 +427,7 @@ class Bench(object):
         eng.profile(False)
         pk = peaks()
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r02_tc_gemm_dram_traffic_%s.json" % c["key"])
+        tpath = os.path.join(ROOT, "profiles", "r02b_tc_gemm_dram_traffic_%s.json" % c["key"])
         if world == 1 and os.path.exists(tpath):                # from the committed `ncu --set full` capture
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["dram_bytes_per_launch_mean"], os.path.relpath(tpath, ROOT) + ": " + tj["note"]
@@ -436,6 +436,12 @@ class Bench(object):
         roofline = {"kernel": "tc_gemm_kernel (tcgen05 kind::tf32, TMA, TMEM; CTA pairs cta_group::2 on the many-tile GEMMs)",
                     "bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                     "frac": achieved / pk["tf_sust"], "traffic": traffic, "traffic_source": traffic_src,
+                    "basis": "EXECUTED MMA flops (2*M*N*K of every tcgen05 launch) over the summed CUDA-event time of those "
+                             "launches.  The step executes fewer flops than the reference graph (SURVEY 8(d): I*(8k+30E) per "
+                             "row): see achieved_algorithmic for that count over the same GEMM time",
+                    "achieved_algorithmic": flops_per_row(c) * c["B"] * K / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
+                    "frac_algorithmic": (flops_per_row(c) * c["B"] * K / (gemm_ms * 1e-3) / 1e12 / pk["tf_sust"])
+                    if gemm_ms > 0 else None,
                     "algorithmic_bytes_per_launch_mean": alg_bytes / alg_launches,
                     "routes": eng.step_routes(),
                     "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json); kind::tf32 issues at half the "
@@ -446,8 +452,8 @@ class Bench(object):
                             "separate optimiser pass", "rank": 0,
                     "gemms": gemm_table,
                     "gemms_note": "k = 250 GEMMs (N or K = 250) and the two Adam-fused weight-gradient GEMMs are HBM-bound "
-                                  "(output / optimiser traffic), see profiles/r02_ncu_full_tc_gemm_cfg5.txt: 65-89 % of the "
-                                  "copy peak; the others run the tensor pipe at 77-92 %",
+                                  "(output / optimiser traffic), see profiles/r02b_ncu_full_step_pair_cfg5.txt: 61-94 % of the "
+                                  "copy peak; the others run the tensor pipe at 76-89 %",
                     "gemm_launches_per_step": gemm_launches / K, "gemm_share_of_step": gemm_ms / max(ms, 1e-9),
                     "step_algorithmic_tflops_per_gpu": flops_per_row(c) * c["B"] * K / (ms * 1e-3) / 1e12,
                     "step_algorithmic_note": "SURVEY 8(d) dense count I*(8k+30E) per row, i.e. the reference graph's "
@@ -653,7 +659,7 @@ def real_config_records(epochs=4):
                     "ms_per_step_pair": dt / (epochs * -(-model.num_users // bp["batch_size"])) * 1e3,
                     "config": {"workload": "%s: committed %s split %dx%d, best_params (k=%d, B=%d)" %
                                (run, d, train.shape[0], train.shape[1], bp["num_factors"], bp["batch_size"]),
-                               "note": "launch-bound: ~34 kernel launches per D+G step pair"}})
+                               "note": "launch-bound: a D+G step pair is ~40 kernel launches of a few microseconds each"}})
     return out
 
 
