@@ -77,15 +77,19 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
             if dist is not None:
                 import torch
                 device = torch.cuda.current_device()
-        train_rows = self._URM_users_items.T.tocsr() if self.mode == 'item' else self._URM_users_items
-        n_rows, width = train_rows.shape
+        # item mode trains on the transposed matrix (GANMF.py:32-33); it is transposed on the device (set_csr_transposed)
+        urm = self._URM_users_items
+        n_rows, width = urm.shape[::-1] if self.mode == 'item' else urm.shape
         if world > 1 and self.KIND == L.KIND_GANMF:
             from ..parallel import ItemShardedTrainer, item_slices
             lo, hi = item_slices(width, world)[rank]
             eng = Engine(self.KIND, n_rows, hi - lo, max_batch=int(batch_size), item_mode=(self.mode == 'item'),
                          device=device, gemm_path=gemm_path, global_width=width, item_offset=lo, tp_rank=rank,
                          tp_world=world, **self._engine_kwargs())
-            eng.set_csr(L.CSR_TRAIN, train_rows[:, lo:hi].tocsr())
+            if self.mode == 'item':                 # columns [lo, hi) of URM^T = (rows [lo, hi) of URM)^T
+                eng.set_csr_transposed(L.CSR_TRAIN, urm[lo:hi])
+            else:
+                eng.set_csr(L.CSR_TRAIN, urm[:, lo:hi].tocsr())
             eng.init_params(self.seed)           # every rank draws ITS slice of the same whole tensors
             self._engine = eng
             self._trainer = ItemShardedTrainer(eng)
@@ -93,8 +97,11 @@ class GanRecommenderBase(BaseRecommender, Incremental_Training_Early_Stopping):
         else:
             eng = Engine(self.KIND, n_rows, width, max_batch=int(batch_size), item_mode=(self.mode == 'item'),
                          device=device, gemm_path=gemm_path, **self._engine_kwargs())
-            eng.set_csr(L.CSR_TRAIN, train_rows)
-            eng.set_csr(L.CSR_SEEN, self._URM_users_items, with_data=False)
+            if self.mode == 'item':
+                eng.set_csr_transposed(L.CSR_TRAIN, urm)
+            else:
+                eng.set_csr(L.CSR_TRAIN, urm)
+            eng.set_csr(L.CSR_SEEN, urm, with_data=False)
             eng.init_params(self.seed)
             self._engine = eng
         names = [(n, g) for n, _, _, g in eng.param_infos()]

@@ -42,6 +42,8 @@ SIGNATURES = {
     "ganmf_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "ganmf_synchronize": (C.c_int, [_ctx]),
     "ganmf_set_csr": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f32p]),
+    "ganmf_get_csr": (C.c_int, [_ctx, C.c_int, _i32p, _i32p, _i64p, _i32p, _i32p, _f32p]),
+    "ganmf_set_csr_transposed": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f32p]),
     "ganmf_set_csr_device": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "ganmf_param_count": (C.c_int, [_ctx]),
     "ganmf_param_info": (C.c_int, [_ctx, C.c_int, C.c_char_p, C.c_int, _i32p, _i32p, _i32p]),

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "csr_kernels.cuh"
 #include "eval_kernels.cuh"
 #include "kernels.cuh"
 #include "score_select.cuh"
@@ -160,6 +161,11 @@ struct ganmf_ctx {
   // (GANMF_LOWRANK).
   int lowrank_mode = -1;
   bool lowrank = false;
+  // ... and the encoder weight gradient of an item-sharded rank: dWe = X2^T.dH2 = R^T.dH_r + V.(Pb^T.dH_f) halves the
+  // K of that GEMM (K = 2B -> B + k).  Worth it where the GEMM is tensor-bound, i.e. where the minibatch is long and
+  // the optimiser traffic (then a separate pass over this rank's slice) is small: tp_world >= 4.  GANMF_LOWRANK_DWE=0/1.
+  int lowrank_dwe_mode = -1;
+  bool lowrank_dwe = false;
   Mat M1, T1t;                // V^T . We  [k, E];  Pb^T . dHf  [k, E]
   // decoder-bias gradient from the residual GEMM's per-32-row column sums (Epilogue::colpart)
   float* colpart = nullptr; int colpart_rows = 0;
@@ -266,7 +272,7 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   // same unit (a 128 x BN x 32 tf32 k-block at ~600 TFLOP/s vs ~5 TB/s of workspace traffic).
   int splits = 1;
   if (tiles < 148 && total_kb >= 16) {
-    const size_t per = (size_t)M * rup(N, 4);
+    const size_t per = (size_t)M * rup(N, 32);
     const int smax = std::min(std::min(total_kb / 8, 64), (int)std::min<size_t>(c->ws_floats / per, 64));
     const double kb_us = 2.0 * g.mt * TC_BM * g.bn * TC_BK / (600e6 / 148.0);   // us per k-block per tile on one SM
     double best = 1e30;
@@ -350,6 +356,7 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   if (const char* sr = getenv("GANMF_SPARSE_REAL")) c->sparse_mode = atoi(sr);          // A/B switch / tests
   if (const char* cp = getenv("GANMF_COLPART")) c->colpart_on = !(cp[0] == '0');        // A/B switch / tests
   if (const char* lr = getenv("GANMF_LOWRANK")) c->lowrank_mode = atoi(lr);             // A/B switch / tests
+  if (const char* ld = getenv("GANMF_LOWRANK_DWE")) c->lowrank_dwe_mode = atoi(ld);     // A/B switch / tests
   if (const char* ax = getenv("GANMF_AUX_STREAM")) c->aux_on = !(ax[0] == '0');         // A/B switch / tests
   c->B = cfg->max_batch; c->W = cfg->width; c->Wp = rup(cfg->width, 32);
   c->k = cfg->num_factors; c->kp = rup(c->k, 32);
@@ -440,6 +447,7 @@ static int create_buffers(ganmf_ctx* c) {
     c->colpart_rows = (2 * B + 31) / 32;
     RC(dalloc(&c->colpart, (size_t)c->colpart_rows * c->Wp));
     c->lowrank = c->lowrank_mode == 1 || (c->lowrank_mode < 0 && 2 * c->k <= B);
+    c->lowrank_dwe = c->tp_world > 1 && (c->lowrank_dwe_mode == 1 || (c->lowrank_dwe_mode < 0 && c->lowrank && c->tp_world >= 4));
     RC(mat_alloc(&c->M1, c->k, c->E));
     RC(mat_alloc(&c->T1t, c->k, c->E));
   } else if (cfg->kind == GANMF_KIND_DISGANMF) {
@@ -644,6 +652,114 @@ static int aux_join(ganmf_ctx* c) {
   CU(cudaEventRecord(c->ev_join, c->st_aux));
   CU(cudaStreamWaitEvent(c->st, c->ev_join, 0));
   c->aux_pending = false;
+  return 0;
+}
+
+int ganmf_get_csr(ganmf_ctx* c, int which, int32_t* n_rows, int32_t* n_cols, int64_t* nnz, int32_t* indptr,
+                  int32_t* indices, float* data) {
+  if (!c || which < 0 || which > 2) return fail("bad argument");
+  const Csr& m = c->csr[which];
+  if (!m.indptr) return fail("CSR %d not set", which);
+  if (n_rows) *n_rows = m.n_rows;
+  if (n_cols) *n_cols = m.n_cols;
+  if (nnz) *nnz = m.nnz;
+  CU(cudaStreamSynchronize(c->st));
+  if (indptr) CU(cudaMemcpy(indptr, m.indptr, ((size_t)m.n_rows + 1) * 4, cudaMemcpyDeviceToHost));
+  if (indices && m.nnz) CU(cudaMemcpy(indices, m.indices, (size_t)m.nnz * 4, cudaMemcpyDeviceToHost));
+  if (data && m.nnz) {
+    if (!m.data) return fail("CSR %d holds no values (implicit ones)", which);
+    CU(cudaMemcpy(data, m.data, (size_t)m.nnz * 4, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+// CSR `which` := transpose of the given host CSR [n_rows x n_cols], built on the device (csr_kernels.cuh).
+int ganmf_set_csr_transposed(ganmf_ctx* c, int which, int n_rows, int n_cols, const int32_t* indptr,
+                             const int32_t* indices, const float* data) {
+  if (!c || which < 0 || which > 2 || !indptr || n_rows < 0 || n_cols < 0) return fail("bad argument");
+  if (which == GANMF_CSR_TRAIN && (n_cols != c->cfg.n_rows || n_rows != c->W))
+    return fail("transposed train CSR is %dx%d, context expects %dx%d", n_cols, n_rows, c->cfg.n_rows, c->W);
+  const long long nnz = indptr[n_rows];
+  if (nnz < 0 || (nnz > 0 && !indices)) return fail("bad argument");
+  for (long long i = 0; i < nnz; ++i)
+    if (indices[i] < 0 || indices[i] >= n_cols) return fail("column index %d at position %lld outside [0, %d)", indices[i], i, n_cols);
+  int *s_ip = nullptr, *s_ix = nullptr, *cursor = nullptr;
+  float* s_dat = nullptr;
+  Csr t;
+  t.n_rows = n_cols; t.n_cols = n_rows; t.nnz = nnz;
+  auto cleanup = [&]() { cudaFree(s_ip); cudaFree(s_ix); cudaFree(s_dat); cudaFree(cursor); };
+  auto bail = [&](int rc) { cleanup(); csr_free(t); return rc; };
+#define TRY(x) do { int r__ = (x); if (r__) return bail(r__); } while (0)
+#define TRYCU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return bail(fail("%s -> %s", #x, cudaGetErrorString(e__))); } while (0)
+  TRY(dalloc(&s_ip, (size_t)n_rows + 1));
+  TRY(dalloc(&s_ix, (size_t)nnz));
+  TRY(dalloc(&cursor, (size_t)n_cols + 1));
+  TRY(dalloc(&t.indptr, (size_t)n_cols + 1));
+  TRY(dalloc(&t.indices, (size_t)nnz));
+  TRYCU(cudaMemcpyAsync(s_ip, indptr, ((size_t)n_rows + 1) * 4, cudaMemcpyHostToDevice, c->st));
+  if (nnz) TRYCU(cudaMemcpyAsync(s_ix, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->st));
+  if (data) {
+    TRY(dalloc(&s_dat, (size_t)nnz));
+    TRY(dalloc(&t.data, (size_t)nnz));
+    if (nnz) TRYCU(cudaMemcpyAsync(s_dat, data, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->st));
+  }
+  if (nnz) {
+    csr_col_count_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, c->st>>>(s_ix, nnz, cursor);
+    TRYCU(cudaGetLastError());
+  }
+  exclusive_scan_kernel<<<1, 1024, 0, c->st>>>(cursor, n_cols, t.indptr);
+  TRYCU(cudaGetLastError());
+  TRYCU(cudaMemsetAsync(cursor, 0, ((size_t)n_cols + 1) * 4, c->st));
+  if (nnz && n_rows) {
+    csr_scatter_kernel<<<(unsigned)(((long long)n_rows * 32 + 255) / 256), 256, 0, c->st>>>(s_ip, s_ix, s_dat, n_rows, t.indptr,
+                                                                                          cursor, t.indices, t.data);
+    TRYCU(cudaGetLastError());
+    csr_sort_segments_kernel<<<n_cols, TR_THREADS, 0, c->st>>>(t.indptr, t.indices, t.data);
+    TRYCU(cudaGetLastError());
+  }
+  c->launches += 4;
+  // columns with more than TR_CAP entries (popular items): found on the host from the new indptr, sorted in a
+  // padded global scratch, one CTA each
+  std::vector<int> tip((size_t)n_cols + 1);
+  TRYCU(cudaMemcpyAsync(tip.data(), t.indptr, ((size_t)n_cols + 1) * 4, cudaMemcpyDeviceToHost, c->st));
+  TRYCU(cudaStreamSynchronize(c->st));
+  std::vector<int> longs;
+  int max_len = 0;
+  for (int j = 0; j < n_cols; ++j) {
+    const int len = tip[j + 1] - tip[j];
+    if (len > TR_CAP) { longs.push_back(j); max_len = std::max(max_len, len); }
+  }
+  if (!longs.empty()) {
+    int cap2 = 2;
+    while (cap2 < max_len) cap2 <<= 1;
+    int *seg = nullptr, *sk = nullptr;
+    float* sv = nullptr;
+    auto bail2 = [&](int rc) { cudaFree(seg); cudaFree(sk); cudaFree(sv); return bail(rc); };
+    // (scratch for a bounded number of long columns at a time: a CTA each)
+    const size_t per_launch = std::max<size_t>(1, ((size_t)256 << 20) / ((size_t)cap2 * 8));
+    int r1 = dalloc(&seg, longs.size());
+    if (!r1) r1 = dalloc(&sk, std::min(per_launch, longs.size()) * cap2);
+    if (!r1 && t.data) r1 = dalloc(&sv, std::min(per_launch, longs.size()) * cap2);
+    if (r1) return bail2(r1);
+    cudaError_t e = cudaMemcpyAsync(seg, longs.data(), longs.size() * 4, cudaMemcpyHostToDevice, c->st);
+    for (size_t o = 0; e == cudaSuccess && o < longs.size(); o += per_launch) {
+      const unsigned nb = (unsigned)std::min(per_launch, longs.size() - o);
+      csr_sort_long_segments_kernel<<<nb, TR_THREADS, 0, c->st>>>(seg + o, t.indptr, t.indices, t.data, sk, sv, cap2);
+      e = cudaGetLastError();
+      c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+    cudaFree(seg); cudaFree(sk); cudaFree(sv);
+    if (e != cudaSuccess) return bail(fail("long-segment sort -> %s", cudaGetErrorString(e)));
+  }
+#undef TRY
+#undef TRYCU
+  cleanup();
+  Csr& m = c->csr[which];
+  csr_free(m);
+  m = t;
+  if (which == GANMF_CSR_TEST) c->have_tables = false;
+  if (which == GANMF_CSR_TRAIN) note_train_csr(c);
   return 0;
 }
 
@@ -1420,10 +1536,33 @@ int ganmf_tp_d_phase(ganmf_ctx* c, int phase, int ids_offset, int B, float lr, f
     case 5: {                                                                      // summed dH2 | dbe -> dWe, biases
       const float alpha = c->tp_d_alpha;
       CU(cudaMemcpyAsync(be->g, c->dH2.row(2 * B), (size_t)be->w.ld * 4, cudaMemcpyDeviceToDevice, c->st));
+      if (c->lowrank_dwe) {
+        // dWe[slice] = R^T.dH_r + V[slice].(Pb^T.dH_f): K = B + k instead of 2B; plain gradient + one Adam pass
+        const Param& V = c->params[c->n_d + 1];
+        Epilogue et;                                                               // T = Pb^T . dH_f  [k, E]
+        et.out = c->T1t.p; et.ldo = c->T1t.ld;
+        RC(gemm(c, c->Pb.p, c->Pb.ld, 1, c->dH2.row(B), c->dH2.ld, 1, c->k, c->E, B, et));
+        Epilogue ea;                                                               // R^T . dH_r
+        ea.out = We->g; ea.ldo = We->w.ld;
+        RC(gemm(c, c->X2.p, c->X2.ld, 1, c->dH2.p, c->dH2.ld, 1, c->W, c->E, B, ea));
+        Epilogue eb;                                                               // + V . T
+        eb.out = We->g; eb.ldo = We->w.ld;
+        eb.c1 = We->g; eb.ldc1 = We->w.ld; eb.beta1 = 1.f;
+        RC(gemm(c, V.w.p, V.w.ld, 0, c->T1t.p, c->T1t.ld, 1, c->W, c->E, c->k, eb));
+        AdamArgs aw;
+        memset(&aw, 0, sizeof aw);
+        aw.nseg = 1;
+        aw.seg[0].theta = We->w.p; aw.seg[0].m = We->m; aw.seg[0].v = We->v; aw.seg[0].g = We->g;
+        aw.seg[0].ld = We->w.ld; aw.seg[0].n4 = We->w.elems() / 4;
+        aw.alpha = alpha; aw.reg = reg; aw.l2_out = &c->sc->l2;
+        CU(fused_adam(aw, c->st));
+        c->launches++;
+      } else {
       Epilogue e6;                                                                 // G6: dWe[slice, :] -> Adam
       e6.out = We->w.p; e6.ldo = We->w.ld;
       e6.adam_m = We->m; e6.adam_v = We->v; e6.adam_alpha = alpha; e6.adam_reg = reg; e6.adam_l2 = &c->sc->l2;
       RC(gemm(c, c->X2.p, c->X2.ld, 1, c->dH2.p, c->dH2.ld, 1, c->W, c->E, 2 * B, e6));
+      }
       // biases: bd is a slice, be is replicated (every rank applies the same update; its l2 counts once)
       Param* bs[2] = {be, bd};
       for (int i = 0; i < 2; ++i) {

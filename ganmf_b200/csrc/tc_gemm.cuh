@@ -422,12 +422,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (u < 0) break;
       const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN, BM);
       const uint32_t acc = ui % ACC;
-      // A ragged last column tile still takes the vector path when the layout convention (ld = roundup(cols, 32),
-      // zero padding) covers the tile: the accumulator columns >= N are exactly zero (TMA zero-fills the operand
-      // beyond its true extent), so are the padding columns of addends and biases, and zeros land in padding that is
-      // zero anyway (N = k = 250 -> 256: the item-factor gradient GEMMs, whose every tile is ragged).
-      const bool n_pad_ok = !partial && ep.ldo == ((args.N + 31) & ~31) && un.n0 + BN <= ep.ldo &&
-                            (!ep.c1 || un.n0 + BN <= ep.ldc1) && ep.act != ACT_SIGMOID;
+      // A ragged last column tile still takes the vector path under the layout convention (ld = roundup(cols, 32),
+      // zero padding): chunks are 32 columns wide and start at multiples of 32, so every chunk that starts below N
+      // lies inside the padded row (chunks at or beyond N are skipped below); the accumulator columns >= N are
+      // exactly zero (TMA zero-fills the operand beyond its true extent), so are the padding columns of addends and
+      // biases, and zeros land in padding that is zero anyway.  Without this every GEMM whose N is not a multiple of
+      // 256 (I = 200 000 or 25 000 per rank, k = 250) finishes on a column of tiles in the scalar path, ~10x slower.
+      // Split-K partials: the workspace rows are padded to 32 floats for the same reason (ws_ld).
+      const bool n_pad_ok = partial ? (args.ws_ld & 31) == 0
+                                    : (ep.ldo == ((args.N + 31) & ~31) && (!ep.c1 || ep.ldc1 >= ep.ldo) &&
+                                       ep.act != ACT_SIGMOID);
       const bool interior = vec_all && (un.m0 + row_off + MT * TC_BM <= args.M) && (un.n0 + BN <= args.N || n_pad_ok);
       // this warp's chunks of the unit: 32 rows x 32 columns each, NCH = MT * BN / 64 of them
       constexpr int CH = BN / 64, NCH = MT * CH;
@@ -438,14 +442,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // consumed -- so the HBM latency (ncu: 30 % of the epilogue warps' time when paid per chunk) hides
       // under the TMEM read, the transpose and the stores of the chunk in between.
       const bool pf = interior && use_c1 && !(ep.adam_m && !LEAN);
+      auto chunk_live = [&](int j) { return un.n0 + chunk_c(j) < args.N; };   // (a ragged tile skips its last chunks)
+      int t1_for = -1;                              // chunk whose addend rows sit in t1
       float4 t1[8];
       auto load_c1 = [&](int j, int itr) {
         const float* p1 = ep.c1 + (size_t)(chunk_mw(j) + sub_r + itr * 4) * ep.ldc1 + un.n0 + chunk_c(j) + sub_g * 4;
         t1[itr] = __ldg(reinterpret_cast<const float4*>(p1));
       };
-      if (pf) {
+      if (pf && chunk_live(0)) {
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr) load_c1(0, itr);
+        t1_for = 0;
       }
       ptx::mbar_wait(&tmem_full_bar[acc], (ui / ACC) & 1);
       ptx::tc_fence_after();
@@ -533,8 +540,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               __syncwarp();
               continue;
             }
-            const bool more = j + 1 < NCH;
+            const bool more = j + 1 < NCH && chunk_live(j + 1);
             float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (use_c1 && t1_for != j) {               // (not prefetched: the chunk before it was skipped)
+#pragma unroll
+              for (int itr = 0; itr < 8; ++itr) load_c1(j, itr);
+            }
+            if (use_c1) t1_for = more ? j + 1 : -1;
 #pragma unroll
             for (int itr = 0; itr < 8; ++itr) {
               const int row = itr * 4 + sub_r;
@@ -751,7 +763,7 @@ struct TcGemmCall {
   int M, N, K;
   Epilogue ep;
   int splits = 1;          // > 1 needs ws
-  float* ws = nullptr;     // >= splits * M * roundup(N,4) floats
+  float* ws = nullptr;     // >= splits * M * roundup(N,32) floats
   int bn = 128;            // 128 or 256
   int mt = 1;              // 1: 128-row CTA tiles; 2: 256-row CTA tiles (needs bn == 256)
   int cg = 1;              // 2: CTA pairs (cta_group::2) on 256 x 256 tiles (needs bn == 256, mt == 1)
@@ -883,7 +895,7 @@ inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   args.splits = splits;
   args.dbg_epi = c.dbg_epi;
   args.ws = c.ws;
-  args.ws_ld = (c.N + 3) & ~3;
+  args.ws_ld = (c.N + 31) & ~31;       // rows padded like every matrix: ragged tiles store whole 32-column chunks
   // shared-memory matrix descriptors (bytes >> 4):
   //  K-major : SWIZZLE_128B; rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (=1).
   //  MN-major: SWIZZLE_128B_BASE32B (TMA 128B_ATOM_32B); each TMA box is 32 k-rows of 128 B

@@ -109,6 +109,33 @@ class Engine(object):
         L.check(self.lib.ganmf_set_csr(self.ctx, which, m.shape[0], m.shape[1], ip, ix, dp))
         return m
 
+    def set_csr_transposed(self, which, m, with_data=True):
+        """CSR `which` := m.T, transposed on the device (item mode: GANMF.py:32-33 does `URM_train.T.tocsr()` on the
+        host).  Returns the canonical host matrix that was uploaded (NOT transposed)."""
+        m = sps.csr_matrix(m)
+        if not m.has_canonical_format:
+            m = m.copy()
+            m.sum_duplicates()
+        _, ip = L.i32(m.indptr)
+        idx, ix = L.i32(m.indices)
+        if with_data:
+            dat, dp = L.f32(m.data)
+        else:
+            dp = None
+        L.check(self.lib.ganmf_set_csr_transposed(self.ctx, which, m.shape[0], m.shape[1], ip, ix, dp))
+        return m
+
+    def get_csr(self, which, with_data=True):
+        """The resident CSR `which` as a scipy matrix (values = ones when it was set without data)."""
+        nr, nc, nnz = C.c_int32(), C.c_int32(), C.c_int64()
+        L.check(self.lib.ganmf_get_csr(self.ctx, which, C.byref(nr), C.byref(nc), C.byref(nnz), None, None, None))
+        ip = np.empty(nr.value + 1, dtype=np.int32)
+        ix = np.empty(nnz.value, dtype=np.int32)
+        dat = np.ones(nnz.value, dtype=np.float32)
+        L.check(self.lib.ganmf_get_csr(self.ctx, which, None, None, None, ip.ctypes.data_as(L._i32p),
+                                       ix.ctypes.data_as(L._i32p), dat.ctypes.data_as(L._f32p) if with_data else None))
+        return sps.csr_matrix((dat, ix, ip), shape=(nr.value, nc.value))
+
     def set_csr_device(self, which, n_rows, n_cols, indptr, indices, data=None):
         """CSR already on the device (torch int32 / float32 tensors or anything with data_ptr()); indices of a row
         sorted and unique.  Copied device-to-device; the caller may free its arrays afterwards."""

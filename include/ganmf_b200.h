@@ -87,6 +87,17 @@ int ganmf_set_csr(ganmf_ctx* ctx, int which, int n_rows, int n_cols, const int32
 /* The same from DEVICE arrays (copied device-to-device; nnz = indptr[n_rows]).  ~ sps.load_npz + upload of
  * experiments/datasets/*.npz without a host detour when the matrix is built or transposed on the GPU
  * (GANMF.py:32-33 transposes on the host). */
+/* CSR `which` := the TRANSPOSE of the host CSR [n_rows x n_cols] given here, transposed on the device (count, scan,
+ * scatter, per-column sort: the result is canonical, bit-identical to scipy's).  ~ `URM_train.T.tocsr()` of item mode
+ * (GANRec/GANMF.py:32-33): the users x items matrix is uploaded as it is and the items x users training matrix is built on
+ * the GPU.  For GANMF_CSR_TRAIN the context expects n_cols x n_rows = config.n_rows x config.width. */
+int ganmf_set_csr_transposed(ganmf_ctx* ctx, int which, int n_rows, int n_cols, const int32_t* indptr_host,
+                             const int32_t* indices_host, const float* data_host);
+/* Read a resident CSR back (sizes first with NULL arrays, then the arrays): the matrix `get_URM_train()` returns
+ * (Base/BaseRecommender.py:51-52) as the device holds it, e.g. after ganmf_set_csr_transposed.  data_host must be NULL
+ * for a CSR that was set without values. */
+int ganmf_get_csr(ganmf_ctx* ctx, int which, int32_t* n_rows, int32_t* n_cols, int64_t* nnz, int32_t* indptr_host,
+                  int32_t* indices_host, float* data_host);
 int ganmf_set_csr_device(ganmf_ctx* ctx, int which, int n_rows, int n_cols, const int32_t* indptr_dev,
                          const int32_t* indices_dev, const float* data_dev, int64_t nnz);
 

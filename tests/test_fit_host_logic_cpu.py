@@ -28,6 +28,9 @@ class StandInEngine(object):
     def set_csr(self, which, m, with_data=True):
         self.csr[which] = sps.csr_matrix(m).shape
 
+    def set_csr_transposed(self, which, m, with_data=True):      # the device holds m.T
+        self.csr[which] = sps.csr_matrix(m).shape[::-1]
+
     def init_params(self, seed):
         self.seed = seed
 

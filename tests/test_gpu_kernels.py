@@ -174,3 +174,60 @@ def test_topk_bit_exact_vs_oracle(eng, n_items, K):
     assert np.array_equal(gi[:, :kk], wi)
     assert np.array_equal(gv[:, :kk], wv)
     assert np.all(gi[:, kk:] == -1)
+
+
+def test_csr_transposed_on_device_is_canonical_and_equals_scipy():
+    """ganmf_set_csr_transposed (GANMF.py:32-33 `URM_train.T.tocsr()` on the GPU): indptr, indices (ascending inside every
+    row of the transpose) and values bit-identical to scipy's canonical transpose -- empty columns, explicit ratings,
+    implicit ones, a column longer than the shared-memory sort (6000 > 4096 entries) and one past the next power of two."""
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    rs = np.random.RandomState(3)
+    for n_rows, n_cols, dens, with_data in [(300, 517, 0.05, True), (9000, 40, 0.02, False), (64, 1, 0.5, True)]:
+        m = sps.random(n_rows, n_cols, dens, format="csr", dtype=np.float32, random_state=rs)
+        m.data[:] = rs.randint(1, 6, size=m.nnz)
+        m = m.tolil()
+        if n_rows == 9000:
+            m[rs.permutation(n_rows)[:6000], 7] = 3.0           # popular item: global-memory sort path
+            m[rs.permutation(n_rows)[:4097], 9] = 2.0
+            m[:, 11] = 0.0                                      # empty column
+        m = sps.csr_matrix(m)
+        m.eliminate_zeros()
+        m.sort_indices()
+        e = Engine(L.KIND_GANMF, n_cols, n_rows, 4, emb_dim=4, max_batch=8)
+        e.set_csr_transposed(L.CSR_TRAIN, m, with_data=with_data)
+        got = e.get_csr(L.CSR_TRAIN, with_data=with_data)
+        want = m.T.tocsr()
+        want.sort_indices()
+        assert got.shape == want.shape
+        assert np.array_equal(got.indptr, want.indptr)
+        assert np.array_equal(got.indices, want.indices)
+        if with_data:
+            assert np.array_equal(got.data, want.data)
+        e.close()
+
+
+def test_csr_encode_rows_matches_float64():
+    """csr_encode_rows_kernel alone: be + sum of the weight rows of the interactions, against float64."""
+    from ganmf_b200 import _lib as L
+    from ganmf_b200.engine import Engine
+    rs = np.random.RandomState(5)
+    for n_rows, width, E, B in [(200, 3000, 100, 64), (50, 700, 1024, 17), (30, 90, 8, 30)]:
+        urm = sps.random(n_rows, width, 0.03, format="csr", dtype=np.float32, random_state=rs)
+        urm.data[:] = rs.randint(1, 6, size=urm.nnz)
+        e = Engine(L.KIND_GANMF, n_rows, width, 4, emb_dim=E, max_batch=B)
+        e.set_csr(L.CSR_TRAIN, urm)
+        e.init_params(9)
+        p = e.get_params()
+        be = (rs.standard_normal(E) * 0.1).astype(np.float32)
+        e.set_params({"autoencoder/encoding/bias": be})
+        ids = rs.permutation(n_rows)[:B].astype(np.int32)
+        e.upload_ids(ids)
+        ldo = rup(E)
+        out = torch.full((B, ldo), 7.0, dtype=torch.float32, device="cuda")
+        L.check(e.lib.ganmf_k_csr_encode_rows(e.ctx, 0, B, out.data_ptr(), ldo))
+        got = out.cpu().numpy()
+        want = urm[ids].astype(np.float64) @ p["autoencoder/encoding/kernel"].astype(np.float64) + be
+        assert np.max(np.abs(got[:, :E] - want)) <= 1e-5 * max(1.0, np.abs(want).max())
+        assert np.all(got[:, E:] == 0)
+        e.close()

@@ -40,11 +40,13 @@ def make_engines(urm, k, E, B, world, gemm_path=None):
 
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("hp", [HP, dict(HP, m=0.05, g_reg=1e-3, alpha=0.3)])     # gate open / closed, dense P update
-@pytest.mark.parametrize("routes", ["00", "10", "01", "11"])   # sparse real codes x low-rank generator route
+# sparse real codes x low-rank generator route x low-rank encoder weight gradient (ranks of >= 4-GPU groups)
+@pytest.mark.parametrize("routes", ["000", "100", "010", "110", "011", "111"])
 def test_item_sharded_steps_parity(monkeypatch, world, hp, routes):
     from ganmf_b200 import _lib as L
     monkeypatch.setenv("GANMF_SPARSE_REAL", routes[0])
     monkeypatch.setenv("GANMF_LOWRANK", routes[1])
+    monkeypatch.setenv("GANMF_LOWRANK_DWE", routes[2])
     from ganmf_b200.parallel import ItemShardedTrainer
     n_rows, width, k, E, B, epochs = 300, 517, 24, 40, 64, 10
     urm = make_urm(n_rows, width, 0.05, 0)

@@ -106,7 +106,11 @@ class NumpyTPEngine(object):
             l2 = (self.p[WE] ** 2).sum() + (self.p[WD] ** 2).sum() + (self.p[BD] ** 2).sum()
             if self.rank == 0:
                 l2 += (self.p[BE] ** 2).sum()
-            grads = {WD: self.dWd + reg * self.p[WD], WE: self.X2.T @ dh[:2 * B] + reg * self.p[WE],
+            if self.lowrank:               # dWe = R^T.dH_r + V.(Pb^T.dH_f)  (ganmf_ctx::lowrank_dwe)
+                dwe = self.R.T @ dh[:B] + self.p[V_] @ (self.Pb.T @ dh[B:2 * B])
+            else:
+                dwe = self.X2.T @ dh[:2 * B]
+            grads = {WD: self.dWd + reg * self.p[WD], WE: dwe + reg * self.p[WE],
                      BE: dh[2 * B] + reg * self.p[BE], BD: self.dbd + reg * self.p[BD]}
             self.opt_d.apply(self.p, grads)
             self.losses[slot] = (self.loss_main if self.rank == 0 else 0.0) + reg * 0.5 * l2

@@ -81,7 +81,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dRs, hRs, 8, cudaMemcpyHostToDevice));
   CK(cudaMemset(dSq, 0, 16));
   CK(cudaMemset(dO, 0xff, (size_t)M * ldo * 4));
-  if (splits > 1) CK(cudaMalloc(&dWs, (size_t)splits * M * rup(N, 4) * 4));
+  if (splits > 1) CK(cudaMalloc(&dWs, (size_t)splits * M * rup(N, 32) * 4));
 
   ganmf::TcGemmCall c;
   c.A = dA; c.lda = lda; c.a_mn = a_mn;
