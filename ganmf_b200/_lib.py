@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libganmf_b200.so")
 KIND_GANMF, KIND_DISGANMF, KIND_MF = 0, 1, 2
 ACT = {"linear": 0, None: 0, "tanh": 1, "relu": 2, "sigmoid": 3}
 CSR_TRAIN, CSR_SEEN, CSR_TEST = 0, 1, 2
-GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_TC3 = 0, 1, 2, 3
+GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_TC3, GEMM_RESIDENT_A = 0, 1, 2, 3, 4
 MC_NAMES = ["PRECISION", "RECALL", "PRECISION_RECALL_MIN_DEN", "MAP", "NDCG", "MRR", "ARHR", "ROC_AUC",
             "HIT_RATE", "NOVELTY", "AVERAGE_POPULARITY", "COVERED", "RMSE"]
 MC_NCOL = len(MC_NAMES)

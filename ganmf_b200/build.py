@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libganmf_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["ptx.cuh", "tc_gemm.cuh", "kernels.cuh", "csr_kernels.cuh", "eval_kernels.cuh", "score_select.cuh"]
+HEADERS = ["ptx.cuh", "tc_gemm.cuh", "kernels.cuh", "csr_kernels.cuh", "eval_kernels.cuh", "score_select.cuh",
+           "gen_gemm.cuh"]
 
 
 def _stale():

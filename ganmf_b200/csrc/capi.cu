@@ -14,6 +14,7 @@
 
 #include "csr_kernels.cuh"
 #include "eval_kernels.cuh"
+#include "gen_gemm.cuh"
 #include "kernels.cuh"
 #include "score_select.cuh"
 #include "tc_gemm.cuh"
@@ -150,6 +151,9 @@ struct ganmf_ctx {
   cudaStream_t st_aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool aux_on = true, aux_pending = false;
+  // generator GEMM F = Pb . V^T on the resident-A kernel (gen_gemm.cuh): -1 = when the minibatch fills a pair tile
+  // (B >= 256) and k <= 256, 0 / 1 forced (GANMF_GEN_RESIDENT)
+  int gen_resident_mode = -1;
   // low-rank generator route: the fake profiles F = Pb . V^T have rank k, so every product that contracts F (or a
   // gradient flowing back into it) over the items can go through a [k, E] matrix instead of a [B, I] one:
   //   codes      Hf  = F . We            = Pb . (V^T . We)                        = Pb . M1
@@ -357,6 +361,7 @@ int ganmf_create(const ganmf_config* cfg, ganmf_ctx** out) {
   if (const char* cp = getenv("GANMF_COLPART")) c->colpart_on = !(cp[0] == '0');        // A/B switch / tests
   if (const char* lr = getenv("GANMF_LOWRANK")) c->lowrank_mode = atoi(lr);             // A/B switch / tests
   if (const char* ld = getenv("GANMF_LOWRANK_DWE")) c->lowrank_dwe_mode = atoi(ld);     // A/B switch / tests
+  if (const char* gr = getenv("GANMF_GEN_RESIDENT")) c->gen_resident_mode = atoi(gr);   // A/B switch / tests
   if (const char* ax = getenv("GANMF_AUX_STREAM")) c->aux_on = !(ax[0] == '0');         // A/B switch / tests
   c->B = cfg->max_batch; c->W = cfg->width; c->Wp = rup(cfg->width, 32);
   c->k = cfg->num_factors; c->kp = rup(c->k, 32);
@@ -933,10 +938,42 @@ static int forward_profiles(ganmf_ctx* c, int ids_offset, int B, bool dense_real
   }
   return 0;
 }
+// out[M, N] = A . B^T on the resident-A generator kernel (gen_gemm.cuh); accounted like every tensor-core GEMM
+static int gen_gemm(ganmf_ctx* c, const GenGemmCall& g) {
+  c->launches += 1;
+  cudaEvent_t ev1 = nullptr;
+  if (c->profile) {
+    while (c->ev_pool.size() < c->ev_used + 2) {
+      cudaEvent_t ev;
+      CU(cudaEventCreate(&ev));
+      c->ev_pool.push_back(ev);
+    }
+    cudaEvent_t ev0 = c->ev_pool[c->ev_used++];
+    ev1 = c->ev_pool[c->ev_used++];
+    CU(cudaEventRecord(ev0, c->st));
+  }
+  cudaError_t e = resident_a_gemm(g, c->st);
+  if (e != cudaSuccess) return fail("resident_a_gemm(M=%d N=%d K=%d) -> %s", g.M, g.N, g.K, cudaGetErrorString(e));
+  if (c->profile) {
+    CU(cudaEventRecord(ev1, c->st));
+    c->prof_flops += 2.0 * g.M * g.N * g.K;
+    c->prof_launches += 1;
+    c->prof_shapes.insert(c->prof_shapes.end(), {g.M, g.N, g.K, 1});
+  }
+  return 0;
+}
 // fake profiles F = Pb . V^T -> X2[B:2B]
 static int forward_fake(ganmf_ctx* c, int B) {
   RC(aux_join(c));
   const Param& V = c->params[c->n_d + 1];
+  if (c->gen_resident_mode != 0 && c->cfg.gemm_path != GANMF_GEMM_SIMT && (c->gen_resident_mode == 1 || B >= 256)) {
+    GenGemmCall g;
+    g.A = c->Pb.p; g.lda = c->Pb.ld; g.B = V.w.p; g.ldb = V.w.ld;
+    g.M = B; g.N = c->W; g.K = c->k;
+    g.out = c->X2.row(B); g.ldo = c->X2.ld;
+    g.cache = &c->tmaps; g.max_ctas = c->gemm_sm_cap;
+    if (resident_a_gemm_ok(g)) return gen_gemm(c, g);                                // G1
+  }
   Epilogue ep;
   ep.out = c->X2.row(B); ep.ldo = c->X2.ld;
   return gemm(c, c->Pb.p, c->Pb.ld, 0, V.w.p, V.w.ld, 0, B, c->W, c->k, ep);      // G1
@@ -2592,6 +2629,14 @@ int ganmf_metrics_from_topk(ganmf_ctx* c, const int32_t* topk, int K, const int3
 int ganmf_k_gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, int M, int N,
                  int K, float* out, int ldo, int path) {
   if (!c) return fail("null ctx");
+  if (path == GANMF_GEMM_RESIDENT_A) {
+    GenGemmCall g;
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.out = out; g.ldo = ldo;
+    g.cache = &c->tmaps; g.max_ctas = c->gemm_sm_cap;
+    if (a_mn || b_mn || !resident_a_gemm_ok(g))
+      return fail("resident-A GEMM: K-major operands, K <= 256, ldo >= roundup(N, 32), 16-byte aligned");
+    return gen_gemm(c, g);
+  }
   Epilogue e;
   e.out = out; e.ldo = ldo;
   return gemm(c, A, lda, a_mn, B, ldb, b_mn, M, N, K, e, path);

@@ -35,7 +35,9 @@ enum { GANMF_CSR_TRAIN = 0,   /* rows of the TRAINING orientation (items x users
        GANMF_CSR_TEST = 2 };  /* users x items held-out interactions (evaluator)                  */
 enum { GANMF_GEMM_AUTO = 0, GANMF_GEMM_SIMT = 1, GANMF_GEMM_TC = 2,
        /* tcgen05 on split-TF32 operands (hi.hi + hi.lo + lo.hi): fp32-accurate products at 3x the MMA work */
-       GANMF_GEMM_TC3 = 3 };
+       GANMF_GEMM_TC3 = 3,
+       /* ganmf_k_gemm only: the generator kernel with a resident A tile (both operands K-major, K <= 256) */
+       GANMF_GEMM_RESIDENT_A = 4 };
 
 /* Per-(user, cutoff) metric columns produced by the device evaluator. */
 enum { GANMF_MC_PRECISION = 0, GANMF_MC_RECALL, GANMF_MC_PRMD, GANMF_MC_MAP, GANMF_MC_NDCG,

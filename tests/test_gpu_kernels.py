@@ -231,3 +231,32 @@ def test_csr_encode_rows_matches_float64():
         assert np.max(np.abs(got[:, :E] - want)) <= 1e-5 * max(1.0, np.abs(want).max())
         assert np.all(got[:, E:] == 0)
         e.close()
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 64), (1024, 5000, 250), (300, 700, 250), (129, 40000, 96), (2048, 3000, 256),
+                                   (64, 517, 24)])
+def test_resident_a_generator_gemm_matches_fp64(eng_pair, shape):
+    """gen_gemm.cuh: F = Pb . V^T with the A tile resident in shared memory (K <= 256, both operands K-major): ragged
+    M / N / K tails, fewer rows than a pair tile, several row blocks and column segments per pair, launched twice
+    (barrier phases / TMEM hand-back between launches); padding columns stay zero."""
+    from ganmf_b200 import _lib as L
+    M, N, K = shape
+    rs = np.random.RandomState(M + N + K)
+    A = rs.standard_normal((M, K)).astype(np.float32)
+    B = rs.standard_normal((N, K)).astype(np.float32)
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+
+    def padded(x):
+        out = np.full((x.shape[0], rup(x.shape[1])), 1e30, dtype=np.float32)      # TMA must never read the padding
+        out[:, :x.shape[1]] = x
+        return out
+    As, Bs = padded(A), padded(B)
+    dA, dB = torch.from_numpy(As).cuda(), torch.from_numpy(Bs).cuda()
+    ldo = rup(N)
+    out = torch.zeros((M, ldo), dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        L.check(eng_pair.lib.ganmf_k_gemm(eng_pair.ctx, dA.data_ptr(), As.shape[1], 0, dB.data_ptr(), Bs.shape[1], 0,
+                                          M, N, K, out.data_ptr(), ldo, L.GEMM_RESIDENT_A))
+    got = out.cpu().numpy()[:, :N].astype(np.float64)
+    assert np.max(np.abs(got - want)) / np.sqrt(K) < 2e-3
+    assert np.all(out.cpu().numpy()[:, N:] == 0)

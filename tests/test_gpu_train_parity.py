@@ -132,6 +132,18 @@ def test_ganmf_sparse_route_is_chosen_by_density_and_matches_dense(monkeypatch):
     assert any(not np.array_equal(res["auto"][4][n], res["0"][4][n]) for n in res["0"][4])
 
 
+def test_ganmf_steps_parity_resident_generator_gemm(monkeypatch):
+    """GANMF_GEN_RESIDENT=1: the fake profiles through the resident-A generator kernel (gen_gemm.cuh), which the engine
+    takes by itself from 256 minibatch rows on; 160-row batches = one partly filled pair tile, 44-row last batch."""
+    from ganmf_b200 import _lib as L
+    monkeypatch.setenv("GANMF_GEN_RESIDENT", "1")
+    dl, gl, odl, ogl, got, want = run_ganmf(600, 517, 24, 300, 160, 4, HP, L.GEMM_TC)
+    np.testing.assert_allclose(dl, odl, rtol=REL)
+    np.testing.assert_allclose(gl, ogl, rtol=REL)
+    for n in want:
+        assert rel_err(got[n], want[n]) <= REL, (n, rel_err(got[n], want[n]))
+
+
 def test_ganmf_decoder_bias_grad_from_the_colsum_pass(monkeypatch):
     """GANMF_COLPART=0: dbd from the pass over the residual instead of the residual GEMM's per-32-row column sums
     (the default whenever the real / fake boundary falls on a 32-row group, i.e. in every other test here)."""
