@@ -115,6 +115,14 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       : "memory");
 }
 
+// 3D box global -> L2 only (no shared-memory destination, no barrier): the TMA engine pulls a tile that LSU loads
+// will want a whole mainloop later (the optimiser state under a weight-gradient tile)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05
 // (the *_pair forms are the cta_group::2 instructions: two CTAs of a cluster, i.e. two SMs of one TPC, hold
 //  one 256-row accumulator tile and share the B operand; they are issued by the leader CTA)

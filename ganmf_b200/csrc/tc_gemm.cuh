@@ -119,6 +119,8 @@ struct TcGemmArgs {
   uint32_t a_mtstep;                     // start-address advance per 128-row sub-tile of A, bytes >> 4
   uint32_t idesc;
   unsigned int* sched;     // {next unit, CTAs done}: dynamic unit scheduler state (self-resetting)
+  int pf_planes;           // > 0: map_p describes [planes][M][N] (theta, m, v of the fused optimiser): the producer
+                           // prefetches the unit's tile of every plane into L2 before its operand loads
   Epilogue ep;
 };
 
@@ -218,7 +220,7 @@ __device__ __forceinline__ TcUnit tc_unit(int u, int tiles_m, int tiles_n, int m
 template <int BN, int STAGES, int MT, int CG, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const TcGemmArgs args) {
+               const __grid_constant__ CUtensorMap map_p, const TcGemmArgs args) {
   static_assert(CG == 1 || (CG == 2 && MT == 1), "a CTA pair holds one 128-row sub-tile per CTA");
   using S = TcSmem<BN, STAGES, MT, CG>;
   constexpr bool LEAN = EPI == 1;
@@ -297,6 +299,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const TcUnit un = tc_unit(u, tiles_m, tiles_n, m_fastest, BN, BM);
         const int kb_begin = un.split * args.kb_per_split;
         const int kb_end = min(kb_begin + args.kb_per_split, total_kb);
+        if (!LEAN && args.pf_planes > 0) {
+          // fused optimiser: this CTA's rows of theta / m / v under the unit's tile start their way into L2 now; the
+          // epilogue warps read them a whole mainloop later (their LSU loads then cost an L2 hit, not an HBM round trip)
+#pragma unroll 1
+          for (int pl = 0; pl < args.pf_planes; ++pl)
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt)
+              ptx::tma_prefetch_l2_3d(&map_p, un.n0, un.m0 + row_off + mt * TC_BM, pl);
+        }
         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -757,6 +768,27 @@ inline int make_tmap_2d(CUtensorMap* map, const float* ptr, int rows, int cols, 
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
+// [planes][rows][cols] fp32 (planes plane_bytes apart), box = {box_cols, box_rows, 1}, no swizzle: L2 prefetch only
+inline int make_tmap_planes(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, size_t plane_bytes,
+                            int planes, int box_cols, int box_rows, TmapCache* cache = nullptr) {
+  const TmapKey key{ptr, rows, cols, ld, box_cols, box_rows, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32, -(int)(plane_bytes >> 4) - planes};
+  if (cache) {
+    if (const CUtensorMap* hit = cache->find(key)) { *map = *hit; return 0; }
+  }
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return 1;
+  if ((plane_bytes & 15) || (reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 3)) return 3;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, (cuuint64_t)plane_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS && cache) cache->put(key, *map);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
 struct TcGemmCall {
   const float* A; int lda; int a_mn;
   const float* B; int ldb; int b_mn;
@@ -811,7 +843,7 @@ inline cudaError_t tc_sched_slot(unsigned int** out) {
 
 template <int BN, int STAGES, int MT, int CG, int EPI>
 inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const CUtensorMap& ma,
-                                    const CUtensorMap& mb, int splits, cudaStream_t stream) {
+                                    const CUtensorMap& mb, const CUtensorMap& mp, int splits, cudaStream_t stream) {
   using S = TcSmem<BN, STAGES, MT, CG>;
   static bool configured = false;
   if (!configured) {
@@ -843,7 +875,7 @@ inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, STAGES, MT, CG, EPI>, ma, mb, args);
+    return cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, STAGES, MT, CG, EPI>, ma, mb, mp, args);
   }
   const int grid = units < sms ? units : sms;
   static int static_sched = -1;          // GANMF_STATIC_SCHED=1: A/B switch, units blockIdx.x + i*gridDim.x
@@ -856,7 +888,7 @@ inline cudaError_t tc_gemm_launch_t(const TcGemmCall& c, TcGemmArgs& args, const
     cudaError_t es = tc_sched_slot(&args.sched);
     if (es != cudaSuccess) return es;
   }
-  tc_gemm_kernel<BN, STAGES, MT, CG, EPI><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, args);
+  tc_gemm_kernel<BN, STAGES, MT, CG, EPI><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, mp, args);
   return cudaGetLastError();
 }
 
@@ -918,11 +950,26 @@ inline cudaError_t tc_gemm(const TcGemmCall& c, cudaStream_t stream) {
   args.idesc = make_idesc_tf32(bn, c.a_mn, c.b_mn, cg * TC_BM);
   args.ep = c.ep;
 
+  // fused optimiser: theta, m, v as the planes of ONE 3D tensor map when they sit a constant stride apart (they do:
+  // [theta | m | v] slabs), box = {BN columns, 128 rows, 1 plane}; prefetched into L2 by the producer, unit by unit.
+  // OFF by default: measured at cfg5 it makes both weight-gradient GEMMs 0.24 ms SLOWER (1.56 -> 1.80, 1.50 -> 1.74 ms,
+  // profiles/r02b_ab_adam_prefetch.txt) -- 57 MB of prefetched state in flight push the operand tiles out of L2.
+  // GANMF_ADAM_PREFETCH=1 turns it on (A/B switch).
+  CUtensorMap mp = ma;
+  args.pf_planes = 0;
+  static int adam_pf = -1;
+  if (adam_pf < 0) { const char* ev = getenv("GANMF_ADAM_PREFETCH"); adam_pf = (ev && ev[0] == '1') ? 1 : 0; }
+  if (adam_pf && c.ep.adam_m && c.ep.adam_v && splits == 1 && c.ep.adam_m > c.ep.out &&
+      (c.ep.adam_v - c.ep.adam_m) == (c.ep.adam_m - c.ep.out)) {
+    const size_t plane = (size_t)(c.ep.adam_m - c.ep.out) * 4;
+    if (make_tmap_planes(&mp, c.ep.out, c.M, c.N, c.ep.ldo, plane, 3, bn, TC_BM, c.cache) == 0) args.pf_planes = 3;
+    else mp = ma;
+  }
   cudaError_t e;
   const bool lean = tc_lean_epilogue(c.ep);
 #define TC_LAUNCH(BN_, ST_, MT_, CG_)                                                            \
-  (lean ? tc_gemm_launch_t<BN_, ST_, MT_, CG_, 1>(c, args, ma, mb, splits, stream)               \
-        : tc_gemm_launch_t<BN_, ST_, MT_, CG_, 0>(c, args, ma, mb, splits, stream))
+  (lean ? tc_gemm_launch_t<BN_, ST_, MT_, CG_, 1>(c, args, ma, mb, mp, splits, stream)           \
+        : tc_gemm_launch_t<BN_, ST_, MT_, CG_, 0>(c, args, ma, mb, mp, splits, stream))
   if (cg == 2)                     e = TC_LAUNCH(256, 6, 1, 2);
   else if (bn == 256 && c.mt == 2) e = TC_LAUNCH(256, 3, 2, 1);
   else if (bn == 256)              e = TC_LAUNCH(256, 4, 1, 1);
