@@ -583,16 +583,17 @@ int ganmf_profile_read(ganmf_ctx* c, double* ms, double* flops, int64_t* launche
 }
 
 // ------------------------------------------------------------------------------ data
-// Route of the real rows' codes.  The gather-sum reads 4*E bytes of We per interaction from HBM, the
-// dense product spends 2*E flops per matrix cell: on a B200 (~6.5 TB/s against ~650 TFLOP/s of tf32 MMAs inside the
-// step) the two meet near 0.5 % density; the sparse route is taken below half of that (cfg5: 0.1 %; cfg4 at 0.5 %
-// and the committed MovieLens / LastFM splits stay dense).
+// Route of the real rows' codes.  The gather-sum reads 4*E bytes of We per interaction, the dense
+// product spends 2*E flops per matrix cell: on a B200 (~5.6 TB/s of gathered weight rows against ~600 TFLOP/s of tf32
+// MMAs inside the step) the two meet near 0.5 % density.  Measured on both benchmark shapes: cfg5 (0.1 %) 12.14 ->
+// 11.36 ms per step pair, cfg4 (0.5 %, We = 110 MB: partly L2-resident) 1.750 -> 1.644 ms; the sparse route is taken
+// up to 0.55 % (the committed MovieLens / LastFM splits, 0.3-4.5 % dense with tiny We, stay dense or do not care).
 static void note_train_csr(ganmf_ctx* c) {
   const Csr& m = c->csr[GANMF_CSR_TRAIN];
   const double cells = (double)m.n_rows * (double)m.n_cols;
   const double density = cells > 0 ? (double)m.nnz / cells : 1.0;
   c->sparse_real = c->cfg.kind == GANMF_KIND_GANMF &&
-                   (c->sparse_mode == 1 || (c->sparse_mode < 0 && density <= 0.0025));
+                   (c->sparse_mode == 1 || (c->sparse_mode < 0 && density <= 0.0055));
 }
 
 int ganmf_set_csr(ganmf_ctx* c, int which, int n_rows, int n_cols, const int32_t* indptr,

@@ -262,7 +262,7 @@ int ganmf_metrics_from_topk(ganmf_ctx* ctx, const int32_t* topk_idx_host, int K,
 
 /* Which routes the training step of this context takes (decided when the train CSR is set; GANRec/GANMF.py:62-70,
  * 184-187 is one dense graph): *sparse_real = 1 when the codes of the real rows are the CSR gather-sum instead of
- * the real half of the dense encode GEMM (density <= 0.25 %, or GANMF_SPARSE_REAL=1); *bias_grad_from_gemm = 1 when
+ * the real half of the dense encode GEMM (density <= 0.55 %, or GANMF_SPARSE_REAL=1); *bias_grad_from_gemm = 1 when
  * the decoder-bias gradient is formed from the residual GEMM's per-32-row column sums (GANMF_COLPART != 0);
  * *lowrank_fake = 1 when the products that contract the generated profiles `fake_profile = P[u] . V^T`
  * (GANRec/GANMF.py:82-84) over the items go through the [k, emb_dim] matrix V^T . W_enc (2 * num_factors <=

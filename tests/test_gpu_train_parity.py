@@ -98,7 +98,7 @@ def test_ganmf_steps_parity_on_cta_pairs(monkeypatch, hp, lowrank):
 def test_ganmf_steps_parity_sparse_real_route(monkeypatch, pair, hp, explicit):
     """GANMF_SPARSE_REAL=1 forces the codes of the real rows through the CSR gather-sum
     (csr_encode_rows_kernel, exact fp32) and only the fake rows through the tensor cores -- the route the engine
-    takes by itself below 0.25 % density (cfg5).  Same contract as the dense route; ratings other than 1 exercise
+    takes by itself up to 0.55 % density (cfg4, cfg5).  Same contract as the dense route; ratings other than 1 exercise
     the value column of the CSR; 44-row last batch = ragged fake-half GEMM."""
     from ganmf_b200 import _lib as L
     monkeypatch.setenv("GANMF_SPARSE_REAL", "1")
