@@ -266,6 +266,8 @@ static int gemm(ganmf_ctx* c, const float* A, int lda, int a_mn, const float* B,
   // Small outputs with a long K (the split-K GEMMs) run 256-row CTA tiles: two accumulators share every
   // B stage (1.5x flops per byte from L2; measured +9..11 % at 2048x1024x27000); no accumulator
   // double-buffering is needed there because the epilogue is a small part of a long K loop.
+  // (The same 256 x 256 tiles on CTA pairs -- six 32 KB stages instead of three of 64 KB -- were measured at cfg5:
+  //  the split-K code-gradient GEMMs lose 3-13 %, so split-K stays on single-CTA 256-row tiles.)
   if (tiles < 148 && g.bn == 256 && M >= 256 && N >= 512 && total_kb >= 256) {
     g.mt = 2;
     tiles = ((M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((N + g.bn - 1) / g.bn);
