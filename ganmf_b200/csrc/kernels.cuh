@@ -429,7 +429,18 @@ rowdot_kernel(const float* __restrict__ W, int rows, int cols, int ld, const flo
   const float4* x4 = reinterpret_cast<const float4*>(x);
   float acc = 0.f;
   const int n4 = cols >> 2;
-  for (int i = threadIdx.x; i < n4; i += 256) {
+  int i = threadIdx.x;
+  for (; i + 3 * 256 < n4; i += 4 * 256) {          // four independent 16-byte loads of W in flight per thread
+    float4 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a[u] = w4[i + u * 256]; b[u] = __ldg(x4 + i + u * 256); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc = fmaf(a[u].x, b[u].x, acc); acc = fmaf(a[u].y, b[u].y, acc);
+      acc = fmaf(a[u].z, b[u].z, acc); acc = fmaf(a[u].w, b[u].w, acc);
+    }
+  }
+  for (; i < n4; i += 256) {
     const float4 a = w4[i], b = __ldg(x4 + i);
     acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
   }
