@@ -563,7 +563,13 @@ def run_workload(c, args, torch, dist, world, rank, local_rank, with_cpu):
                        "parallelism": ("tp%d over items: rank r holds I/%d columns of the matrix and the matching slices "
                                        "of We/Wd/bd/V with their Adam state; all-reduce of [2B,E] codes, code gradients and "
                                        "[B,k] user-factor gradients per step (NCCL over NVLink); P replicated" % (world, world))
-                       if world > 1 else "single GPU"},
+                       if world > 1 else "single GPU",
+                       "routes": tr["roofline"]["routes"],
+                       "routes_note": "every step is the reference's full update (all D and G parameters, both Adam "
+                                      "optimisers, both losses); the routes evaluate the same mathematics along cheaper "
+                                      "paths (CSR gather-sum for the 0.1 %-dense real rows, [k,E] matrices for products over "
+                                      "the rank-k fake profiles) and are held to the same oracle parity as the dense chain "
+                                      "(tests/test_gpu_train_parity.py, test_gpu_tp.py, test_gpu_baseline_shapes.py)"},
             "gpu_launches": tr["launches"], "clocks": tr["clocks"], "roofline": tr["roofline"], "loss_last": tr["loss_last"]}
     if args.quick:
         line.update(quick=True, gemm_tflops=tr["gemm_tflops"],
